@@ -1,0 +1,141 @@
+// common.cuh -- engine-wide helpers: error handling, the engine singleton (device, stream, memory pool),
+// stream-ordered device buffers, Morton keys.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "../../include/hbsm_b200.h"
+
+namespace hbsm_b200 {
+
+struct Error : public std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define HB_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            throw ::hbsm_b200::Error(HBSM_E_CUDA, std::string("CUDA error: ") +                \
+                                     cudaGetErrorString(_e) + " at " __FILE__ ":" +            \
+                                     std::to_string(__LINE__));                                \
+    } while (0)
+
+// the reference's own exception text is preserved: "Error in HierarchicalBlockSparseMatrix<Treal>::..."
+[[noreturn]] inline void throw_ref(const char* msg) { throw Error(HBSM_E_RUNTIME, msg); }
+
+struct Engine {
+    int device = -1;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;  // kernels launched by this library
+    bool ready = false;
+    std::string name;
+    int gemm_variant = 0;
+    hbsm_stage_times last{};
+};
+Engine& engine();
+void ensure_engine();
+
+// every kernel launch goes through this so gpu_launches can be reported honestly
+#define HB_LAUNCH(kernel, grid, block, smem, ...)                                              \
+    do {                                                                                       \
+        kernel<<<(grid), (block), (smem), ::hbsm_b200::engine().stream>>>(__VA_ARGS__);        \
+        ::hbsm_b200::engine().launches++;                                                      \
+        HB_CUDA(cudaGetLastError());                                                           \
+    } while (0)
+
+// stream-ordered device buffer (cudaMallocAsync pool with an unbounded release threshold = caching allocator)
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return;
+        ensure_engine();
+        HB_CUDA(cudaMallocAsync((void**)&p, std::max<size_t>(count * sizeof(T), 256), engine().stream));
+    }
+    void release() {
+        if (p) { cudaFreeAsync(p, engine().stream); p = nullptr; }
+        n = 0;
+    }
+    void zero() { if (p && n) HB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), engine().stream)); }
+    void upload(const T* host, size_t count) {
+        if (count) HB_CUDA(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, engine().stream));
+    }
+    void download(T* host, size_t count) const {
+        if (count) HB_CUDA(cudaMemcpyAsync(host, p, count * sizeof(T), cudaMemcpyDeviceToHost, engine().stream));
+    }
+    std::vector<T> to_host() const {
+        std::vector<T> v(n);
+        download(v.data(), n);
+        HB_CUDA(cudaStreamSynchronize(engine().stream));
+        return v;
+    }
+};
+
+inline void sync_stream() { HB_CUDA(cudaStreamSynchronize(engine().stream)); }
+
+// ---- Morton keys: digit = 2*colbit + rowbit (H:52-56), most significant level first ----
+__host__ __device__ inline uint64_t spread_bits(uint32_t x) {
+    uint64_t v = x;
+    v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+    v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+}
+__host__ __device__ inline uint32_t compact_bits(uint64_t v) {
+    v &= 0x5555555555555555ull;
+    v = (v | (v >> 1)) & 0x3333333333333333ull;
+    v = (v | (v >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+    v = (v | (v >> 4)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v >> 8)) & 0x0000FFFF0000FFFFull;
+    v = (v | (v >> 16)) & 0x00000000FFFFFFFFull;
+    return (uint32_t)v;
+}
+__host__ __device__ inline uint64_t morton_encode(uint32_t bi, uint32_t bj) {
+    return spread_bits(bi) | (spread_bits(bj) << 1);
+}
+__host__ __device__ inline uint32_t morton_row(uint64_t key) { return compact_bits(key); }
+__host__ __device__ inline uint32_t morton_col(uint64_t key) { return compact_bits(key >> 1); }
+__host__ __device__ inline uint64_t morton_transpose(uint64_t key) {
+    return ((key & 0x5555555555555555ull) << 1) | ((key >> 1) & 0x5555555555555555ull);
+}
+
+struct EventTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    EventTimer() { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~EventTimer() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    void start() { cudaEventRecord(a, engine().stream); }
+    void stop() { cudaEventRecord(b, engine().stream); }
+    double ms() { float t = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&t, a, b); return t; }
+};
+
+// ---- primitives.cu ----
+// exclusive prefix sum of n uint32 counts into uint64 offsets; out[n] = total (out has n+1 entries)
+void exclusive_scan_u32(const uint32_t* d_in, uint64_t* d_out, size_t n);
+// stable LSD radix sort of (key,value) pairs on the low `key_bits` bits; result left in d_keys/d_vals
+void radix_sort_pairs(uint64_t* d_keys, uint32_t* d_vals, size_t n, int key_bits);
+
+}  // namespace hbsm_b200

@@ -1,0 +1,1078 @@
+// matrix.cu -- the flat block table: sizing, assembly (COO / whole tiles), readback, norms, line indices and the
+// HBM-bound structure operations (add, transpose, upper triangle, rescale, copy, symmetric expansion).
+// Reference behaviour reproduced here is cited as H:<line> of source/HierarchicalBlockSparseMatrix.h.
+#include "matrix.cuh"
+#include <cmath>
+
+namespace hbsm_b200 {
+
+// ---------------------------------------------------------------------------------------------------
+// engine
+// ---------------------------------------------------------------------------------------------------
+Engine& engine() {
+    static Engine e;
+    return e;
+}
+
+void ensure_engine() {
+    Engine& e = engine();
+    if (e.ready) {
+        cudaSetDevice(e.device);
+        return;
+    }
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0)
+        throw Error(HBSM_E_CUDA, "hbsm_b200: no CUDA device available (this engine has no CPU fallback)");
+    int dev = e.device >= 0 ? e.device : 0;
+    if (dev >= count) throw Error(HBSM_E_CUDA, "hbsm_b200: device index out of range");
+    HB_CUDA(cudaSetDevice(dev));
+    cudaDeviceProp p;
+    HB_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (p.major != 10)
+        throw Error(HBSM_E_CUDA, std::string("hbsm_b200: kernels are built for sm_100a only; device is ") + p.name);
+    e.device = dev;
+    e.sm_count = p.multiProcessorCount;
+    e.cc_major = p.major;
+    e.cc_minor = p.minor;
+    e.name = p.name;
+    HB_CUDA(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    HB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t thr = UINT64_MAX;
+    HB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    e.ready = true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Matrix basics
+// ---------------------------------------------------------------------------------------------------
+void Matrix::clear() {  // H:614
+    keys.release(); tiles.release(); norms.release();
+    invalidate_indices();
+    drop_tasks();
+    L = 0; M = 0; N = 0; sized = false;
+    root_norm_cached = 0.0;
+}
+
+void Matrix::resize(int m, int n) {  // H:544
+    if (b <= 0) throw Error(HBSM_E_ARG, "hbsm_b200: blocksize must be set before resize");
+    if (m < 0 || n < 0) throw Error(HBSM_E_ARG, "hbsm_b200: negative dimension");
+    clear();
+    M = m; N = n; sized = true;
+    if (m <= b && n <= b) {  // lowest level: a single zero-filled leaf, H:553-558
+        DevBuf<uint64_t> k(1);
+        k.zero();
+        DevBuf<char> t(tile_bytes());
+        t.zero();
+        set_table(std::move(k), std::move(t), 1);
+    }
+}
+
+void Matrix::set_table(DevBuf<uint64_t>&& k, DevBuf<char>&& t, size_t count) {
+    keys = std::move(k);
+    tiles = std::move(t);
+    L = count;
+    norms.alloc(std::max<size_t>(count, 1) * esize());
+    norms.zero();
+    invalidate_indices();
+}
+
+namespace {
+
+template <typename T> struct DT;
+template <> struct DT<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+};
+template <> struct DT<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+};
+
+inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// lower_bound over sorted keys; returns index or -1 if absent
+__device__ __forceinline__ long long find_key(const uint64_t* __restrict__ keys, size_t n, uint64_t key) {
+    size_t lo = 0, hi = n;
+    while (lo < hi) {
+        size_t mid = (lo + hi) >> 1;
+        if (keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return (lo < n && keys[lo] == key) ? (long long)lo : -1;
+}
+
+// ---- assembly kernels ----
+// element key = tile Morton key * b^2 + column-major offset inside the tile; flag bit 0: out of [0,M)x[0,N)
+__global__ void k_coo_keys(const int* __restrict__ rows, const int* __restrict__ cols, size_t n, int b, int M, int N,
+                           long long vsize, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx,
+                           unsigned* __restrict__ flags) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = rows[i], c = cols[i];
+    idx[i] = (uint32_t)i;
+    bool inside = r >= 0 && r < M && c >= 0 && c < N;
+    bool invirt = r >= 0 && r < vsize && c >= 0 && c < vsize;
+    if (!inside) atomicOr(flags, invirt ? 1u : 3u);
+    if (!invirt) { keys[i] = ~0ull; return; }   // dropped by the 4-way split of H:755-789
+    uint64_t tk = morton_encode((uint32_t)(r / b), (uint32_t)(c / b));
+    keys[i] = tk * (uint64_t)b * (uint64_t)b + (uint64_t)(c % b) * b + (uint64_t)(r % b);
+}
+
+__global__ void k_flag_tile_heads(const uint64_t* __restrict__ ekeys, size_t n, uint64_t bb, uint32_t* __restrict__ head) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = ekeys[i];
+    if (k == ~0ull) { head[i] = 0; return; }
+    head[i] = (i == 0 || ekeys[i - 1] / bb != k / bb) ? 1u : 0u;
+}
+
+__global__ void k_emit_tile_keys(const uint64_t* __restrict__ ekeys, size_t n, uint64_t bb,
+                                 const uint32_t* __restrict__ head, const uint64_t* __restrict__ pos,
+                                 uint64_t* __restrict__ tkeys) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (head[i]) tkeys[pos[i]] = ekeys[i] / bb;
+}
+
+// one thread per sorted element; run heads fold their run sequentially in input order (stable sort), so duplicates
+// are summed exactly as the reference's leaf loop does (H:703-721): x = ((x + v1) + v2) ... / x = max(x, v)
+template <typename T>
+__global__ void k_scatter_runs(const uint64_t* __restrict__ ekeys, const uint32_t* __restrict__ eidx, size_t n,
+                               uint64_t bb, int b, int M, int N, const int* __restrict__ rows, const int* __restrict__ cols,
+                               const T* __restrict__ vals, const uint64_t* __restrict__ tkeys, size_t L,
+                               T* __restrict__ tiles, int use_max) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = ekeys[i];
+    if (k == ~0ull) return;
+    if (i > 0 && ekeys[i - 1] == k) return;
+    long long t = find_key(tkeys, L, k / bb);
+    if (t < 0) return;
+    T* dst = tiles + (size_t)t * bb + (k % bb);
+    T x = *dst;
+    for (size_t j = i; j < n && ekeys[j] == k; ++j) {
+        uint32_t e = eidx[j];
+        if (rows[e] >= M || cols[e] >= N) continue;   // padding of a boundary leaf, H:708
+        T v = vals[e];
+        if (use_max) x = (v > x) ? v : x;
+        else x = DT<T>::add(x, v);
+    }
+    *dst = x;
+}
+
+// ---- readback kernels ----
+template <typename T>
+__global__ void k_get_values(const uint64_t* __restrict__ tkeys, size_t L, const T* __restrict__ tiles, int b,
+                             const int* __restrict__ rows, const int* __restrict__ cols, size_t n, T* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = rows[i], c = cols[i];
+    long long t = find_key(tkeys, L, morton_encode((uint32_t)(r / b), (uint32_t)(c / b)));
+    out[i] = t < 0 ? (T)0 : tiles[(size_t)t * b * b + (size_t)(c % b) * b + (r % b)];   // absent child => 0, H:878
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_tile_nnz(const T* __restrict__ tiles, size_t bb, uint32_t* __restrict__ cnt) {
+    __shared__ uint32_t s[8];
+    const T* t = tiles + (size_t)blockIdx.x * bb;
+    uint32_t c = 0;
+    for (size_t i = threadIdx.x; i < bb; i += blockDim.x) c += (fabs((double)t[i]) > 0.0) ? 1u : 0u;
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (unsigned w = 0; w < blockDim.x / 32; ++w) tot += s[w];
+        cnt[blockIdx.x] = tot;
+    }
+}
+
+// ordered compaction of one tile: storage (column-major) order, only fabs(v) > 0 (H:1051-1063)
+template <typename T>
+__global__ void __launch_bounds__(256) k_tile_gather(const uint64_t* __restrict__ tkeys, const T* __restrict__ tiles,
+                                                      int b, const uint64_t* __restrict__ offs, int* __restrict__ rows,
+                                                      int* __restrict__ cols, T* __restrict__ vals) {
+    __shared__ uint32_t wsum[8];
+    __shared__ uint32_t carry;
+    const size_t bb = (size_t)b * b;
+    const T* t = tiles + (size_t)blockIdx.x * bb;
+    uint64_t key = tkeys[blockIdx.x];
+    int r0 = (int)morton_row(key) * b, c0 = (int)morton_col(key) * b;
+    uint64_t base = offs[blockIdx.x];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (size_t s = 0; s < bb; s += blockDim.x) {
+        size_t i = s + threadIdx.x;
+        T v = i < bb ? t[i] : (T)0;
+        bool nz = i < bb && fabs((double)v) > 0.0;
+        unsigned bal = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t before = carry;
+        for (unsigned w = 0; w < warp; ++w) before += wsum[w];
+        if (nz) {
+            uint64_t p = base + before + __popc(bal & ((1u << lane) - 1u));
+            rows[p] = r0 + (int)(i % b);
+            cols[p] = c0 + (int)(i / b);
+            vals[p] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (unsigned w = 0; w < blockDim.x / 32; ++w) tot += wsum[w];
+            carry += tot;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- norms ----
+// One lane per leaf does the reference's strictly sequential sum_i fl(s + fl(x_i*x_i)) (H:646-652) -- a tree or
+// shuffle reduction would change the last ulp and could flip a borderline SpAMM test.  A warp owns 32 leaves and
+// streams them in 256-byte coalesced segments through shared memory so HBM sees full-line requests.
+template <typename T, int SEG /* elements per leaf per stage */>
+__global__ void __launch_bounds__(128) k_leaf_norms(const T* __restrict__ tiles, size_t L, size_t bb, T* __restrict__ out) {
+    constexpr int WARPS = 4;
+    __shared__ T buf[WARPS][32][SEG + 1];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    size_t leaf0 = ((size_t)blockIdx.x * WARPS + warp) * 32;
+    if (leaf0 >= L) return;
+    unsigned nleaf = (unsigned)min((size_t)32, L - leaf0);
+    const size_t nseg = (bb + SEG - 1) / SEG;
+    T acc = 0;
+    T reg[SEG];   // staged next segment: reg[j] = element (j*32+lane) of the 32xSEG stage in leaf-major order
+    auto load = [&](size_t sidx) {
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) {
+            unsigned flat = j * 32 + lane;
+            unsigned lf = flat / SEG, e = flat % SEG;
+            size_t pos = sidx * SEG + e;
+            reg[j] = (lf < nleaf && pos < bb) ? tiles[(leaf0 + lf) * bb + pos] : (T)0;
+        }
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) {
+            unsigned flat = j * 32 + lane;
+            buf[warp][flat / SEG][flat % SEG] = reg[j];
+        }
+    };
+    load(0);
+    for (size_t s = 0; s < nseg; ++s) {
+        stash();
+        __syncwarp();
+        if (s + 1 < nseg) load(s + 1);
+        size_t rem = bb - s * SEG;
+        int cnt = rem < (size_t)SEG ? (int)rem : SEG;
+        if (cnt == SEG) {
+#pragma unroll
+            for (int e = 0; e < SEG; ++e) { T x = buf[warp][lane][e]; acc = DT<T>::add(acc, DT<T>::mul(x, x)); }
+        } else {
+            for (int e = 0; e < cnt; ++e) { T x = buf[warp][lane][e]; acc = DT<T>::add(acc, DT<T>::mul(x, x)); }
+        }
+        __syncwarp();
+    }
+    if (lane < nleaf) out[leaf0 + lane] = acc;
+}
+
+// one level of H:3918-3923 / H:656-662: parent = sum of existing children in order 0..3, starting from 0
+__global__ void k_level_heads(const uint64_t* __restrict__ keys, size_t n, uint32_t* __restrict__ head) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    head[i] = (i == 0 || (keys[i - 1] >> 2) != (keys[i] >> 2)) ? 1u : 0u;
+}
+template <typename T>
+__global__ void k_level_reduce(const uint64_t* __restrict__ keys, const T* __restrict__ vals, size_t n,
+                               const uint32_t* __restrict__ head, const uint64_t* __restrict__ pos,
+                               uint64_t* __restrict__ okeys, T* __restrict__ ovals) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !head[i]) return;
+    uint64_t pk = keys[i] >> 2;
+    T s = 0;
+    for (size_t j = i; j < n && (keys[j] >> 2) == pk; ++j) s = DT<T>::add(s, vals[j]);
+    okeys[pos[i]] = pk;
+    ovals[pos[i]] = s;
+}
+
+// ---- line index ----
+__global__ void k_line_keys(const uint64_t* __restrict__ keys, size_t n, int by_col, int dbits, uint64_t* __restrict__ skey,
+                            uint32_t* __restrict__ idx) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t r = morton_row(keys[i]), c = morton_col(keys[i]);
+    uint32_t line = by_col ? c : r, other = by_col ? r : c;
+    skey[i] = ((uint64_t)line << dbits) | other;
+    idx[i] = (uint32_t)i;
+}
+__global__ void k_line_ptr(const uint64_t* __restrict__ skey, size_t n, int dbits, uint32_t n_lines,
+                           uint32_t* __restrict__ ptr, uint32_t* __restrict__ other) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t line = (uint32_t)(skey[i] >> dbits);
+    other[i] = (uint32_t)(skey[i] & ((1ull << dbits) - 1ull));
+    uint32_t prev = i == 0 ? 0u : (uint32_t)(skey[i - 1] >> dbits) + 1u;
+    for (uint32_t l = prev; l <= line; ++l) ptr[l] = (uint32_t)i;   // lines (prev_line, line] start here
+    if (i == n - 1)
+        for (uint32_t l = line + 1; l <= n_lines; ++l) ptr[l] = (uint32_t)n;
+}
+
+// ---- structure ops ----
+// merge-union of two sorted key lists: flags per output slot which inputs contribute
+__global__ void k_union_mark(const uint64_t* __restrict__ ka, size_t na, const uint64_t* __restrict__ kb, size_t nb,
+                             uint32_t* __restrict__ keep_b /* 1 if kb[i] not in ka */) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    keep_b[i] = find_key(ka, na, kb[i]) < 0 ? 1u : 0u;
+}
+// position of every A tile and of every B-only tile in the union: rankA(i) = i + #(B-only keys < ka[i]) etc.
+__global__ void k_union_pos_a(const uint64_t* __restrict__ ka, size_t na, const uint64_t* __restrict__ kb, size_t nb,
+                              const uint64_t* __restrict__ bonly_prefix, uint64_t* __restrict__ ukeys,
+                              uint32_t* __restrict__ src_a, uint32_t* __restrict__ src_b) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= na) return;
+    uint64_t key = ka[i];
+    size_t lo = 0, hi = nb;
+    while (lo < hi) { size_t mid = (lo + hi) >> 1; if (kb[mid] < key) lo = mid + 1; else hi = mid; }
+    size_t p = i + bonly_prefix[lo];
+    ukeys[p] = key;
+    src_a[p] = (uint32_t)i;
+    src_b[p] = (lo < nb && kb[lo] == key) ? (uint32_t)lo : 0xffffffffu;
+}
+__global__ void k_union_pos_b(const uint64_t* __restrict__ ka, size_t na, const uint64_t* __restrict__ kb, size_t nb,
+                              const uint32_t* __restrict__ keep_b, const uint64_t* __restrict__ bonly_prefix,
+                              uint64_t* __restrict__ ukeys, uint32_t* __restrict__ src_a, uint32_t* __restrict__ src_b) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb || !keep_b[i]) return;
+    uint64_t key = kb[i];
+    size_t lo = 0, hi = na;
+    while (lo < hi) { size_t mid = (lo + hi) >> 1; if (ka[mid] < key) lo = mid + 1; else hi = mid; }
+    size_t p = lo + bonly_prefix[i];
+    ukeys[p] = key;
+    src_a[p] = 0xffffffffu;
+    src_b[p] = (uint32_t)i;
+}
+
+// C tile = A tile + B tile (fl(a+b), H:1674-1677), or a copy when only one exists (the reference aliases, H:1699).
+// 16-byte vectorised when the tile is a multiple of 16 bytes; one CTA streams a slice of one tile.
+template <typename T>
+__global__ void __launch_bounds__(256) k_add_tiles(const T* __restrict__ ta, const T* __restrict__ tb,
+                                                    const uint32_t* __restrict__ src_a, const uint32_t* __restrict__ src_b,
+                                                    size_t bb, T* __restrict__ tc) {
+    const size_t t = blockIdx.x;
+    const uint32_t ia = src_a[t], ib = src_b[t];
+    T* c = tc + t * bb;
+    const T* a = ia != 0xffffffffu ? ta + (size_t)ia * bb : nullptr;
+    const T* b = ib != 0xffffffffu ? tb + (size_t)ib * bb : nullptr;
+    constexpr int V = 16 / sizeof(T);
+    if ((bb % V) == 0) {
+        const size_t nv = bb / V;
+        const int4* a4 = reinterpret_cast<const int4*>(a);
+        const int4* b4 = reinterpret_cast<const int4*>(b);
+        int4* c4 = reinterpret_cast<int4*>(c);
+        for (size_t i = (size_t)blockIdx.y * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.y * blockDim.x) {
+            if (a && b) {
+                int4 x = __ldg(a4 + i), y = __ldg(b4 + i);
+                T* xp = reinterpret_cast<T*>(&x);
+                const T* yp = reinterpret_cast<const T*>(&y);
+#pragma unroll
+                for (int j = 0; j < V; ++j) xp[j] = DT<T>::add(xp[j], yp[j]);
+                c4[i] = x;
+            } else {
+                c4[i] = __ldg((a ? a4 : b4) + i);
+            }
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.y * blockDim.x + threadIdx.x; i < bb; i += (size_t)gridDim.y * blockDim.x)
+            c[i] = (a && b) ? DT<T>::add(a[i], b[i]) : (a ? a[i] : b[i]);
+    }
+}
+
+// out tile t = transpose of in tile src[t] (through shared memory so both sides are coalesced), H:3748-3752
+template <typename T>
+__global__ void __launch_bounds__(256) k_transpose_tiles(const T* __restrict__ tin, const uint32_t* __restrict__ src,
+                                                          int b, T* __restrict__ tout) {
+    __shared__ T s[32][33];
+    const size_t bb = (size_t)b * b;
+    const T* in = tin + (size_t)src[blockIdx.x] * bb;
+    T* out = tout + (size_t)blockIdx.x * bb;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int c0 = 0; c0 < b; c0 += 32)
+        for (int r0 = 0; r0 < b; r0 += 32) {
+            for (int j = ty; j < 32; j += 8) {
+                int r = r0 + tx, c = c0 + j;
+                s[j][tx] = (r < b && c < b) ? in[(size_t)c * b + r] : (T)0;
+            }
+            __syncthreads();
+            for (int j = ty; j < 32; j += 8) {
+                int r = c0 + tx, c = r0 + j;    // out(r,c) = in(c,r)
+                if (r < b && c < b) out[(size_t)c * b + r] = s[tx][j];
+            }
+            __syncthreads();
+        }
+}
+
+__global__ void k_transpose_keys(const uint64_t* __restrict__ keys, size_t n, uint64_t* __restrict__ okeys,
+                                 uint32_t* __restrict__ idx) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    okeys[i] = morton_transpose(keys[i]);
+    idx[i] = (uint32_t)i;
+}
+
+// keep tiles with bi <= bj (H:3515-3559)
+__global__ void k_upper_flags(const uint64_t* __restrict__ keys, size_t n, uint32_t* __restrict__ keep) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keep[i] = morton_row(keys[i]) <= morton_col(keys[i]) ? 1u : 0u;
+}
+__global__ void k_compact_keys(const uint64_t* __restrict__ keys, size_t n, const uint32_t* __restrict__ keep,
+                               const uint64_t* __restrict__ pos, uint64_t* __restrict__ okeys, uint32_t* __restrict__ src) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    okeys[pos[i]] = keys[i];
+    src[pos[i]] = (uint32_t)i;
+}
+// copy tile src[t] -> t; mode 0 plain copy * alpha (alpha_on), mode 1: diagonal tiles keep only row <= col
+template <typename T>
+__global__ void __launch_bounds__(256) k_copy_tiles(const T* __restrict__ tin, const uint32_t* __restrict__ src,
+                                                     const uint64_t* __restrict__ okeys, int b, int mask_diag,
+                                                     int scale, T alpha, T* __restrict__ tout) {
+    const size_t bb = (size_t)b * b;
+    const size_t si = src ? (size_t)src[blockIdx.x] : (size_t)blockIdx.x;
+    const T* in = tin + si * bb;
+    T* out = tout + (size_t)blockIdx.x * bb;
+    bool diag = false;
+    if (mask_diag) { uint64_t k = okeys[blockIdx.x]; diag = morton_row(k) == morton_col(k); }
+    for (size_t i = (size_t)blockIdx.y * blockDim.x + threadIdx.x; i < bb; i += (size_t)gridDim.y * blockDim.x) {
+        T v = in[i];
+        if (diag && (int)(i % b) > (int)(i / b)) v = (T)0;
+        if (scale) v = DT<T>::mul(v, alpha);
+        out[i] = v;
+    }
+}
+
+// symmetric expansion of upper storage: S(i,j) = A(min,max).  Output tile t has source tile src[t]; flag bit0 =
+// take it transposed (strict-lower tile), bit1 = diagonal tile (mirror the upper part onto the lower part).
+template <typename T>
+__global__ void __launch_bounds__(256) k_sym_tiles(const T* __restrict__ tin, const uint32_t* __restrict__ src,
+                                                    const uint32_t* __restrict__ flag, int b, T* __restrict__ tout) {
+    const size_t bb = (size_t)b * b;
+    const T* in = tin + (size_t)src[blockIdx.x] * bb;
+    T* out = tout + (size_t)blockIdx.x * bb;
+    const uint32_t f = flag[blockIdx.x];
+    for (size_t i = threadIdx.x; i < bb; i += blockDim.x) {
+        int r = (int)(i % b), c = (int)(i / b);
+        T v;
+        if (f & 2u) { int rr = r < c ? r : c, cc = r < c ? c : r; v = in[(size_t)cc * b + rr]; }
+        else if (f & 1u) v = in[(size_t)r * b + c];
+        else v = in[i];
+        out[i] = v;
+    }
+}
+__global__ void k_sym_keys(const uint64_t* __restrict__ keys, size_t n, uint64_t* __restrict__ okeys,
+                           uint32_t* __restrict__ osrc, uint32_t* __restrict__ valid) {
+    // input tile i with bi<bj yields (bi,bj) and (bj,bi); bi==bj yields itself; bi>bj (never stored) is ignored
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t r = morton_row(keys[i]), c = morton_col(keys[i]);
+    okeys[2 * i] = keys[i];               osrc[2 * i] = (uint32_t)i;     valid[2 * i] = r <= c ? 1u : 0u;
+    okeys[2 * i + 1] = morton_transpose(keys[i]); osrc[2 * i + 1] = (uint32_t)i; valid[2 * i + 1] = r < c ? 1u : 0u;
+}
+__global__ void k_sym_compact(const uint64_t* __restrict__ keys2, const uint32_t* __restrict__ src2,
+                              const uint32_t* __restrict__ valid, const uint64_t* __restrict__ pos, size_t n2,
+                              uint64_t* __restrict__ okeys, uint32_t* __restrict__ osrc_packed) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2 || !valid[i]) return;
+    okeys[pos[i]] = keys2[i];
+    osrc_packed[pos[i]] = (src2[i] << 1) | (uint32_t)(i & 1);   // low bit: mirrored copy
+}
+__global__ void k_sym_unpack(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ packed, size_t n,
+                             uint32_t* __restrict__ src, uint32_t* __restrict__ flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    src[i] = packed[i] >> 1;
+    uint32_t f = packed[i] & 1u;
+    if (morton_row(keys[i]) == morton_col(keys[i])) f |= 2u;
+    flag[i] = f;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_mask_diag(const uint64_t* __restrict__ keys, int b, T* __restrict__ tiles) {
+    uint64_t k = keys[blockIdx.x];
+    if (morton_row(k) != morton_col(k)) return;
+    const size_t bb = (size_t)b * b;
+    T* t = tiles + (size_t)blockIdx.x * bb;
+    for (size_t i = threadIdx.x; i < bb; i += blockDim.x)
+        if ((int)(i % b) > (int)(i / b)) t[i] = (T)0;
+}
+
+// ---- banded exponential-decay generator: a_ij = (0.5 + 0.5 u(seed,i,j)) exp(-lambda |i-j|), |i-j| <= W ----
+__host__ __device__ inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__host__ __device__ inline double hash_u01(uint64_t seed, uint64_t i, uint64_t j) {
+    uint64_t h = splitmix64(seed ^ splitmix64(i * 0x100000001B3ull + splitmix64(j)));
+    return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+}
+__global__ void k_decay_keys(uint32_t lo, uint32_t hi, uint32_t g, uint32_t wb, uint64_t* __restrict__ keys) {
+    // tile rows [lo,hi), per row columns [bi-wb, bi+wb] clipped; enumerated densely, invalid = ~0
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t span = 2 * (size_t)wb + 1;
+    if (i >= (size_t)(hi - lo) * span) return;
+    uint32_t bi = lo + (uint32_t)(i / span);
+    long long bj = (long long)bi - wb + (long long)(i % span);
+    keys[i] = (bj < 0 || bj >= g) ? ~0ull : morton_encode(bi, (uint32_t)bj);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_decay_fill(const uint64_t* __restrict__ keys, int b, int n, int W,
+                                                     const double* __restrict__ table, uint64_t seed, int symmetric,
+                                                     T* __restrict__ tiles) {
+    const size_t bb = (size_t)b * b;
+    uint64_t k = keys[blockIdx.x];
+    long long r0 = (long long)morton_row(k) * b, c0 = (long long)morton_col(k) * b;
+    T* t = tiles + (size_t)blockIdx.x * bb;
+    for (size_t i = threadIdx.x; i < bb; i += blockDim.x) {
+        long long r = r0 + (long long)(i % b), c = c0 + (long long)(i / b);
+        long long d = r > c ? r - c : c - r;
+        double v = 0.0;
+        if (r < n && c < n && d <= W) {
+            uint64_t hi_ = symmetric ? (uint64_t)(r < c ? r : c) : (uint64_t)r;
+            uint64_t hj_ = symmetric ? (uint64_t)(r < c ? c : r) : (uint64_t)c;
+            v = (0.5 + 0.5 * hash_u01(seed, hi_, hj_)) * table[d];
+        }
+        t[i] = (T)v;
+    }
+}
+
+template <typename F>
+void dispatch(int dtype, F&& f) {
+    if (dtype == HBSM_F64) f((double)0);
+    else f((float)0);
+}
+
+// compact helper: exclusive scan of flags -> positions, returns total (synchronises)
+size_t scan_flags(const DevBuf<uint32_t>& flags, size_t n, DevBuf<uint64_t>& pos) {
+    pos.alloc(n + 1);
+    exclusive_scan_u32(flags.p, pos.p, n);
+    uint64_t total = 0;
+    HB_CUDA(cudaMemcpyAsync(&total, pos.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, engine().stream));
+    sync_stream();
+    return (size_t)total;
+}
+
+int key_bits_for(const Matrix& A) { return std::max(1, 2 * A.vdepth()); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// assembly
+// ---------------------------------------------------------------------------------------------------
+void assign_coo(Matrix& A, size_t n, const int* rows, const int* cols, const void* vals, bool use_max, bool checked) {
+    if (!A.sized) throw_ref("Error in HierarchicalBlockSparseMatrix<Treal>::assign_from_vectors: index outside matrix boundaries.");
+    if (n == 0) return;   // H:679
+    if (n >= 0xffffffffull) throw Error(HBSM_E_ARG, "hbsm_b200: more than 2^32-1 triplets in one assign call");
+    ensure_engine();
+    const int depth = A.vdepth();
+    const long long vsize = (long long)A.b << depth;
+    const uint64_t bb = A.tile_elems();
+    DevBuf<int> d_rows(n), d_cols(n);
+    DevBuf<char> d_vals(n * A.esize());
+    d_rows.upload(rows, n);
+    d_cols.upload(cols, n);
+    HB_CUDA(cudaMemcpyAsync(d_vals.p, vals, n * A.esize(), cudaMemcpyHostToDevice, engine().stream));
+    DevBuf<uint64_t> ekeys(n);
+    DevBuf<uint32_t> eidx(n);
+    DevBuf<unsigned> flags(1);
+    flags.zero();
+    HB_LAUNCH(k_coo_keys, blocks_for(n, 256), 256, 0, d_rows.p, d_cols.p, n, A.b, A.M, A.N, vsize, ekeys.p, eidx.p, flags.p);
+    unsigned hflags = 0;
+    HB_CUDA(cudaMemcpyAsync(&hflags, flags.p, sizeof(unsigned), cudaMemcpyDeviceToHost, engine().stream));
+    sync_stream();
+    if (hflags && !checked)   // H:682-688
+        throw_ref("Error in HierarchicalBlockSparseMatrix<Treal>::assign_from_vectors: index outside matrix boundaries.");
+    // element keys < vsize^2; dropped elements (~0) sort to the end because the sort covers all 64 bits in that case
+    int bits = 1;
+    while (bits < 64 && (1ull << bits) < (uint64_t)vsize * (uint64_t)vsize) ++bits;
+    if (hflags & 2u) bits = 64;
+    radix_sort_pairs(ekeys.p, eidx.p, n, bits);
+    DevBuf<uint32_t> head(n);
+    HB_LAUNCH(k_flag_tile_heads, blocks_for(n, 256), 256, 0, ekeys.p, n, bb, head.p);
+    DevBuf<uint64_t> pos;
+    size_t Lnew = scan_flags(head, n, pos);
+    if (Lnew == 0) return;
+    DevBuf<uint64_t> tkeys(Lnew);
+    HB_LAUNCH(k_emit_tile_keys, blocks_for(n, 256), 256, 0, ekeys.p, n, bb, head.p, pos.p, tkeys.p);
+
+    Matrix fresh;   // where the new elements are folded
+    Matrix* target = &A;
+    if (depth == 0) {
+        // single leaf: += / max onto the existing content (H:703-721), nothing to create
+    } else if (A.L == 0) {
+        DevBuf<char> t(Lnew * A.tile_bytes());
+        t.zero();
+        A.set_table(std::move(tkeys), std::move(t), Lnew);
+    } else {
+        // second assign on a populated tree: the reference throws when a root quadrant is touched twice (H:793)
+        std::vector<uint64_t> ka = A.keys.to_host(), kn = tkeys.to_host();
+        const int sh = 2 * (depth - 1);
+        bool have[4] = {false, false, false, false};
+        for (uint64_t k : ka) have[(k >> sh) & 3] = true;
+        for (uint64_t k : kn)
+            if (have[(k >> sh) & 3]) {
+                char msg[160];
+                snprintf(msg, sizeof msg,
+                         "Error in HierarchicalBlockSparseMatrix<Treal>::assign_from_vectors: non-null child%d matrix occured.",
+                         (int)((k >> sh) & 3));
+                throw_ref(msg);
+            }
+        fresh.dtype = A.dtype; fresh.b = A.b; fresh.M = A.M; fresh.N = A.N; fresh.sized = true;
+        DevBuf<char> t(Lnew * A.tile_bytes());
+        t.zero();
+        fresh.set_table(std::move(tkeys), std::move(t), Lnew);
+        target = &fresh;
+    }
+    dispatch(A.dtype, [&](auto z) {
+        using T = decltype(z);
+        HB_LAUNCH(k_scatter_runs<T>, blocks_for(n, 256), 256, 0, ekeys.p, eidx.p, n, bb, A.b, A.M, A.N, d_rows.p, d_cols.p,
+                  (const T*)d_vals.p, target->keys.p, target->L, (T*)target->tiles.p, use_max ? 1 : 0);
+    });
+    if (target == &fresh) {
+        Matrix merged;
+        size_t keep_mults = A.n_mults;
+        op_add(A, fresh, merged);   // disjoint tile sets: pure union
+        A.keys = std::move(merged.keys); A.tiles = std::move(merged.tiles); A.norms = std::move(merged.norms);
+        A.L = merged.L; A.n_mults = keep_mults;
+    }
+    A.invalidate_indices();
+    sync_stream();   // host staging buffers die here
+}
+
+void assign_tiles_device(Matrix& A, size_t n_tiles, const uint64_t* d_keys, const void* d_tiles, const void* d_norms) {
+    if (!A.sized) throw Error(HBSM_E_ARG, "hbsm_b200: assign_tiles on an unsized matrix");
+    ensure_engine();
+    if (n_tiles == 0) return;
+    if (A.vdepth() == 0) {
+        if (n_tiles != 1) throw Error(HBSM_E_ARG, "hbsm_b200: a single-leaf matrix takes exactly one tile");
+        HB_CUDA(cudaMemcpyAsync(A.tiles.p, d_tiles, A.tile_bytes(), cudaMemcpyDeviceToDevice, engine().stream));
+        if (d_norms) HB_CUDA(cudaMemcpyAsync(A.norms.p, d_norms, A.esize(), cudaMemcpyDeviceToDevice, engine().stream));
+        return;
+    }
+    if (A.L != 0) throw_ref("Error in HierarchicalBlockSparseMatrix<Treal>::assign_from_vectors: non-null child0 matrix occured.");
+    DevBuf<uint64_t> skeys(n_tiles);
+    DevBuf<uint32_t> idx(n_tiles);
+    HB_CUDA(cudaMemcpyAsync(skeys.p, d_keys, n_tiles * sizeof(uint64_t), cudaMemcpyDeviceToDevice, engine().stream));
+    {
+        // reuse k_transpose_keys-style iota: idx[i] = i
+        DevBuf<uint64_t> dummy(n_tiles);
+        HB_LAUNCH(k_transpose_keys, blocks_for(n_tiles, 256), 256, 0, skeys.p, n_tiles, dummy.p, idx.p);
+    }
+    radix_sort_pairs(skeys.p, idx.p, n_tiles, key_bits_for(A));
+    DevBuf<char> t(n_tiles * A.tile_bytes());
+    dispatch(A.dtype, [&](auto z) {
+        using T = decltype(z);
+        dim3 grid((unsigned)n_tiles, (unsigned)std::max<size_t>(1, std::min<size_t>(8, A.tile_elems() / 1024)));
+        HB_LAUNCH(k_copy_tiles<T>, grid, 256, 0, (const T*)d_tiles, idx.p, skeys.p, A.b, 0, 0, (T)1, (T*)t.p);
+    });
+    A.set_table(std::move(skeys), std::move(t), n_tiles);
+    if (d_norms) {
+        // gather norms in sorted order with the same permutation (1-element "tiles")
+        dispatch(A.dtype, [&](auto z) {
+            using T = decltype(z);
+            HB_LAUNCH(k_copy_tiles<T>, dim3((unsigned)n_tiles, 1), 32, 0, (const T*)d_norms, idx.p, A.keys.p, 1, 0, 0, (T)1,
+                      (T*)A.norms.p);
+        });
+    }
+    sync_stream();
+}
+
+void assign_tiles_host(Matrix& A, size_t n_tiles, const int* bi, const int* bj, const void* tiles) {
+    if (!A.sized) throw Error(HBSM_E_ARG, "hbsm_b200: assign_tiles on an unsized matrix");
+    if (n_tiles == 0) return;
+    ensure_engine();
+    const uint32_t g = A.grid_side();
+    std::vector<uint64_t> hk(n_tiles);
+    for (size_t i = 0; i < n_tiles; ++i) {
+        if (bi[i] < 0 || bj[i] < 0 || (uint32_t)bi[i] >= g || (uint32_t)bj[i] >= g ||
+            (long long)bi[i] * A.b >= std::max(A.M, 1) || (long long)bj[i] * A.b >= std::max(A.N, 1))
+            throw_ref("Error in HierarchicalBlockSparseMatrix<Treal>::assign_from_vectors: index outside matrix boundaries.");
+        hk[i] = morton_encode((uint32_t)bi[i], (uint32_t)bj[i]);
+    }
+    DevBuf<uint64_t> dk(n_tiles);
+    dk.upload(hk.data(), n_tiles);
+    DevBuf<char> dt(n_tiles * A.tile_bytes());
+    HB_CUDA(cudaMemcpyAsync(dt.p, tiles, n_tiles * A.tile_bytes(), cudaMemcpyHostToDevice, engine().stream));
+    assign_tiles_device(A, n_tiles, dk.p, dt.p, nullptr);
+    sync_stream();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// readback
+// ---------------------------------------------------------------------------------------------------
+void get_values(const Matrix& A, size_t n, const int* rows, const int* cols, void* out) {
+    if (A.empty()) throw_ref("Error in HierarchicalBlockSparseMatrix<Treal>::get_values: empty matrix occured.");
+    if (n == 0) return;
+    for (size_t i = 0; i < n; ++i)
+        if (!(0 <= rows[i] && rows[i] < A.M && 0 <= cols[i] && cols[i] < A.N))
+            throw_ref("Error in HierarchicalBlockSparseMatrix<Treal>::get_single_value: bad index at highest level.");
+    ensure_engine();
+    DevBuf<int> dr(n), dc(n);
+    dr.upload(rows, n);
+    dc.upload(cols, n);
+    DevBuf<char> dv(n * A.esize());
+    dispatch(A.dtype, [&](auto z) {
+        using T = decltype(z);
+        HB_LAUNCH(k_get_values<T>, blocks_for(n, 256), 256, 0, A.keys.p, A.L, (const T*)A.tiles.p, A.b, dr.p, dc.p, n, (T*)dv.p);
+    });
+    HB_CUDA(cudaMemcpyAsync(out, dv.p, n * A.esize(), cudaMemcpyDeviceToHost, engine().stream));
+    sync_stream();
+}
+
+static void tile_nnz_counts(const Matrix& A, DevBuf<uint32_t>& cnt) {
+    cnt.alloc(A.L);
+    dispatch(A.dtype, [&](auto z) {
+        using T = decltype(z);
+        HB_LAUNCH(k_tile_nnz<T>, (unsigned)A.L, 256, 0, (const T*)A.tiles.p, A.tile_elems(), cnt.p);
+    });
+}
+
+size_t count_nnz(const Matrix& A) {
+    if (A.empty()) throw_ref("Error in HierarchicalBlockSparseMatrix<Treal>::get_nnz: empty matrix occured.");
+    if (A.L == 0) return 0;
+    ensure_engine();
+    DevBuf<uint32_t> cnt;
+    tile_nnz_counts(A, cnt);
+    DevBuf<uint64_t> pos;
+    return scan_flags(cnt, A.L, pos);
+}
+
+size_t get_all_values(const Matrix& A, size_t cap, int* rows, int* cols, void* vals) {
+    if (A.empty() || A.L == 0) return 0;   // H:1047
+    ensure_engine();
+    DevBuf<uint32_t> cnt;
+    tile_nnz_counts(A, cnt);
+    DevBuf<uint64_t> pos;
+    size_t total = scan_flags(cnt, A.L, pos);
+    if (cap < total || total == 0) return total;
+    DevBuf<int> dr(total), dc(total);
+    DevBuf<char> dv(total * A.esize());
+    dispatch(A.dtype, [&](auto z) {
+        using T = decltype(z);
+        HB_LAUNCH(k_tile_gather<T>, (unsigned)A.L, 256, 0, A.keys.p, (const T*)A.tiles.p, A.b, pos.p, dr.p, dc.p, (T*)dv.p);
+    });
+    dr.download(rows, total);
+    dc.download(cols, total);
+    HB_CUDA(cudaMemcpyAsync(vals, dv.p, total * A.esize(), cudaMemcpyDeviceToHost, engine().stream));
+    sync_stream();
+    return total;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// norms
+// ---------------------------------------------------------------------------------------------------
+void compute_leaf_norms(const Matrix& A, void* d_out) {
+    if (A.L == 0) return;
+    ensure_engine();
+    const unsigned grid = (unsigned)((A.L + 127) / 128);
+    if (A.dtype == HBSM_F64) {
+        auto kfn = k_leaf_norms<double, 32>;
+        HB_LAUNCH(kfn, grid, 128, 0, (const double*)A.tiles.p, A.L, A.tile_elems(), (double*)d_out);
+    } else {
+        auto kfn = k_leaf_norms<float, 64>;
+        HB_LAUNCH(kfn, grid, 128, 0, (const float*)A.tiles.p, A.L, A.tile_elems(), (float*)d_out);
+    }
+}
+
+double hierarchical_norm(const Matrix& A, const void* d_leaf_norms) {
+    if (A.L == 0) return 0.0;
+    ensure_engine();
+    const int depth = A.vdepth();
+    size_t n = A.L;
+    DevBuf<uint64_t> k0(n), k1(n);
+    DevBuf<char> v0(n * A.esize()), v1(n * A.esize());
+    HB_CUDA(cudaMemcpyAsync(k0.p, A.keys.p, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, engine().stream));
+    HB_CUDA(cudaMemcpyAsync(v0.p, d_leaf_norms, n * A.esize(), cudaMemcpyDeviceToDevice, engine().stream));
+    DevBuf<uint32_t> head(n);
+    DevBuf<uint64_t> pos;
+    uint64_t* kin = k0.p; uint64_t* kout = k1.p;
+    char* vin = v0.p; char* vout = v1.p;
+    for (int lvl = 0; lvl < depth; ++lvl) {
+        HB_LAUNCH(k_level_heads, blocks_for(n, 256), 256, 0, kin, n, head.p);
+        size_t nn = scan_flags(head, n, pos);
+        dispatch(A.dtype, [&](auto z) {
+            using T = decltype(z);
+            HB_LAUNCH(k_level_reduce<T>, blocks_for(n, 256), 256, 0, kin, (const T*)vin, n, head.p, pos.p, kout, (T*)vout);
+        });
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+        n = nn;
+    }
+    double res = 0.0;
+    if (A.dtype == HBSM_F64) {
+        HB_CUDA(cudaMemcpyAsync(&res, vin, sizeof(double), cudaMemcpyDeviceToHost, engine().stream));
+        sync_stream();
+    } else {
+        float f = 0;
+        HB_CUDA(cudaMemcpyAsync(&f, vin, sizeof(float), cudaMemcpyDeviceToHost, engine().stream));
+        sync_stream();
+        res = f;
+    }
+    return res;
+}
+
+void update_norms(Matrix& A) {   // H:3905
+    if (A.L == 0) { A.root_norm_cached = 0.0; return; }
+    compute_leaf_norms(A, A.norms.p);
+    A.root_norm_cached = hierarchical_norm(A, A.norms.p);
+}
+
+double frob_squared(const Matrix& A) {   // H:641
+    if (A.empty()) throw_ref("Error in HierarchicalBlockSparseMatrix<Treal>::get_frob_squared: empty matrix occured.");
+    if (A.L == 0) return 0.0;
+    DevBuf<char> tmp(A.L * A.esize());
+    compute_leaf_norms(A, tmp.p);
+    return hierarchical_norm(A, tmp.p);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// line indices
+// ---------------------------------------------------------------------------------------------------
+const LineIndex& line_index(const Matrix& A, bool by_col) {
+    LineIndex& ix = const_cast<LineIndex&>(by_col ? A.by_col : A.by_row);
+    if (ix.valid) return ix;
+    ensure_engine();
+    const int depth = A.vdepth();
+    const int dbits = std::max(depth, 1);
+    ix.n_lines = A.grid_side();
+    ix.ptr.alloc((size_t)ix.n_lines + 1);
+    ix.other.alloc(std::max<size_t>(A.L, 1));
+    ix.tile.alloc(std::max<size_t>(A.L, 1));
+    if (A.L == 0) {
+        ix.ptr.zero();
+    } else {
+        DevBuf<uint64_t> skey(A.L);
+        HB_LAUNCH(k_line_keys, blocks_for(A.L, 256), 256, 0, A.keys.p, A.L, by_col ? 1 : 0, dbits, skey.p, ix.tile.p);
+        radix_sort_pairs(skey.p, ix.tile.p, A.L, 2 * dbits);
+        HB_LAUNCH(k_line_ptr, blocks_for(A.L, 256), 256, 0, skey.p, A.L, dbits, ix.n_lines, ix.ptr.p, ix.other.p);
+    }
+    ix.valid = true;
+    return ix;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// structure operations
+// ---------------------------------------------------------------------------------------------------
+static unsigned slices_for(const Matrix& A) {
+    return (unsigned)std::max<size_t>(1, std::min<size_t>(8, A.tile_elems() * A.esize() / 8192));
+}
+
+void op_add(const Matrix& A, const Matrix& B, Matrix& C) {   // H:1644
+    C.clear();
+    if (A.empty() && B.empty()) return;
+    if (A.M != B.M || A.N != B.N)
+        throw_ref("Error in HierarchicalBlockSparseMatrix::add(): matrices to add have different sizes!");
+    if (A.dtype != B.dtype || A.b != B.b) throw Error(HBSM_E_ARG, "hbsm_b200: add: operands differ in dtype or blocksize");
+    ensure_engine();
+    C.dtype = A.dtype;
+    C.b = A.b;
+    C.resize(A.M, A.N);
+    C.n_mults = A.n_mults + B.n_mults;   // H:1719
+    const size_t na = A.L, nb = B.L;
+    if (na + nb == 0) return;
+    DevBuf<uint32_t> keep_b(std::max<size_t>(nb, 1));
+    DevBuf<uint64_t> bpre;
+    size_t n_bonly = 0;
+    if (nb) {
+        HB_LAUNCH(k_union_mark, blocks_for(nb, 256), 256, 0, A.keys.p, na, B.keys.p, nb, keep_b.p);
+        n_bonly = scan_flags(keep_b, nb, bpre);
+    } else {
+        bpre.alloc(1);
+        bpre.zero();
+    }
+    const size_t nu = na + n_bonly;
+    DevBuf<uint64_t> ukeys(nu);
+    DevBuf<uint32_t> src_a(nu), src_b(nu);
+    if (na) HB_LAUNCH(k_union_pos_a, blocks_for(na, 256), 256, 0, A.keys.p, na, B.keys.p, nb, bpre.p, ukeys.p, src_a.p, src_b.p);
+    if (nb) HB_LAUNCH(k_union_pos_b, blocks_for(nb, 256), 256, 0, A.keys.p, na, B.keys.p, nb, keep_b.p, bpre.p, ukeys.p, src_a.p, src_b.p);
+    DevBuf<char> t(nu * C.tile_bytes());
+    dispatch(C.dtype, [&](auto z) {
+        using T = decltype(z);
+        dim3 grid((unsigned)nu, slices_for(C));
+        HB_LAUNCH(k_add_tiles<T>, grid, 256, 0, (const T*)A.tiles.p, (const T*)B.tiles.p, src_a.p, src_b.p, C.tile_elems(), (T*)t.p);
+    });
+    C.set_table(std::move(ukeys), std::move(t), nu);
+    sync_stream();
+}
+
+void op_transpose(const Matrix& A, Matrix& C) {   // H:3733
+    if (!C.empty()) throw_ref("Error in HierarchicalBlockSparseMatrix::transpose(): non-empty matrix to write result!");
+    ensure_engine();
+    if (A.empty()) return;
+    C.dtype = A.dtype;
+    C.b = A.b;
+    C.resize(A.N, A.M);
+    if (A.L == 0) return;
+    DevBuf<uint64_t> okeys(A.L);
+    DevBuf<uint32_t> idx(A.L);
+    HB_LAUNCH(k_transpose_keys, blocks_for(A.L, 256), 256, 0, A.keys.p, A.L, okeys.p, idx.p);
+    radix_sort_pairs(okeys.p, idx.p, A.L, key_bits_for(A));
+    DevBuf<char> t(A.L * A.tile_bytes());
+    dispatch(A.dtype, [&](auto z) {
+        using T = decltype(z);
+        HB_LAUNCH(k_transpose_tiles<T>, (unsigned)A.L, 256, 0, (const T*)A.tiles.p, idx.p, A.b, (T*)t.p);
+    });
+    C.set_table(std::move(okeys), std::move(t), A.L);
+    sync_stream();
+}
+
+void op_upper(const Matrix& A, Matrix& C) {   // H:3515
+    if (A.M != A.N) throw_ref("Error in HierarchicalBlockSparseMatrix::get_upper_triangle(): call for non-square matrix!");
+    ensure_engine();
+    C.clear();
+    if (A.empty()) return;
+    C.dtype = A.dtype;
+    C.b = A.b;
+    C.resize(A.M, A.N);
+    if (A.L == 0) return;
+    DevBuf<uint32_t> keep(A.L);
+    HB_LAUNCH(k_upper_flags, blocks_for(A.L, 256), 256, 0, A.keys.p, A.L, keep.p);
+    DevBuf<uint64_t> pos;
+    size_t nk = scan_flags(keep, A.L, pos);
+    if (nk == 0) { if (A.vdepth() > 0) { C.keys.release(); C.tiles.release(); C.L = 0; } return; }
+    DevBuf<uint64_t> okeys(nk);
+    DevBuf<uint32_t> src(nk);
+    HB_LAUNCH(k_compact_keys, blocks_for(A.L, 256), 256, 0, A.keys.p, A.L, keep.p, pos.p, okeys.p, src.p);
+    DevBuf<char> t(nk * A.tile_bytes());
+    dispatch(A.dtype, [&](auto z) {
+        using T = decltype(z);
+        dim3 grid((unsigned)nk, slices_for(A));
+        HB_LAUNCH(k_copy_tiles<T>, grid, 256, 0, (const T*)A.tiles.p, src.p, okeys.p, A.b, 1, 0, (T)1, (T*)t.p);
+    });
+    C.set_table(std::move(okeys), std::move(t), nk);
+    sync_stream();
+}
+
+void op_rescale(Matrix& C, const Matrix& A, double alpha) {   // H:3078
+    if (!C.empty()) throw_ref("Error in HierarchicalBlockSparseMatrix::rescale(): non-empty matrix called this method!");
+    ensure_engine();
+    if (A.empty()) return;
+    C.dtype = A.dtype;
+    C.b = A.b;
+    C.resize(A.M, A.N);
+    if (A.L == 0) return;
+    DevBuf<uint64_t> okeys(A.L);
+    HB_CUDA(cudaMemcpyAsync(okeys.p, A.keys.p, A.L * sizeof(uint64_t), cudaMemcpyDeviceToDevice, engine().stream));
+    DevBuf<char> t(A.L * A.tile_bytes());
+    dispatch(A.dtype, [&](auto z) {
+        using T = decltype(z);
+        dim3 grid((unsigned)A.L, slices_for(A));
+        HB_LAUNCH(k_copy_tiles<T>, grid, 256, 0, (const T*)A.tiles.p, (const uint32_t*)nullptr, okeys.p, A.b, 0, 1, (T)alpha, (T*)t.p);
+    });
+    C.set_table(std::move(okeys), std::move(t), A.L);
+    sync_stream();
+}
+
+void op_copy(Matrix& C, const Matrix& A) {   // H:1490
+    if (&C == &A) return;
+    ensure_engine();
+    C.clear();
+    if (A.empty()) return;
+    C.dtype = A.dtype;
+    C.b = A.b;
+    C.resize(A.M, A.N);
+    C.n_mults = A.n_mults;
+    C.root_norm_cached = A.vdepth() > 0 ? A.root_norm_cached : 0.0;   // H:1507-1513: inner nodes only
+    if (A.L == 0) return;
+    DevBuf<uint64_t> okeys(A.L);
+    HB_CUDA(cudaMemcpyAsync(okeys.p, A.keys.p, A.L * sizeof(uint64_t), cudaMemcpyDeviceToDevice, engine().stream));
+    DevBuf<char> t(A.L * A.tile_bytes());
+    HB_CUDA(cudaMemcpyAsync(t.p, A.tiles.p, A.L * A.tile_bytes(), cudaMemcpyDeviceToDevice, engine().stream));
+    C.set_table(std::move(okeys), std::move(t), A.L);
+    sync_stream();
+}
+
+void sym_expand(const Matrix& A, Matrix& S) {
+    ensure_engine();
+    S.clear();
+    S.dtype = A.dtype;
+    S.b = A.b;
+    S.resize(A.M, A.N);
+    if (A.L == 0) return;
+    const size_t n2 = 2 * A.L;
+    DevBuf<uint64_t> k2(n2);
+    DevBuf<uint32_t> s2(n2), valid(n2);
+    HB_LAUNCH(k_sym_keys, blocks_for(A.L, 256), 256, 0, A.keys.p, A.L, k2.p, s2.p, valid.p);
+    DevBuf<uint64_t> pos;
+    size_t ns = scan_flags(valid, n2, pos);
+    if (ns == 0) return;
+    DevBuf<uint64_t> okeys(ns);
+    DevBuf<uint32_t> packed(ns);
+    HB_LAUNCH(k_sym_compact, blocks_for(n2, 256), 256, 0, k2.p, s2.p, valid.p, pos.p, n2, okeys.p, packed.p);
+    radix_sort_pairs(okeys.p, packed.p, ns, key_bits_for(A));
+    DevBuf<uint32_t> src(ns), flag(ns);
+    HB_LAUNCH(k_sym_unpack, blocks_for(ns, 256), 256, 0, okeys.p, packed.p, ns, src.p, flag.p);
+    DevBuf<char> t(ns * A.tile_bytes());
+    dispatch(A.dtype, [&](auto z) {
+        using T = decltype(z);
+        HB_LAUNCH(k_sym_tiles<T>, (unsigned)ns, 256, 0, (const T*)A.tiles.p, src.p, flag.p, A.b, (T*)t.p);
+    });
+    S.set_table(std::move(okeys), std::move(t), ns);
+    sync_stream();
+}
+
+void mask_diag_upper(Matrix& C) {
+    if (C.L == 0) return;
+    ensure_engine();
+    dispatch(C.dtype, [&](auto z) {
+        using T = decltype(z);
+        HB_LAUNCH(k_mask_diag<T>, (unsigned)C.L, 256, 0, C.keys.p, C.b, (T*)C.tiles.p);
+    });
+}
+
+void generate_decay(Matrix& A, int n, const double* table, int W, uint64_t seed, bool symmetric, int lo, int hi) {
+    ensure_engine();
+    A.resize(n, n);
+    const uint32_t g = (uint32_t)((n + A.b - 1) / A.b);
+    if (hi < 0 || hi > (int)g) hi = (int)g;
+    if (lo < 0) lo = 0;
+    if (lo >= hi) return;
+    const uint32_t wb = (uint32_t)std::min<long long>(g, ((long long)W + A.b - 1) / A.b);
+    if (A.vdepth() == 0) {
+        DevBuf<double> dtab((size_t)W + 1);
+        dtab.upload(table, (size_t)W + 1);
+        dispatch(A.dtype, [&](auto z) {
+            using T = decltype(z);
+            HB_LAUNCH(k_decay_fill<T>, 1, 256, 0, A.keys.p, A.b, n, W, dtab.p, seed, symmetric ? 1 : 0, (T*)A.tiles.p);
+        });
+        sync_stream();
+        return;
+    }
+    const size_t span = 2 * (size_t)wb + 1, cand = (size_t)(hi - lo) * span;
+    DevBuf<uint64_t> ck(cand);
+    DevBuf<uint32_t> ci(cand);
+    HB_LAUNCH(k_decay_keys, blocks_for(cand, 256), 256, 0, (uint32_t)lo, (uint32_t)hi, g, wb, ck.p);
+    // sort (invalid ~0 keys go last), count valid
+    HB_CUDA(cudaMemsetAsync(ci.p, 0, cand * sizeof(uint32_t), engine().stream));
+    radix_sort_pairs(ck.p, ci.p, cand, 64);
+    std::vector<uint64_t> hk = ck.to_host();
+    size_t L = 0;
+    while (L < cand && hk[L] != ~0ull) ++L;
+    if (L == 0) return;
+    DevBuf<uint64_t> keys(L);
+    HB_CUDA(cudaMemcpyAsync(keys.p, ck.p, L * sizeof(uint64_t), cudaMemcpyDeviceToDevice, engine().stream));
+    DevBuf<char> t(L * A.tile_bytes());
+    DevBuf<double> dtab((size_t)W + 1);
+    dtab.upload(table, (size_t)W + 1);
+    dispatch(A.dtype, [&](auto z) {
+        using T = decltype(z);
+        HB_LAUNCH(k_decay_fill<T>, (unsigned)L, 256, 0, keys.p, A.b, n, W, dtab.p, seed, symmetric ? 1 : 0, (T*)t.p);
+    });
+    A.set_table(std::move(keys), std::move(t), L);
+    sync_stream();
+}
+
+}  // namespace hbsm_b200

@@ -1,0 +1,96 @@
+// matrix.cuh -- the flat (Morton block table) replacement for the reference's pointer quadtree (H:37-60).
+//
+// HBM layout of one matrix:
+//   keys  [L]            uint64  ascending Morton keys of the existing leaf tiles (digit = 2*colbit + rowbit, H:52-56)
+//   tiles [L][b*b]       Treal   dense column-major tiles (H:715) in key order; for b in {32,64,128,256} every tile
+//                                starts on a 128-byte boundary (b*b*sizeof(Treal) is a multiple of 128)
+//   norms [L]            Treal   cached leaf ||.||_F^2 (frob_norm_squared_internal of the leaves, H:48); zero until
+//                                update_internal_info (H:3905) -- products/add/transpose leave it stale, as upstream
+// plus lazily built line indices (tiles grouped by block row or by block column) used by the task-list builder.
+#pragma once
+#include "common.cuh"
+
+namespace hbsm_b200 {
+
+// tiles grouped by line (block row or block column), inside a line ascending in the other coordinate
+struct LineIndex {
+    bool valid = false;
+    uint32_t n_lines = 0;
+    DevBuf<uint32_t> ptr;    // [n_lines + 1]
+    DevBuf<uint32_t> other;  // [L] the other block coordinate
+    DevBuf<uint32_t> tile;   // [L] index into keys/tiles/norms
+    void reset() { valid = false; n_lines = 0; ptr.release(); other.release(); tile.release(); }
+};
+
+struct Matrix {
+    int dtype = HBSM_F64;
+    int b = -1;
+    int M = 0, N = 0;
+    bool sized = false;
+    size_t L = 0;
+    DevBuf<uint64_t> keys;
+    DevBuf<char> tiles;
+    DevBuf<char> norms;
+    double root_norm_cached = 0.0;  // frob_norm_squared_internal of the root, stored exactly (float values fit)
+    size_t n_mults = 0;
+    LineIndex by_row, by_col;
+    // executed products of the call that produced this matrix (parity hook, hbsm_export_tasks)
+    DevBuf<uint64_t> task_begin;    // [L + 1]
+    DevBuf<uint32_t> task_k;        // [P]
+    size_t n_tasks = 0;
+
+    size_t esize() const { return dtype == HBSM_F64 ? 8 : 4; }
+    size_t tile_elems() const { return (size_t)b * (size_t)b; }
+    size_t tile_bytes() const { return tile_elems() * esize(); }
+    bool empty() const { return !sized; }
+    // virtual depth P (H:521-541): 0 when the matrix is a single leaf
+    int vdepth() const { return depth_for(M, N, b); }
+    static int depth_for(int m, int n, int bs) {
+        if (m <= bs && n <= bs) return 0;
+        int maxdim = m > n ? m : n;
+        int covers = maxdim / bs + (maxdim % bs != 0);
+        int P = 1, two = 2;
+        while (covers > two) { two *= 2; ++P; }
+        return P;
+    }
+    uint32_t grid_side() const { return 1u << vdepth(); }
+    void invalidate_indices() { by_row.reset(); by_col.reset(); }
+    void drop_tasks() { task_begin.release(); task_k.release(); n_tasks = 0; }
+    void clear();                     // H:614
+    void resize(int m, int n);        // H:544
+    void set_table(DevBuf<uint64_t>&& k, DevBuf<char>&& t, size_t count);  // adopt a sorted table, zero norms
+};
+
+// ---- matrix.cu ----
+void assign_coo(Matrix& A, size_t n, const int* rows, const int* cols, const void* vals, bool use_max, bool checked);
+void assign_tiles_host(Matrix& A, size_t n_tiles, const int* bi, const int* bj, const void* tiles);
+void assign_tiles_device(Matrix& A, size_t n_tiles, const uint64_t* d_keys, const void* d_tiles, const void* d_norms);
+void get_values(const Matrix& A, size_t n, const int* rows, const int* cols, void* out);
+size_t get_all_values(const Matrix& A, size_t cap, int* rows, int* cols, void* vals);
+size_t count_nnz(const Matrix& A);
+void compute_leaf_norms(const Matrix& A, void* d_out);   // bit-exact sequential sum per leaf (H:646-652)
+double hierarchical_norm(const Matrix& A, const void* d_leaf_norms);   // root value of H:3918-3923 / H:656-662
+void update_norms(Matrix& A);
+double frob_squared(const Matrix& A);
+const LineIndex& line_index(const Matrix& A, bool by_col);
+void op_add(const Matrix& A, const Matrix& B, Matrix& C);
+void op_transpose(const Matrix& A, Matrix& C);
+void op_upper(const Matrix& A, Matrix& C);
+void op_rescale(Matrix& C, const Matrix& A, double alpha);
+void op_copy(Matrix& C, const Matrix& A);
+void sym_expand(const Matrix& A, Matrix& S);             // S = triu(A) + striu(A)^T as a full matrix
+void mask_diag_upper(Matrix& C);                         // zero the strict lower part of diagonal tiles in place
+void generate_decay(Matrix& A, int n, const double* table, int W, uint64_t seed, bool symmetric, int lo, int hi);
+
+// ---- product.cu ----
+struct ProductOpts {
+    bool spamm = false;
+    double tau = 0.0;
+    bool updated = true;
+    bool upper_only = false;   // keep only C tiles with ci <= cj (symm_square / symm_rk)
+};
+void op_product(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, const ProductOpts& o,
+                size_t* n_mults, size_t* n_blocks);
+bool worth_product(const Matrix& A, bool tA, const Matrix& B, bool tB, bool spamm, double tau);
+
+}  // namespace hbsm_b200

@@ -1,0 +1,570 @@
+// product.cu -- multiply / SpAMM on the flat block table.
+//
+// Replaces the reference's two phases:
+//   symbolic  get_batches_multiply H:5478 / get_batches_spamm H:6291  -> task-list builder (count, scan, fill, sort by
+//             (Morton key of the C tile, k), segment heads = C's block table)
+//   numeric   multiply_batches H:7240 (+ BLAS gemm H:7273)            -> one persistent grouped leaf-GEMM kernel,
+//             C-stationary (a CTA owns a C tile for its whole k-list, no atomics on data), A/B tiles staged by TMA bulk
+//             copies into padded shared memory behind an mbarrier ring, FP64 DMMA (mma.sync m8n8k4) accumulation.
+//
+// Executed set: exact = every (ci,k,cj) with both tiles present; SpAMM additionally requires
+// fl(nsq(A_tile) * nsq(B_tile)) > fl(tau*tau) evaluated in Treal with a strict '>' (H:2008, H:6651).  The hierarchical
+// test of the reference collapses to this flat leaf-pair rule because node norms are sums of non-negative child norms.
+#include "matrix.cuh"
+
+namespace hbsm_b200 {
+
+namespace {
+
+inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// ---------------------------------------------------------------------------------------------------
+// task-list builder
+// ---------------------------------------------------------------------------------------------------
+struct JoinArgs {
+    const uint32_t* a_ptr; const uint32_t* a_other; const uint32_t* a_tile; uint32_t a_lines;   // op(A): line = ci, other = k
+    const uint32_t* b_ptr; const uint32_t* b_other; const uint32_t* b_tile; uint32_t b_lines;   // op(B): line = k, other = cj
+    const void* a_norms; const void* b_norms;
+    int spamm; int upper_only;
+    double tau2_d; float tau2_f;
+    size_t a_entries;
+};
+
+template <typename T> __device__ __forceinline__ bool spamm_keep(T na, T nb, const JoinArgs& g);
+template <> __device__ __forceinline__ bool spamm_keep<double>(double na, double nb, const JoinArgs& g) {
+    return __dmul_rn(na, nb) > g.tau2_d;
+}
+template <> __device__ __forceinline__ bool spamm_keep<float>(float na, float nb, const JoinArgs& g) {
+    return __fmul_rn(na, nb) > g.tau2_f;
+}
+
+// one warp per tile of op(A): walks row k of op(B).  FILL=false counts survivors, FILL=true writes them.
+template <typename T, bool FILL>
+__global__ void __launch_bounds__(256) k_join(JoinArgs g, const uint32_t* __restrict__ a_line_of_entry,
+                                               uint32_t* __restrict__ counts, const uint64_t* __restrict__ offsets,
+                                               int kbits, uint64_t* __restrict__ keys, uint32_t* __restrict__ pa,
+                                               uint32_t* __restrict__ pb, unsigned long long* __restrict__ n_cand) {
+    const unsigned lane = threadIdx.x & 31;
+    const size_t e = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (e >= g.a_entries) return;
+    const uint32_t ci = a_line_of_entry[e];
+    const uint32_t k = g.a_other[e];
+    const uint32_t ta = g.a_tile[e];
+    uint32_t beg = 0, end = 0;
+    if (k < g.b_lines) { beg = g.b_ptr[k]; end = g.b_ptr[k + 1]; }
+    T na = g.spamm ? reinterpret_cast<const T*>(g.a_norms)[ta] : (T)0;
+    uint32_t total = 0;
+    uint64_t base = FILL ? offsets[e] : 0;
+    for (uint32_t f0 = beg; f0 < end; f0 += 32) {
+        uint32_t f = f0 + lane;
+        bool keep = false;
+        uint32_t cj = 0, tb = 0;
+        if (f < end) {
+            cj = g.b_other[f];
+            tb = g.b_tile[f];
+            keep = true;
+            if (g.spamm) keep = spamm_keep<T>(na, reinterpret_cast<const T*>(g.b_norms)[tb], g);
+            if (g.upper_only && ci > cj) keep = false;
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (FILL && keep) {
+            uint64_t p = base + total + __popc(bal & ((1u << lane) - 1u));
+            keys[p] = (morton_encode(ci, cj) << kbits) | (uint64_t)k;
+            pa[p] = ta;
+            pb[p] = tb;
+        }
+        total += __popc(bal);
+    }
+    if (!FILL && lane == 0) {
+        counts[e] = total;
+        if (n_cand && end > beg) atomicAdd(n_cand, (unsigned long long)(end - beg));
+    }
+}
+
+// line number of every entry of a line index (inverse of ptr)
+__global__ void k_entry_lines(const uint32_t* __restrict__ ptr, uint32_t n_lines, uint32_t* __restrict__ line_of) {
+    uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_lines) return;
+    for (uint32_t e = ptr[l]; e < ptr[l + 1]; ++e) line_of[e] = l;
+}
+
+__global__ void k_iota(uint32_t* __restrict__ v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (uint32_t)i;
+}
+
+__global__ void k_task_heads(const uint64_t* __restrict__ keys, size_t n, int kbits, uint32_t* __restrict__ head) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    head[i] = (i == 0 || (keys[i - 1] >> kbits) != (keys[i] >> kbits)) ? 1u : 0u;
+}
+
+// sorted keys -> C block table, segment starts, gathered operand indices, k per task
+__global__ void k_task_finish(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ perm, size_t n, int kbits,
+                              const uint32_t* __restrict__ head, const uint64_t* __restrict__ pos,
+                              const uint32_t* __restrict__ pa, const uint32_t* __restrict__ pb,
+                              uint64_t* __restrict__ ckeys, uint64_t* __restrict__ begin, uint2* __restrict__ ab,
+                              uint32_t* __restrict__ task_k, size_t n_ctiles) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t key = keys[i];
+    if (head[i]) { ckeys[pos[i]] = key >> kbits; begin[pos[i]] = i; }
+    uint32_t src = perm[i];
+    ab[i] = make_uint2(pa[src], pb[src]);
+    task_k[i] = (uint32_t)(key & ((1ull << kbits) - 1ull));
+    if (i == n - 1) begin[n_ctiles] = n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// generic leaf GEMM (any blocksize, both dtypes): one CTA per C tile, plain FMA from global/L2.  Used for the
+// blocksizes without a tensor-pipe kernel and as the debug/parity variant (hbsm_set_gemm_variant(1)).
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_gemm_generic(const T* __restrict__ At, const T* __restrict__ Bt,
+                                                       const uint2* __restrict__ ab, const uint64_t* __restrict__ begin,
+                                                       int b, int tA, int tB, T* __restrict__ Ct) {
+    const size_t bb = (size_t)b * b;
+    const uint64_t p0 = begin[blockIdx.x], p1 = begin[blockIdx.x + 1];
+    T* C = Ct + (size_t)blockIdx.x * bb;
+    for (size_t idx = threadIdx.x; idx < bb; idx += blockDim.x) {
+        const int i = (int)(idx % b), j = (int)(idx / b);
+        T acc = 0;
+        for (uint64_t p = p0; p < p1; ++p) {
+            const T* A = At + (size_t)ab[p].x * bb;
+            const T* B = Bt + (size_t)ab[p].y * bb;
+            for (int l = 0; l < b; ++l) {
+                T a = tA ? A[(size_t)i * b + l] : A[(size_t)l * b + i];
+                T bv = tB ? B[(size_t)l * b + j] : B[(size_t)j * b + l];
+                acc = fma(a, bv, acc);
+            }
+        }
+        C[idx] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// FP64 leaf GEMM: persistent, warp-specialised, TMA bulk copies + mbarrier ring + DMMA
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// Shared-memory staging layout of one pipeline stage = one K-chunk (KC wide) of op(A) and of op(B).
+// Leaves are column-major with leading dimension BS (H:715), so a K-chunk is a set of contiguous "pieces":
+//   op(A) = A   : KC pieces (columns k) of BS doubles  -> smem [k][i], ld = BS + 4
+//   op(A) = A^T : BS pieces (columns i) of KC doubles  -> smem [i][k], ld = KC + 4
+//   op(B) = B   : BS pieces (columns n) of KC doubles  -> smem [n][k], ld = KC + 4
+//   op(B) = B^T : KC pieces (columns k) of BS doubles  -> smem [k][n], ld = BS + 4
+// ld == 4 (mod 16) doubles makes every DMMA fragment load (4 consecutive elements along one axis x 4 along the
+// other per half-warp) hit 16 distinct 8-byte banks: conflict-free for all four (tA,tB) without swizzling.
+template <int BS, int KC, bool TA, bool TB>
+struct GemmCfg {
+    static constexpr int LDA = TA ? KC + 4 : BS + 4;
+    static constexpr int A_PIECES = TA ? BS : KC;
+    static constexpr int A_PIECE_ELEMS = TA ? KC : BS;
+    static constexpr int A_ELEMS = A_PIECES * LDA;
+    static constexpr int LDB = TB ? BS + 4 : KC + 4;
+    static constexpr int B_PIECES = TB ? KC : BS;
+    static constexpr int B_PIECE_ELEMS = TB ? BS : KC;
+    static constexpr int B_ELEMS = B_PIECES * LDB;
+    static constexpr int STAGE_BYTES = (A_ELEMS + B_ELEMS) * 8;
+    static constexpr int TX_BYTES = 2 * BS * KC * 8;
+    static constexpr int NCHUNK = BS / KC;
+    static constexpr int SMEM_BUDGET = 220 * 1024;
+    static constexpr int NST_RAW = SMEM_BUDGET / STAGE_BYTES;
+    static constexpr int NST = NST_RAW > 8 ? 8 : NST_RAW;
+    static constexpr int CONSUMER_WARPS = 8;
+    static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+    static constexpr int WM = BS / 2, WN = BS / 4;   // warp grid 2 (rows) x 4 (cols)
+    static constexpr int MB = WM / 8, NB = WN / 8;
+    static constexpr int HEADER_BYTES = 1024;        // barriers + per-stage metadata
+    static constexpr int SMEM_BYTES = HEADER_BYTES + NST * STAGE_BYTES;
+    static_assert(NST >= 2, "pipeline needs two stages");
+    static_assert(BS % KC == 0 && KC % 16 == 0 && BS % 32 == 0, "tile shape");
+};
+
+struct GemmMeta { int ctile; int flags; };   // flags: 1 = first chunk of a C tile, 2 = last chunk, 4 = no more work
+
+template <int BS, int KC, bool TA, bool TB>
+__global__ void __launch_bounds__(GemmCfg<BS, KC, TA, TB>::THREADS, 1)
+k_gemm_f64(const double* __restrict__ At, const double* __restrict__ Bt, const uint2* __restrict__ ab,
+           const uint64_t* __restrict__ begin, uint32_t n_ctiles, unsigned* __restrict__ next_tile,
+           double* __restrict__ Ct) {
+    using Cfg = GemmCfg<BS, KC, TA, TB>;
+    constexpr int NST = Cfg::NST;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);           // [NST]
+    uint64_t* empty_bar = full_bar + NST;                             // [NST]
+    GemmMeta* meta = reinterpret_cast<GemmMeta*>(empty_bar + NST);    // [NST]
+    unsigned char* stages = smem + Cfg::HEADER_BYTES;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), Cfg::CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    constexpr size_t BB = (size_t)BS * BS;
+    if (warp == Cfg::CONSUMER_WARPS) {
+        // ===== producer warp: dynamic C-tile scheduler (Morton order => concurrently running CTAs share A rows /
+        // B columns in L2) + TMA bulk copies, running ahead of the consumers by up to NST chunks =====
+        uint32_t it = 0;
+        for (;;) {
+            unsigned tile = 0;
+            if (lane == 0) tile = atomicAdd(next_tile, 1u);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile >= n_ctiles) break;
+            const uint64_t p0 = begin[tile], p1 = begin[tile + 1];
+            for (uint64_t p = p0; p < p1; ++p) {
+                const uint2 t = ab[p];
+                const double* A = At + (size_t)t.x * BB;
+                const double* B = Bt + (size_t)t.y * BB;
+#pragma unroll 1
+                for (int ch = 0; ch < Cfg::NCHUNK; ++ch, ++it) {
+                    const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                    const uint32_t fb = smem_u32(&full_bar[s]);
+                    if (lane == 0) {
+                        int fl = 0;
+                        if (p == p0 && ch == 0) fl |= 1;
+                        if (p + 1 == p1 && ch == Cfg::NCHUNK - 1) fl |= 2;
+                        meta[s].ctile = (int)tile;
+                        meta[s].flags = fl;
+                        mbar_arrive_expect_tx(fb, Cfg::TX_BYTES);
+                    }
+                    __syncwarp();
+                    const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + Cfg::A_ELEMS * 8;
+                    const int k0 = ch * KC;
+                    for (int pc = lane; pc < Cfg::A_PIECES; pc += 32) {
+                        const double* src = TA ? A + (size_t)pc * BS + k0 : A + (size_t)(k0 + pc) * BS;
+                        tma_bulk_g2s(sa + pc * Cfg::LDA * 8, src, Cfg::A_PIECE_ELEMS * 8, fb);
+                    }
+                    for (int pc = lane; pc < Cfg::B_PIECES; pc += 32) {
+                        const double* src = TB ? B + (size_t)(k0 + pc) * BS : B + (size_t)pc * BS + k0;
+                        tma_bulk_g2s(sb + pc * Cfg::LDB * 8, src, Cfg::B_PIECE_ELEMS * 8, fb);
+                    }
+                }
+            }
+        }
+        // end-of-work marker
+        const uint32_t s = it % NST, ph = (it / NST) & 1u;
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        if (lane == 0) {
+            meta[s].ctile = -1;
+            meta[s].flags = 4;
+            mbar_arrive(smem_u32(&full_bar[s]));
+        }
+        return;
+    }
+
+    // ===== consumer warps: 2 x 4 warp grid over the BS x BS C tile, accumulators in registers =====
+    const int wm0 = (int)(warp >> 2) * Cfg::WM, wn0 = (int)(warp & 3) * Cfg::WN;
+    const int g = (int)(lane >> 2), t = (int)(lane & 3);
+    double acc[Cfg::MB][Cfg::NB][2];
+    // per-thread element offsets of fragment (mb=0 / nb=0, ks=0) inside a stage
+    const int a_off = TA ? (wm0 + g) * Cfg::LDA + t : t * Cfg::LDA + (wm0 + g);
+    const int b_off = TB ? t * Cfg::LDB + (wn0 + g) : (wn0 + g) * Cfg::LDB + t;
+    constexpr int A_MB_STRIDE = TA ? 8 * Cfg::LDA : 8;          // +8 rows of op(A)
+    constexpr int A_KS_STRIDE = TA ? 4 : 4 * Cfg::LDA;          // +4 in k
+    constexpr int B_NB_STRIDE = TB ? 8 : 8 * Cfg::LDB;          // +8 columns of op(B)
+    constexpr int B_KS_STRIDE = TB ? 4 * Cfg::LDB : 4;
+    uint32_t it = 0;
+    for (;; ++it) {
+        const uint32_t s = it % NST, ph = (it / NST) & 1u;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        const GemmMeta m = meta[s];
+        if (m.flags & 4) break;
+        if (m.flags & 1) {
+#pragma unroll
+            for (int i = 0; i < Cfg::MB; ++i)
+#pragma unroll
+                for (int j = 0; j < Cfg::NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        }
+        const double* As = reinterpret_cast<const double*>(stages + (size_t)s * Cfg::STAGE_BYTES) + a_off;
+        const double* Bs = reinterpret_cast<const double*>(stages + (size_t)s * Cfg::STAGE_BYTES) + Cfg::A_ELEMS + b_off;
+#pragma unroll
+        for (int ks = 0; ks < KC / 4; ++ks) {
+            double a[Cfg::MB], b[Cfg::NB];
+#pragma unroll
+            for (int i = 0; i < Cfg::MB; ++i) a[i] = As[i * A_MB_STRIDE + ks * A_KS_STRIDE];
+#pragma unroll
+            for (int j = 0; j < Cfg::NB; ++j) b[j] = Bs[j * B_NB_STRIDE + ks * B_KS_STRIDE];
+#pragma unroll
+            for (int i = 0; i < Cfg::MB; ++i)
+#pragma unroll
+                for (int j = 0; j < Cfg::NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&empty_bar[s]));
+        if (m.flags & 2) {
+            double* C = Ct + (size_t)m.ctile * BB;
+#pragma unroll
+            for (int i = 0; i < Cfg::MB; ++i)
+#pragma unroll
+                for (int j = 0; j < Cfg::NB; ++j) {
+                    const int row = wm0 + i * 8 + g, col = wn0 + j * 8 + 2 * t;
+                    C[(size_t)col * BS + row] = acc[i][j][0];
+                    C[(size_t)(col + 1) * BS + row] = acc[i][j][1];
+                }
+        }
+    }
+}
+
+template <int BS, int KC, bool TA, bool TB>
+void launch_gemm_f64_inst(const double* At, const double* Bt, const uint2* ab, const uint64_t* begin, uint32_t n_ctiles,
+                          unsigned* counter, double* Ct) {
+    using Cfg = GemmCfg<BS, KC, TA, TB>;
+    auto kfn = k_gemm_f64<BS, KC, TA, TB>;
+    static bool configured = false;
+    if (!configured) {
+        HB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    unsigned grid = std::min<unsigned>(n_ctiles, (unsigned)engine().sm_count);
+    HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, At, Bt, ab, begin, n_ctiles, counter, Ct);
+}
+
+template <int BS, int KC>
+void launch_gemm_f64(bool tA, bool tB, const double* At, const double* Bt, const uint2* ab, const uint64_t* begin,
+                     uint32_t n_ctiles, unsigned* counter, double* Ct) {
+    if (!tA && !tB) launch_gemm_f64_inst<BS, KC, false, false>(At, Bt, ab, begin, n_ctiles, counter, Ct);
+    else if (!tA && tB) launch_gemm_f64_inst<BS, KC, false, true>(At, Bt, ab, begin, n_ctiles, counter, Ct);
+    else if (tA && !tB) launch_gemm_f64_inst<BS, KC, true, false>(At, Bt, ab, begin, n_ctiles, counter, Ct);
+    else launch_gemm_f64_inst<BS, KC, true, true>(At, Bt, ab, begin, n_ctiles, counter, Ct);
+}
+
+struct TaskList {
+    size_t n_products = 0, n_ctiles = 0;
+    unsigned long long n_candidates = 0;
+    DevBuf<uint64_t> ckeys;    // [n_ctiles] ascending Morton keys of C's tiles
+    DevBuf<uint64_t> begin;    // [n_ctiles + 1]
+    DevBuf<uint2> ab;          // [P] (A tile, B tile), grouped by C tile, k ascending inside a group
+    DevBuf<uint32_t> task_k;   // [P]
+};
+
+// builds the executed-product list; returns with the stream synchronised
+void build_tasks(const Matrix& A, bool tA, const Matrix& B, bool tB, const ProductOpts& o, int kbits, TaskList& tl,
+                 bool count_only) {
+    const LineIndex& la = line_index(A, tA);   // op(A): lines are C rows
+    const LineIndex& lb = line_index(B, tB);   // op(B): lines are k
+    tl.n_products = tl.n_ctiles = 0;
+    tl.n_candidates = 0;
+    if (A.L == 0 || B.L == 0) return;
+    JoinArgs g{};
+    g.a_ptr = la.ptr.p; g.a_other = la.other.p; g.a_tile = la.tile.p; g.a_lines = la.n_lines;
+    g.b_ptr = lb.ptr.p; g.b_other = lb.other.p; g.b_tile = lb.tile.p; g.b_lines = lb.n_lines;
+    g.a_norms = A.norms.p; g.b_norms = B.norms.p;
+    g.spamm = o.spamm ? 1 : 0;
+    g.upper_only = o.upper_only ? 1 : 0;
+    g.tau2_d = o.tau * o.tau;                       // fl(tau*tau) in Treal, H:2008
+    { float tf = (float)o.tau; g.tau2_f = tf * tf; }
+    g.a_entries = A.L;
+    DevBuf<uint32_t> line_of(A.L), counts(A.L);
+    HB_LAUNCH(k_entry_lines, blocks_for(la.n_lines, 256), 256, 0, la.ptr.p, la.n_lines, line_of.p);
+    DevBuf<unsigned long long> ncand(1);
+    ncand.zero();
+    const unsigned jgrid = blocks_for(A.L * 32, 256);
+    if (A.dtype == HBSM_F64) {
+        auto kfn = k_join<double, false>;
+        HB_LAUNCH(kfn, jgrid, 256, 0, g, line_of.p, counts.p, (const uint64_t*)nullptr, kbits, (uint64_t*)nullptr,
+                  (uint32_t*)nullptr, (uint32_t*)nullptr, ncand.p);
+    } else {
+        auto kfn = k_join<float, false>;
+        HB_LAUNCH(kfn, jgrid, 256, 0, g, line_of.p, counts.p, (const uint64_t*)nullptr, kbits, (uint64_t*)nullptr,
+                  (uint32_t*)nullptr, (uint32_t*)nullptr, ncand.p);
+    }
+    DevBuf<uint64_t> offs(A.L + 1);
+    exclusive_scan_u32(counts.p, offs.p, A.L);
+    uint64_t P = 0;
+    HB_CUDA(cudaMemcpyAsync(&P, offs.p + A.L, sizeof(uint64_t), cudaMemcpyDeviceToHost, engine().stream));
+    HB_CUDA(cudaMemcpyAsync(&tl.n_candidates, ncand.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, engine().stream));
+    sync_stream();
+    tl.n_products = (size_t)P;
+    if (P == 0 || count_only) return;
+    if (P >= 0xffffffffull) throw Error(HBSM_E_ARG, "hbsm_b200: more than 2^32-1 leaf products in one call");
+    DevBuf<uint64_t> keys(P);
+    DevBuf<uint32_t> pa(P), pb(P), perm(P);
+    if (A.dtype == HBSM_F64) {
+        auto kfn = k_join<double, true>;
+        HB_LAUNCH(kfn, jgrid, 256, 0, g, line_of.p, (uint32_t*)nullptr, offs.p, kbits, keys.p, pa.p, pb.p,
+                  (unsigned long long*)nullptr);
+    } else {
+        auto kfn = k_join<float, true>;
+        HB_LAUNCH(kfn, jgrid, 256, 0, g, line_of.p, (uint32_t*)nullptr, offs.p, kbits, keys.p, pa.p, pb.p,
+                  (unsigned long long*)nullptr);
+    }
+    HB_LAUNCH(k_iota, blocks_for(P, 256), 256, 0, perm.p, (size_t)P);
+    radix_sort_pairs(keys.p, perm.p, P, 3 * kbits);
+    DevBuf<uint32_t> head(P);
+    HB_LAUNCH(k_task_heads, blocks_for(P, 256), 256, 0, keys.p, (size_t)P, kbits, head.p);
+    DevBuf<uint64_t> pos(P + 1);
+    exclusive_scan_u32(head.p, pos.p, P);
+    uint64_t nct = 0;
+    HB_CUDA(cudaMemcpyAsync(&nct, pos.p + P, sizeof(uint64_t), cudaMemcpyDeviceToHost, engine().stream));
+    sync_stream();
+    tl.n_ctiles = (size_t)nct;
+    tl.ckeys.alloc(nct);
+    tl.begin.alloc(nct + 1);
+    tl.ab.alloc(P);
+    tl.task_k.alloc(P);
+    HB_LAUNCH(k_task_finish, blocks_for(P, 256), 256, 0, keys.p, perm.p, (size_t)P, kbits, head.p, pos.p, pa.p, pb.p,
+              tl.ckeys.p, tl.begin.p, tl.ab.p, tl.task_k.p, (size_t)nct);
+}
+
+int coord_bits(const Matrix& A, const Matrix& B, int cm, int cn, int b) {
+    int d = std::max(A.vdepth(), B.vdepth());
+    d = std::max(d, Matrix::depth_for(cm, cn, b));
+    return std::max(d, 1);
+}
+
+void check_operands(const Matrix& A, bool tA, const Matrix& B, bool tB, const Matrix& C, bool spamm, int& AM, int& BN) {
+    const char* fn = spamm ? "get_batches_spamm" : "get_batches_multiply";
+    char msg[200];
+    if (!C.empty()) {   // H:5681 / H:6493
+        snprintf(msg, sizeof msg, "Error in HierarchicalBlockSparseMatrix::%s(): non-empty matrix to write result!%s", fn,
+                 spamm ? "" : " wow");
+        throw_ref(msg);
+    }
+    if (A.empty() || B.empty()) throw Error(HBSM_E_ARG, "hbsm_b200: product of an empty (unsized) matrix");
+    if (A.dtype != B.dtype || A.b != B.b) throw Error(HBSM_E_ARG, "hbsm_b200: operands differ in dtype or blocksize");
+    AM = tA ? A.N : A.M;
+    const int AN = tA ? A.M : A.N, BM = tB ? B.N : B.M;
+    BN = tB ? B.M : B.N;
+    if (AN != BM) {   // H:5703, H:5730, H:5756, H:5781
+        snprintf(msg, sizeof msg, "Error in HierarchicalBlockSparseMatrix::%s(): matrices have bad sizes!", fn);
+        throw_ref(msg);
+    }
+}
+
+}  // namespace
+
+bool worth_product(const Matrix& A, bool tA, const Matrix& B, bool tB, bool spamm, double tau) {
+    if (A.empty() || B.empty()) return false;
+    ensure_engine();
+    ProductOpts o;
+    o.spamm = spamm;
+    o.tau = tau;
+    TaskList tl;
+    int kb = coord_bits(A, B, 1, 1, A.b);
+    build_tasks(A, tA, B, tB, o, kb, tl, true);
+    return tl.n_products > 0;
+}
+
+void op_product(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, const ProductOpts& o, size_t* n_mults,
+                size_t* n_blocks) {
+    int AM = 0, BN = 0;
+    check_operands(A, tA, B, tB, C, o.spamm, AM, BN);
+    ensure_engine();
+    Engine& e = engine();
+    hbsm_stage_times st{};
+    const uint64_t launches0 = e.launches;
+    EventTimer t_total, t_norm, t_index, t_task, t_gemm;
+    t_total.start();
+    C.dtype = A.dtype;
+    C.b = A.b;
+    C.resize(AM, BN);
+    const int kbits = coord_bits(A, B, AM, BN, A.b);
+    if (3 * kbits > 64) throw Error(HBSM_E_ARG, "hbsm_b200: block grid too deep for 64-bit task keys (depth > 21)");
+
+    t_norm.start();
+    if (o.spamm && !o.updated) {   // the reference's updated=false path is a use-after-free (H:6294-6307): refresh instead
+        update_norms(const_cast<Matrix&>(A));
+        if (&B != &A) update_norms(const_cast<Matrix&>(B));
+    }
+    t_norm.stop();
+    t_index.start();
+    line_index(A, tA);
+    line_index(B, tB);
+    t_index.stop();
+
+    t_task.start();
+    TaskList tl;
+    build_tasks(A, tA, B, tB, o, kbits, tl, false);
+    t_task.stop();
+
+    t_gemm.start();
+    if (tl.n_products > 0) {
+        const size_t nct = tl.n_ctiles;
+        DevBuf<char> ct(nct * C.tile_bytes());
+        const bool fast64 = A.dtype == HBSM_F64 && e.gemm_variant == 0 && (A.b == 32 || A.b == 64 || A.b == 128);
+        if (fast64) {
+            DevBuf<unsigned> counter(1);
+            counter.zero();
+            const double* At = (const double*)A.tiles.p;
+            const double* Bt = (const double*)B.tiles.p;
+            if (A.b == 64) launch_gemm_f64<64, 64>(tA, tB, At, Bt, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
+            else if (A.b == 32) launch_gemm_f64<32, 32>(tA, tB, At, Bt, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
+            else launch_gemm_f64<128, 32>(tA, tB, At, Bt, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
+            t_gemm.stop();   // `counter` is released in stream order
+        } else {
+            if (A.dtype == HBSM_F64) {
+                auto kfn = k_gemm_generic<double>;
+                HB_LAUNCH(kfn, (unsigned)nct, 256, 0, (const double*)A.tiles.p, (const double*)B.tiles.p, tl.ab.p, tl.begin.p,
+                          A.b, tA ? 1 : 0, tB ? 1 : 0, (double*)ct.p);
+            } else {
+                auto kfn = k_gemm_generic<float>;
+                HB_LAUNCH(kfn, (unsigned)nct, 256, 0, (const float*)A.tiles.p, (const float*)B.tiles.p, tl.ab.p, tl.begin.p,
+                          A.b, tA ? 1 : 0, tB ? 1 : 0, (float*)ct.p);
+            }
+            t_gemm.stop();
+        }
+        C.set_table(std::move(tl.ckeys), std::move(ct), nct);
+        C.task_begin = std::move(tl.begin);
+        C.task_k = std::move(tl.task_k);
+        C.n_tasks = tl.n_products;
+    } else {
+        t_gemm.stop();
+    }
+    t_total.stop();
+    sync_stream();
+    C.n_mults = tl.n_products;   // H:2194 / H:3984
+    if (n_mults) *n_mults = tl.n_products;
+    if (n_blocks) *n_blocks = C.L;   // get_n_blocks(), H:7311
+    st.norms_ms = t_norm.ms();
+    st.index_ms = t_index.ms();
+    st.tasklist_ms = t_task.ms();
+    st.gemm_ms = t_gemm.ms();
+    st.total_ms = t_total.ms();
+    st.n_candidates = tl.n_candidates;
+    st.n_products = tl.n_products;
+    st.n_ctiles = tl.n_ctiles;
+    st.gpu_launches = e.launches - launches0;
+    e.last = st;
+}
+
+}  // namespace hbsm_b200

@@ -1,0 +1,143 @@
+/* hbsm_b200.h -- C ABI of the B200-native engine for the quadtree multiply / SpAMM / add hot path of
+ * toxaart/hierarchical_block_sparse_lib.
+ *
+ * The reference has no FFI layer: its boundary is the public section of the header-only class
+ * hbsm::HierarchicalBlockSparseMatrix<Treal> (reference source/HierarchicalBlockSparseMatrix.h:166-428,
+ * cited below as H:<line>).  Each entry point here is what a binding of that class would call; the
+ * drop-in C++ class over this ABI is include/hbsm/HierarchicalBlockSparseMatrix.h.
+ *
+ * Conventions: every function returns 0 on success or an HBSM_E_* code; hbsm_last_error() returns the
+ * thread-local message (the reference's own exception text where one exists).  All pointers are HOST
+ * pointers unless the parameter name starts with d_.  `void*` value buffers hold double (HBSM_F64) or
+ * float (HBSM_F32) according to the handle's dtype.  Calls are synchronous with respect to returned host
+ * data.  There is NO CPU fallback: every call fails with HBSM_E_CUDA if no sm_100 device is usable.
+ */
+#ifndef HBSM_B200_H
+#define HBSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef struct hbsm_matrix_s* hbsm_handle;
+
+enum { HBSM_F64 = 0, HBSM_F32 = 1 };
+
+enum {
+    HBSM_OK = 0,
+    HBSM_E_CUDA = 1,      /* CUDA runtime / no device */
+    HBSM_E_ARG = 2,       /* invalid argument */
+    HBSM_E_RUNTIME = 3    /* the reference would throw std::runtime_error; message in hbsm_last_error() */
+};
+
+/* Stage timings (milliseconds, CUDA events on the engine stream) of the most recent product call. */
+typedef struct hbsm_stage_times_s {
+    double norms_ms;      /* leaf norm refresh inside the call (0 when updated=true) */
+    double index_ms;      /* row/column line indices of op(A), op(B) */
+    double tasklist_ms;   /* count + fill + C table ordering */
+    double gemm_ms;       /* leaf GEMM kernel(s) */
+    double total_ms;      /* whole call, first kernel to last */
+    uint64_t n_candidates;/* Q: leaf pairs tested */
+    uint64_t n_products;  /* P: leaf products executed */
+    uint64_t n_ctiles;    /* tiles of C */
+    uint64_t gpu_launches;/* kernels launched by the call */
+} hbsm_stage_times;
+
+/* ---- library ---- */
+int hbsm_init(int device);                 /* select device, create the engine stream; idempotent */
+int hbsm_finalize(void);
+const char* hbsm_last_error(void);
+int hbsm_device_info(char* name, size_t cap, int* sm_count, int* cc_major, int* cc_minor);
+uint64_t hbsm_kernel_launch_count(void);   /* kernels launched by this library since init */
+
+/* ---- lifetime, sizing (ctor/dtor H:171-178, set_params H:186, resize H:194, clear H:196) ---- */
+int hbsm_create(int dtype, hbsm_handle* out);
+int hbsm_destroy(hbsm_handle h);
+int hbsm_set_blocksize(hbsm_handle h, int blocksize);     /* H:450: throws unless empty */
+int hbsm_get_blocksize(hbsm_handle h, int* blocksize);    /* H:457 */
+int hbsm_resize(hbsm_handle h, int n_rows, int n_cols);   /* H:544 */
+int hbsm_clear(hbsm_handle h);                            /* H:614 */
+int hbsm_is_empty(hbsm_handle h, int* out);               /* H:470 */
+int hbsm_children_exist(hbsm_handle h, int* out);         /* H:464 */
+int hbsm_dims(hbsm_handle h, int* n_rows, int* n_cols);   /* H:588, H:601 */
+int hbsm_depth(hbsm_handle h, int* out);                  /* H:496 */
+int hbsm_expected_depth(hbsm_handle h, int* out);         /* H:521 */
+int hbsm_is_consistent(hbsm_handle h, int* out);          /* H:1809 */
+int hbsm_dtype(hbsm_handle h, int* out);
+
+/* ---- assembly / readback (H:668-849, H:852-1121) ---- */
+int hbsm_assign_coo(hbsm_handle h, size_t n, const int* rows, const int* cols, const void* vals,
+                    int use_max, int boundaries_checked);
+/* bulk path: whole dense column-major tiles, tile t at block coordinates (bi[t], bj[t]); coordinates unique */
+int hbsm_assign_tiles(hbsm_handle h, size_t n_tiles, const int* bi, const int* bj, const void* tiles);
+int hbsm_get_values(hbsm_handle h, size_t n, const int* rows, const int* cols, void* out);      /* H:1012 */
+int hbsm_get_all_values(hbsm_handle h, size_t cap, int* rows, int* cols, void* vals, size_t* n); /* H:1034; cap=0 -> count */
+int hbsm_nnz(hbsm_handle h, size_t* out);                 /* H:985 */
+int hbsm_n_blocks(hbsm_handle h, size_t* out);            /* H:7311 */
+int hbsm_get_n_block_multiplications(hbsm_handle h, size_t* out);   /* H:218 */
+int hbsm_set_n_block_multiplications(hbsm_handle h, size_t n);      /* H:220 */
+
+/* ---- norms (H:641 get_frob_squared, H:3905 update_internal_info, H:216 cached getter) ---- */
+int hbsm_update_norms(hbsm_handle h);
+int hbsm_frob_squared(hbsm_handle h, void* out);
+int hbsm_frob_squared_cached(hbsm_handle h, void* out);
+
+/* ---- products (multiply H:2142/H:260, spamm H:3931/H:305) ---- */
+int hbsm_multiply(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C,
+                  size_t* n_block_multiplies, size_t* n_resizes);
+int hbsm_spamm(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, double tau, int updated,
+               size_t* n_block_multiplies, size_t* n_resizes);
+int hbsm_worth_to_multiply(hbsm_handle A, int tA, hbsm_handle B, int tB, int* out);             /* H:1873 */
+int hbsm_worth_to_spamm(hbsm_handle A, int tA, hbsm_handle B, int tB, double tau, int* out);    /* H:2006 */
+
+/* ---- structure ops (add H:1644, transpose H:3733, get_upper_triangle H:3515, rescale H:3078, copy H:1490) ---- */
+int hbsm_add(hbsm_handle A, hbsm_handle B, hbsm_handle C);
+int hbsm_transpose(hbsm_handle A, hbsm_handle C);
+int hbsm_upper_triangle(hbsm_handle A, hbsm_handle C);
+int hbsm_rescale(hbsm_handle C, hbsm_handle A, double alpha);
+int hbsm_copy(hbsm_handle C, hbsm_handle A);
+
+/* ---- symmetric family, exact (symm_multiply H:3244, symm_square H:3563, symm_rk H:3711) ---- */
+int hbsm_symm_multiply(hbsm_handle A, int sA, hbsm_handle B, int sB, hbsm_handle C);
+int hbsm_symm_square(hbsm_handle A, hbsm_handle C);
+int hbsm_symm_rk(hbsm_handle A, int transposed, hbsm_handle C);
+/* SpAMM-pruned symmetric square: triu(spamm(sym(A), sym(A), tau)) -- BASELINE config 3's tau sweep */
+int hbsm_symm_square_spamm(hbsm_handle A, hbsm_handle C, double tau, size_t* n_block_multiplies, size_t* n_resizes);
+
+/* ---- parity / bench hooks ---- */
+/* executed products of the call that produced C, sorted by (Morton key of (ci,cj), k); cap=0 -> count */
+int hbsm_export_tasks(hbsm_handle C, size_t cap, int64_t* ci, int64_t* cj, int64_t* k, size_t* n);
+/* leaves in ascending Morton order; norms/tiles may be NULL; cap=0 -> count */
+int hbsm_export_leaves(hbsm_handle h, size_t cap, int64_t* bi, int64_t* bj, void* norms_cached, void* tiles, size_t* n);
+int hbsm_stage_times_last(hbsm_stage_times* out);
+int hbsm_set_gemm_variant(int variant);    /* 0 = auto (fastest valid), 1 = generic scalar kernel (debug/parity) */
+
+/* ---- device-side interface (multi-GPU plumbing, device-resident benchmarks) ---- */
+/* borrowed pointers into the matrix's device block table: valid until the matrix is modified */
+int hbsm_device_table(hbsm_handle h, size_t* n_tiles, const uint64_t** d_morton_keys, const void** d_norms,
+                      const void** d_tiles);
+/* build a matrix from device arrays (keys need not be sorted; tiles column-major, b*b each); copies */
+int hbsm_assign_device_tiles(hbsm_handle h, size_t n_tiles, const uint64_t* d_morton_keys, const void* d_tiles,
+                             const void* d_norms_or_null);
+/* banded decay generator a_ij = (0.5+0.5u(seed,i,j)) * table[|i-j|], |i-j| <= W (table has W+1 entries, e.g.
+ * exp(-lambda d)), built on device; u = splitmix64 hash -> [0,1); symmetric != 0 uses u(seed,min,max).
+ * Tile rows [row_tile_lo,row_tile_hi) only (shard); full matrix with 0,-1. */
+int hbsm_generate_decay(hbsm_handle h, int n, const double* table, int W, uint64_t seed, int symmetric,
+                        int row_tile_lo, int row_tile_hi);
+uint64_t hbsm_morton_encode(uint32_t bi, uint32_t bj);
+void hbsm_morton_decode(uint64_t key, uint32_t* bi, uint32_t* bj);
+void* hbsm_stream(void);                  /* cudaStream_t of the engine */
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* HBSM_B200_H */
