@@ -18,7 +18,8 @@ HBSM_OK, HBSM_E_CUDA, HBSM_E_ARG, HBSM_E_RUNTIME = 0, 1, 2, 3
 class StageTimes(C.Structure):
     _fields_ = [("norms_ms", C.c_double), ("index_ms", C.c_double), ("tasklist_ms", C.c_double),
                 ("gemm_ms", C.c_double), ("total_ms", C.c_double), ("n_candidates", C.c_uint64),
-                ("n_products", C.c_uint64), ("n_ctiles", C.c_uint64), ("gpu_launches", C.c_uint64)]
+                ("n_products", C.c_uint64), ("n_ctiles", C.c_uint64), ("gpu_launches", C.c_uint64),
+                ("gemm_kernel", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

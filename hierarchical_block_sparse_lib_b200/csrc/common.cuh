@@ -38,7 +38,8 @@ struct Engine {
     uint64_t launches = 0;  // kernels launched by this library
     bool ready = false;
     std::string name;
-    int gemm_variant = 0;
+    int gemm_variant = 0;      // 0 auto (TMA-tiled DMMA), 1 generic scalar kernel, 2 bulk-copy DMMA kernel
+    int last_gemm_kernel = 0;  // which leaf kernel the last product ran: 0 generic, 1 TMA-tiled DMMA, 2 bulk-copy DMMA
     hbsm_stage_times last{};
 };
 Engine& engine();

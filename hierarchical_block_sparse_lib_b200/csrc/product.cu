@@ -11,6 +11,7 @@
 // fl(nsq(A_tile) * nsq(B_tile)) > fl(tau*tau) evaluated in Treal with a strict '>' (H:2008, H:6651).  The hierarchical
 // test of the reference collapses to this flat leaf-pair rule because node norms are sums of non-negative child norms.
 #include "matrix.cuh"
+#include <cuda.h>   // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 
 namespace hbsm_b200 {
 
@@ -368,6 +369,227 @@ void launch_gemm_f64(bool tA, bool tB, const double* At, const double* Bt, const
     else launch_gemm_f64_inst<BS, KC, true, true>(At, Bt, ab, begin, n_ctiles, counter, Ct);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// FP64 leaf GEMM, TMA-tiled variant (the default): one cp.async.bulk.tensor per operand chunk.
+//
+// A leaf (column-major, ld = BS) is described to TMA as the 4-D tensor  [tile][r/4][c][r%4]  (innermost last), i.e.
+//   dim0 = r % 4 (stride 8 B), dim1 = c (stride BS*8 B), dim2 = r / 4 (stride 32 B), dim3 = tile (stride BS*BS*8 B).
+// A box {4, NC, NR4, 1} therefore lands in shared memory as  smem[(r/4)][c][r%4]: every group of 4 consecutive rows
+// of 4 consecutive columns is 16 consecutive doubles = 128 contiguous bytes.  A DMMA m8n8k4 fragment is exactly
+// "4 consecutive indices along one leaf axis x 4 along the other" per half-warp, for the plain AND the transposed
+// operand, so every fragment load is one conflict-free 128-byte wavefront per half-warp -- no padding, no swizzle,
+// and a whole operand chunk is ONE TMA instruction issued by one thread.
+//   k along leaf columns (A as is, B transposed): box {4, KC, BS/4}, element (x, k) at  x%4 + 4*k + 4*KC*(x/4)
+//   k along leaf rows    (A transposed, B as is): box {4, BS, KC/4}, element (x, k) at  k%4 + 4*x + 4*BS*(k/4)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_tile_g2s(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                             uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
+
+template <int BS, int KC>
+struct TmaCfg {
+    static constexpr int CHUNK_ELEMS = BS * KC;
+    static constexpr int STAGE_BYTES = 2 * CHUNK_ELEMS * 8;
+    static constexpr int NCHUNK = BS / KC;
+    static constexpr int SMEM_BUDGET = 216 * 1024;
+    static constexpr int NST_RAW = SMEM_BUDGET / STAGE_BYTES;
+    static constexpr int NST = NST_RAW > 8 ? 8 : NST_RAW;
+    static constexpr int CONSUMER_WARPS = 8;
+    static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+    static constexpr int WM = BS / 2, WN = BS / 4;
+    static constexpr int MB = WM / 8, NB = WN / 8;
+    static constexpr int HEADER_BYTES = 1024;
+    static constexpr int SMEM_BYTES = HEADER_BYTES + NST * STAGE_BYTES + 1024;   // +1024: manual 1 KiB alignment
+    static_assert(NST >= 2, "pipeline needs two stages");
+};
+
+template <int BS, int KC, bool TA, bool TB>
+__global__ void __launch_bounds__(TmaCfg<BS, KC>::THREADS, 1)
+k_gemm_f64_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const uint2* __restrict__ ab, const uint64_t* __restrict__ begin, uint32_t n_ctiles,
+               unsigned* __restrict__ next_tile, double* __restrict__ Ct) {
+    using Cfg = TmaCfg<BS, KC>;
+    constexpr int NST = Cfg::NST;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty_bar = full_bar + NST;
+    GemmMeta* meta = reinterpret_cast<GemmMeta*>(empty_bar + NST);
+    unsigned char* stages = smem + Cfg::HEADER_BYTES;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), Cfg::CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    constexpr size_t BB = (size_t)BS * BS;
+    if (warp == Cfg::CONSUMER_WARPS) {
+        // ===== producer: one elected lane walks the task list and issues two TMA tile copies per chunk =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+            uint32_t it = 0;
+            for (;;) {
+                const unsigned tile = atomicAdd(next_tile, 1u);
+                if (tile >= n_ctiles) break;
+                const uint64_t p0 = begin[tile], p1 = begin[tile + 1];
+                uint2 t = ab[p0];
+                for (uint64_t p = p0; p < p1; ++p) {
+                    const uint2 tn = (p + 1 < p1) ? ab[p + 1] : t;   // prefetch the next pair
+#pragma unroll 1
+                    for (int ch = 0; ch < Cfg::NCHUNK; ++ch, ++it) {
+                        const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                        const uint32_t fb = smem_u32(&full_bar[s]);
+                        int fl = 0;
+                        if (p == p0 && ch == 0) fl |= 1;
+                        if (p + 1 == p1 && ch == Cfg::NCHUNK - 1) fl |= 2;
+                        meta[s].ctile = (int)tile;
+                        meta[s].flags = fl;
+                        mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
+                        const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
+                        const uint32_t sb = sa + Cfg::CHUNK_ELEMS * 8;
+                        const int k0 = ch * KC;
+                        if (TA) tma_tile_g2s(sa, &mapA, 0, 0, k0 / 4, (int)t.x, fb);   // k along leaf rows
+                        else    tma_tile_g2s(sa, &mapA, 0, k0, 0, (int)t.x, fb);       // k along leaf columns
+                        if (TB) tma_tile_g2s(sb, &mapB, 0, k0, 0, (int)t.y, fb);
+                        else    tma_tile_g2s(sb, &mapB, 0, 0, k0 / 4, (int)t.y, fb);
+                    }
+                    t = tn;
+                }
+            }
+            const uint32_t s = it % NST, ph = (it / NST) & 1u;
+            mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+            meta[s].ctile = -1;
+            meta[s].flags = 4;
+            mbar_arrive(smem_u32(&full_bar[s]));
+        }
+        return;
+    }
+
+    // ===== consumers: 2 x 4 warp grid, DMMA m8n8k4, accumulators in registers =====
+    const int wm0 = (int)(warp >> 2) * Cfg::WM, wn0 = (int)(warp & 3) * Cfg::WN;
+    const int g = (int)(lane >> 2), t = (int)(lane & 3);
+    double acc[Cfg::MB][Cfg::NB][2];
+    // A: x = row of op(A) = wm0 + 8*mb + g ; B: x = column of op(B) = wn0 + 8*nb + g ; k = 4*ks + t
+    const int a_off = TA ? (t + 4 * (wm0 + g)) : ((g & 3) + 4 * t + 4 * KC * ((wm0 >> 2) + (g >> 2)));
+    const int b_off = TB ? ((g & 3) + 4 * t + 4 * KC * ((wn0 >> 2) + (g >> 2))) : (t + 4 * (wn0 + g));
+    constexpr int A_BLK = TA ? 32 : 8 * KC;
+    constexpr int A_KS = TA ? 4 * BS : 16;
+    constexpr int B_BLK = TB ? 8 * KC : 32;
+    constexpr int B_KS = TB ? 16 : 4 * BS;
+    uint32_t it = 0;
+    for (;; ++it) {
+        const uint32_t s = it % NST, ph = (it / NST) & 1u;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        const GemmMeta m = meta[s];
+        if (m.flags & 4) break;
+        if (m.flags & 1) {
+#pragma unroll
+            for (int i = 0; i < Cfg::MB; ++i)
+#pragma unroll
+                for (int j = 0; j < Cfg::NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        }
+        const double* As = reinterpret_cast<const double*>(stages + (size_t)s * Cfg::STAGE_BYTES) + a_off;
+        const double* Bs = reinterpret_cast<const double*>(stages + (size_t)s * Cfg::STAGE_BYTES) + Cfg::CHUNK_ELEMS + b_off;
+#pragma unroll
+        for (int ks = 0; ks < KC / 4; ++ks) {
+            double a[Cfg::MB], b[Cfg::NB];
+#pragma unroll
+            for (int i = 0; i < Cfg::MB; ++i) a[i] = As[i * A_BLK + ks * A_KS];
+#pragma unroll
+            for (int j = 0; j < Cfg::NB; ++j) b[j] = Bs[j * B_BLK + ks * B_KS];
+#pragma unroll
+            for (int i = 0; i < Cfg::MB; ++i)
+#pragma unroll
+                for (int j = 0; j < Cfg::NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&empty_bar[s]));
+        if (m.flags & 2) {
+            double* C = Ct + (size_t)m.ctile * BB;
+#pragma unroll
+            for (int i = 0; i < Cfg::MB; ++i)
+#pragma unroll
+                for (int j = 0; j < Cfg::NB; ++j) {
+                    const int row = wm0 + i * 8 + g, col = wn0 + j * 8 + 2 * t;
+                    C[(size_t)col * BS + row] = acc[i][j][0];
+                    C[(size_t)(col + 1) * BS + row] = acc[i][j][1];
+                }
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// tensor map of a tile pool in the interleaved-by-4-rows view; k_rows: the K-chunk runs along leaf rows
+bool make_tile_map(CUtensorMap* map, const void* tiles, size_t n_tiles, int BS, int KC, bool k_rows, int esize,
+                   CUtensorMapDataType dt) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const int grp = 32 / esize;   // rows per 32-byte group (4 doubles / 8 floats)
+    cuuint64_t gdim[4] = {(cuuint64_t)grp, (cuuint64_t)BS, (cuuint64_t)(BS / grp), (cuuint64_t)n_tiles};
+    cuuint64_t gstr[3] = {(cuuint64_t)BS * esize, 32ull, (cuuint64_t)BS * BS * esize};
+    cuuint32_t box[4] = {(cuuint32_t)grp, (cuuint32_t)(k_rows ? BS : KC), (cuuint32_t)(k_rows ? KC / grp : BS / grp), 1u};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, dt, 4, const_cast<void*>(tiles), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int BS, int KC, bool TA, bool TB>
+bool launch_gemm_f64_tma_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n_ctiles,
+                              unsigned* counter, double* Ct) {
+    using Cfg = TmaCfg<BS, KC>;
+    CUtensorMap mapA, mapB;
+    if (!make_tile_map(&mapA, A.tiles.p, A.L, BS, KC, TA, 8, CU_TENSOR_MAP_DATA_TYPE_FLOAT64)) return false;
+    if (!make_tile_map(&mapB, B.tiles.p, B.L, BS, KC, !TB, 8, CU_TENSOR_MAP_DATA_TYPE_FLOAT64)) return false;
+    auto kfn = k_gemm_f64_tma<BS, KC, TA, TB>;
+    static bool configured = false;
+    if (!configured) {
+        HB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    unsigned grid = std::min<unsigned>(n_ctiles, (unsigned)engine().sm_count);
+    HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, ab, begin, n_ctiles, counter, Ct);
+    return true;
+}
+
+template <int BS, int KC>
+bool launch_gemm_f64_tma(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin,
+                         uint32_t n_ctiles, unsigned* counter, double* Ct) {
+    if (!tA && !tB) return launch_gemm_f64_tma_inst<BS, KC, false, false>(A, B, ab, begin, n_ctiles, counter, Ct);
+    if (!tA && tB) return launch_gemm_f64_tma_inst<BS, KC, false, true>(A, B, ab, begin, n_ctiles, counter, Ct);
+    if (tA && !tB) return launch_gemm_f64_tma_inst<BS, KC, true, false>(A, B, ab, begin, n_ctiles, counter, Ct);
+    return launch_gemm_f64_tma_inst<BS, KC, true, true>(A, B, ab, begin, n_ctiles, counter, Ct);
+}
+
 struct TaskList {
     size_t n_products = 0, n_ctiles = 0;
     unsigned long long n_candidates = 0;
@@ -521,15 +743,25 @@ void op_product(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, c
     if (tl.n_products > 0) {
         const size_t nct = tl.n_ctiles;
         DevBuf<char> ct(nct * C.tile_bytes());
-        const bool fast64 = A.dtype == HBSM_F64 && e.gemm_variant == 0 && (A.b == 32 || A.b == 64 || A.b == 128);
+        const bool fast64 = A.dtype == HBSM_F64 && e.gemm_variant != 1 && (A.b == 32 || A.b == 64 || A.b == 128);
         if (fast64) {
             DevBuf<unsigned> counter(1);
             counter.zero();
             const double* At = (const double*)A.tiles.p;
             const double* Bt = (const double*)B.tiles.p;
-            if (A.b == 64) launch_gemm_f64<64, 64>(tA, tB, At, Bt, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
-            else if (A.b == 32) launch_gemm_f64<32, 32>(tA, tB, At, Bt, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
-            else launch_gemm_f64<128, 32>(tA, tB, At, Bt, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
+            bool done = false;
+            if (e.gemm_variant == 0) {   // TMA-tiled kernel; falls back to the bulk-copy kernel if the driver refuses the map
+                if (A.b == 64) done = launch_gemm_f64_tma<64, 64>(tA, tB, A, B, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
+                else if (A.b == 32) done = launch_gemm_f64_tma<32, 32>(tA, tB, A, B, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
+                else done = launch_gemm_f64_tma<128, 32>(tA, tB, A, B, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
+                e.last_gemm_kernel = done ? 1 : 2;
+            }
+            if (!done) {
+                if (A.b == 64) launch_gemm_f64<64, 64>(tA, tB, At, Bt, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
+                else if (A.b == 32) launch_gemm_f64<32, 32>(tA, tB, At, Bt, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
+                else launch_gemm_f64<128, 32>(tA, tB, At, Bt, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
+                e.last_gemm_kernel = 2;
+            }
             t_gemm.stop();   // `counter` is released in stream order
         } else {
             if (A.dtype == HBSM_F64) {
@@ -542,6 +774,7 @@ void op_product(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, c
                           A.b, tA ? 1 : 0, tB ? 1 : 0, (float*)ct.p);
             }
             t_gemm.stop();
+            e.last_gemm_kernel = 0;
         }
         C.set_table(std::move(tl.ckeys), std::move(ct), nct);
         C.task_begin = std::move(tl.begin);
@@ -564,6 +797,7 @@ void op_product(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, c
     st.n_products = tl.n_products;
     st.n_ctiles = tl.n_ctiles;
     st.gpu_launches = e.launches - launches0;
+    st.gemm_kernel = (uint64_t)e.last_gemm_kernel;
     e.last = st;
 }
 

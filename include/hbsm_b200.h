@@ -47,6 +47,7 @@ typedef struct hbsm_stage_times_s {
     uint64_t n_products;  /* P: leaf products executed */
     uint64_t n_ctiles;    /* tiles of C */
     uint64_t gpu_launches;/* kernels launched by the call */
+    uint64_t gemm_kernel; /* leaf kernel used: 0 generic FMA, 1 TMA-tiled DMMA, 2 bulk-copy DMMA */
 } hbsm_stage_times;
 
 /* ---- library ---- */
@@ -116,7 +117,7 @@ int hbsm_export_tasks(hbsm_handle C, size_t cap, int64_t* ci, int64_t* cj, int64
 /* leaves in ascending Morton order; norms/tiles may be NULL; cap=0 -> count */
 int hbsm_export_leaves(hbsm_handle h, size_t cap, int64_t* bi, int64_t* bj, void* norms_cached, void* tiles, size_t* n);
 int hbsm_stage_times_last(hbsm_stage_times* out);
-int hbsm_set_gemm_variant(int variant);    /* 0 = auto (fastest valid), 1 = generic scalar kernel (debug/parity) */
+int hbsm_set_gemm_variant(int variant);    /* 0 = auto (TMA-tiled DMMA), 1 = generic FMA kernel (debug/parity), 2 = bulk-copy DMMA */
 
 /* ---- device-side interface (multi-GPU plumbing, device-resident benchmarks) ---- */
 /* borrowed pointers into the matrix's device block table: valid until the matrix is modified */
