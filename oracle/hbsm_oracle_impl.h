@@ -327,6 +327,39 @@ int F(orc_product)(const F(Mat)* A, int tA, const F(Mat)* B, int tB, F(Mat)* C, 
     return 0;
 }
 
+/* worth_to_multiply H:1873 / worth_to_spamm H:2006 on whole matrices (operands lifted to a common virtual size) */
+int F(orc_worth)(const F(Mat)* A, int tA, const F(Mat)* B, int tB, int is_spamm, REAL tau) {
+    if (F(orc_empty)(A) || F(orc_empty)(B)) return 0;
+    F(Ctx) cx; memset(&cx, 0, sizeof(cx));
+    cx.b = A->b; cx.tA = tA; cx.tB = tB; cx.spamm = is_spamm; cx.tau2 = tau * tau;
+    int big = A->vsize > B->vsize ? A->vsize : B->vsize;
+    int la = 0, lb = 0;
+    F(Node)* ar = F(lift)(A->root, A->vsize, big, A->b, &la);
+    F(Node)* br = F(lift)(B->root, B->vsize, big, A->b, &lb);
+    int w = F(worth)(&cx, ar, br);
+    F(unlift)(ar, la); F(unlift)(br, lb);
+    return w;
+}
+
+/* check_if_matrix_is_consistent H:1809-1827: a sized, childless non-leaf is inconsistent */
+int F(orc_consistent)(const F(Mat)* m) { return m->sized && m->root != NULL; }
+
+/* get_nnz H:985-1009 */
+long F(orc_nnz)(const F(Mat)* m) { return F(all_rec)(m->root, m->b, 0, 0, 0, 0, NULL, NULL, NULL); }
+
+/* copy H:1490-1529 (n_block_multiplies and cached norms travel with the nodes) */
+int F(orc_copy)(F(Mat)* C, const F(Mat)* A) {
+    if (C == A) return 0;
+    F(orc_clear)(C);
+    if (F(orc_empty)(A)) return 0;
+    C->b = A->b;
+    F(orc_resize)(C, A->M, A->N);
+    if (C->root) { F(node_free)(C->root); C->root = NULL; }
+    C->root = F(node_copy)(A->root, A->b);
+    C->n_mults = A->n_mults;
+    return 0;
+}
+
 /* ---- add H:1644-1722: structure union; both present -> fl(a+b), one present -> that subtree ---- */
 static F(Node)* F(add_rec)(const F(Node)* a, const F(Node)* b, int bs) {
     if (!a && !b) return NULL;

@@ -106,6 +106,8 @@ class OrcMatrix(_Base):
     def n_blocks(self): return self._f("n_blocks", _L)(self.h)
     def n_mults(self): return self._f("n_mults", _L)(self.h)
     def update(self): self._f("update", None)(self.h)
+    def consistent(self): return bool(self._f("consistent")(self.h))
+    def nnz(self): return self._f("nnz", _L)(self.h)
     def frob_sq(self): return self.dtype.type(self._f("frob_sq", _CT[self.dtype])(self.h))
     def frob_sq_cached(self): return self.dtype.type(self._f("frob_sq_cached", _CT[self.dtype])(self.h))
 
@@ -149,6 +151,17 @@ class OrcMatrix(_Base):
         if rc: raise RuntimeError("orc_product rc=%d" % rc)
         tasks = np.stack([ci, cj, kk], 1) if want_tasks else None
         return Cm, nm.value, nb.value, tasks
+
+    @classmethod
+    def worth(cls, A, tA, B, tB, spamm=False, tau=0.0):
+        return bool(A._f("worth")(A.h, C.c_int(tA), B.h, C.c_int(tB), C.c_int(spamm), _CT[A.dtype](tau)))
+
+    @classmethod
+    def copy(cls, A):
+        Cm = cls(A.b, A.dtype)
+        rc = A._f("copy")(Cm.h, A.h)
+        if rc: raise RuntimeError("orc_copy rc=%d" % rc)
+        return Cm
 
     @classmethod
     def _unary(cls, name, A, *extra):
@@ -300,6 +313,16 @@ class RefMatrix(_Base):
         if timed:
             return Cm, nm.value, nb.value, tasks, tuple(t3)
         return Cm, nm.value, nb.value, tasks
+
+    @classmethod
+    def worth(cls, A, tA, B, tB, spamm=False, tau=0.0):
+        if spamm:
+            return bool(A._f("worth_to_spamm")(A.h, C.c_int(tA), B.h, C.c_int(tB), _CT[A.dtype](tau)))
+        return bool(A._f("worth_to_multiply")(A.h, C.c_int(tA), B.h, C.c_int(tB)))
+
+    @classmethod
+    def copy(cls, A):
+        Cm = cls(A.b, A.dtype); A._ck(A._f("copy")(Cm.h, A.h), "copy"); return Cm
 
     @classmethod
     def add(cls, A, B):

@@ -107,11 +107,22 @@ template <class T> struct Api {
         Mat<T> C;
         if (is_spamm) Mat<T>::get_batches_spamm(M(a), tA, M(b), tB, C, tau, true, batches, 0);
         else Mat<T>::get_batches_multiply(M(a), tA, M(b), tB, C, batches, 0);
+        // leaf coordinates come from a walk from each operand's root, not from get_position_code(): the latter follows
+        // `parent` pointers, which transpose()/remove_dummy_levels leave unset or dangling
+        std::unordered_map<const Mat<T>*, std::pair<long, long> > pos_a, pos_b;
+        {
+            std::vector<long> bi, bj; std::vector<const Mat<T>*> lv;
+            walk_leaves<T>(M(a), 0, 0, bi, bj, lv);
+            for (size_t i = 0; i < lv.size(); ++i) pos_a[lv[i]] = std::make_pair(bi[i], bj[i]);
+            bi.clear(); bj.clear(); lv.clear();
+            walk_leaves<T>(M(b), 0, 0, bi, bj, lv);
+            for (size_t i = 0; i < lv.size(); ++i) pos_b[lv[i]] = std::make_pair(bi[i], bj[i]);
+        }
         long n = 0;
         for (auto it = batches.begin(); it != batches.end(); ++it) {
-            long ar, ac, br, bc;
-            code_to_rc(it->second.a->get_position_code(), ar, ac);
-            code_to_rc(it->second.b->get_position_code(), br, bc);
+            auto fa = pos_a.find(it->second.a); auto fb = pos_b.find(it->second.b);
+            if (fa == pos_a.end() || fb == pos_b.end()) throw std::runtime_error("ref_harness: triplet operand is not a leaf of A/B");
+            long ar = fa->second.first, ac = fa->second.second, br = fb->second.first, bc = fb->second.second;
             long i = tA ? ac : ar, k = tA ? ar : ac, k2 = tB ? bc : br, j = tB ? br : bc;
             if (k != k2) throw std::runtime_error("ref_harness: inconsistent k in triplet");
             if (n < cap) { ci[n] = i; cj[n] = j; kk[n] = k; }

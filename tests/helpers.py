@@ -50,3 +50,110 @@ def leaves_equal_structure(g, o):
 def decay_pair(n, lam, dtype=np.float64, seeds=(1, 2), eps=1e-12):
     W = min(G.decay_width(lam, eps), n - 1)
     return G.decay_coo(n, lam, W, seeds[0], dtype=dtype), G.decay_coo(n, lam, W, seeds[1], dtype=dtype)
+
+
+# ---------------------------------------------------------------------------------------------------
+# backend adapters: one scenario (tests/known_answers.py, the golden fixtures) runs through the CPU oracle port,
+# the unmodified reference (oracle/_ref) or the CUDA engine with the same calls
+# ---------------------------------------------------------------------------------------------------
+class OracleBackend:
+    """OrcMatrix (plain-C port) or RefMatrix (unmodified reference compiled in place)."""
+
+    def __init__(self, cls, dtype=np.float64):
+        self.cls = cls
+        self.dtype = np.dtype(dtype)
+        self.name = cls.kind
+
+    def sized(self, b, m, n):
+        A = self.cls(b, self.dtype); A.resize(m, n); return A
+
+    def coo(self, b, m, n, r, c, v, update=True):
+        return po.from_coo(self.cls, b, m, n, r, c, np.asarray(v, self.dtype), self.dtype, update)
+
+    def dense(self, b, D, update=True):
+        return po.from_dense(self.cls, b, D, self.dtype, True, update)
+
+    def to_dense(self, A): return A.to_dense()
+    def depth(self, A): return A.depth()
+    def shape(self, A): return tuple(A.shape())
+    def consistent(self, A): return A.consistent()
+    def n_blocks(self, A): return A.n_blocks()
+    def n_mults(self, A): return A.n_mults()
+    def nnz(self, A): return A.nnz()
+    def frob_sq(self, A): return float(A.frob_sq())
+    def get(self, A, r, c): return A.get(r, c)
+    def get_all(self, A): return A.get_all()
+    def leaves(self, A, tiles=True): return A.leaves(tiles)
+    def update(self, A): A.update()
+
+    def product(self, A, tA, B, tB, spamm=False, tau=0.0, want_tasks=False):
+        return self.cls.product(A, tA, B, tB, spamm=spamm, tau=tau, want_tasks=want_tasks)
+
+    def worth_to_multiply(self, A, tA, B, tB): return self.cls.worth(A, tA, B, tB)
+    def worth_to_spamm(self, A, tA, B, tB, tau): return self.cls.worth(A, tA, B, tB, True, tau)
+    def add(self, A, B): return self.cls.add(A, B)
+    def transpose(self, A): return self.cls.transpose(A)
+    def upper(self, A): return self.cls.upper(A)
+    def rescale(self, A, alpha): return self.cls.rescale(A, alpha)
+    def copy(self, A): return self.cls.copy(A)
+    def symm_multiply(self, A, sA, B, sB): return self.cls.symm_multiply(A, int(sA), B, int(sB))
+    def symm_square(self, A): return self.cls.symm_square(A)
+    def symm_rk(self, A, transposed): return self.cls.symm_rk(A, int(transposed))
+
+
+class GpuBackend:
+    """The CUDA engine through the C ABI (Python mirror of the reference class)."""
+    name = "cuda"
+
+    def __init__(self, dtype=np.float64):
+        self.dtype = np.dtype(dtype)
+
+    def sized(self, b, m, n):
+        A = HBSM(self.dtype, b); A.resize(m, n); return A
+
+    def coo(self, b, m, n, r, c, v, update=True):
+        return gpu_from_coo(b, m, n, r, c, np.asarray(v, self.dtype), self.dtype, update)
+
+    def dense(self, b, D, update=True):
+        D = np.asarray(D, self.dtype)
+        m, n = D.shape
+        r, c = np.meshgrid(np.arange(m), np.arange(n), indexing="ij")
+        return self.coo(b, m, n, r.ravel(), c.ravel(), D.ravel(), update)
+
+    def to_dense(self, A): return A.to_dense()
+    def depth(self, A): return A.get_depth()
+    def shape(self, A): return (A.get_n_rows(), A.get_n_cols())
+    def consistent(self, A): return A.check_if_matrix_is_consistent()
+    def n_blocks(self, A): return A.get_n_blocks()
+    def n_mults(self, A): return A.get_n_block_multiplications()
+    def nnz(self, A): return A.get_nnz()
+    def frob_sq(self, A): return float(A.get_frob_squared())
+    def get(self, A, r, c): return A.get_values(r, c)
+    def get_all(self, A): return A.get_all_values()
+    def update(self, A): A.update_internal_info()
+
+    def leaves(self, A, tiles=True):
+        return A.export_leaves(tiles=tiles)
+
+    def product(self, A, tA, B, tB, spamm=False, tau=0.0, want_tasks=False):
+        Cm = HBSM(self.dtype)
+        if spamm:
+            nm, nb = HBSM.spamm(A, tA, B, tB, Cm, tau, True)
+        else:
+            nm, nb = HBSM.multiply(A, tA, B, tB, Cm)
+        return Cm, nm, nb, (Cm.export_tasks() if want_tasks else None)
+
+    def worth_to_multiply(self, A, tA, B, tB): return HBSM.worth_to_multiply(A, tA, B, tB)
+    def worth_to_spamm(self, A, tA, B, tB, tau): return HBSM.worth_to_spamm(A, tA, B, tB, tau)
+
+    def _out(self, fn, *args):
+        Cm = HBSM(self.dtype); fn(*args, Cm); return Cm
+
+    def add(self, A, B): return self._out(HBSM.add, A, B)
+    def transpose(self, A): return self._out(HBSM.transpose, A)
+    def upper(self, A): Cm = HBSM(self.dtype); A.get_upper_triangle(Cm); return Cm
+    def rescale(self, A, alpha): Cm = HBSM(self.dtype); Cm.rescale(A, alpha); return Cm
+    def copy(self, A): Cm = HBSM(self.dtype); Cm.copy(A); return Cm
+    def symm_multiply(self, A, sA, B, sB): return self._out(HBSM.symm_multiply, A, sA, B, sB)
+    def symm_square(self, A): return self._out(HBSM.symm_square, A)
+    def symm_rk(self, A, transposed): return self._out(HBSM.symm_rk, A, transposed)
