@@ -1,0 +1,318 @@
+"""Multi-GPU multiply / SpAMM: one process per GPU, C sharded by top-level quadtree block rows.
+
+Rank r owns the contiguous slab of block rows  [r*g/G, (r+1)*g/G)  (g = block-grid side, G = world size; for
+G in {2,4,8} these are exactly the top-level quadtree block rows).  It holds the tiles of op(A) whose C-row index
+ci lies in its slab and the tiles of op(B) whose contraction index k lies in its slab.  One product is
+
+  1. request   every rank computes, per k, the largest leaf norm^2 among its op(A) tiles (ci,k)   -> all_to_all
+  2. select    the owner of row k keeps the op(B) tiles (k,cj) that can survive the SpAMM test against that
+               maximum, fl(max_na * nb) > fl(tau*tau) (monotone rounding => exactly the tiles that at least one
+               executed product of the requester touches; exact multiply: every tile of a requested row)
+  3. exchange  keys, leaf norms and tiles of the selected op(B) tiles                                -> all_to_all
+  4. multiply  the single-GPU engine call (task list + leaf GEMMs) on (A_r, received B tiles) -> C_r
+
+There is NO reduction: each rank owns whole block rows of C.  The executed-product set is the disjoint union of
+the per-rank sets and is bit-identical to the single-GPU one because the predicate is per leaf pair.
+
+The planning (steps 1-2) is written with device-agnostic torch ops, so the same code runs on CPU tensors over
+`gloo` (tests/test_sharded_cpu.py, world_size 2) and on CUDA tensors over NCCL/NVLink.  Only step 4 needs the GPU.
+"""
+import ctypes as C
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+# ---------------------------------------------------------------------------------------------------
+# Morton helpers on int64 tensors (digit = 2*colbit + rowbit, H:52-56; same bit tricks as csrc/common.cuh)
+# ---------------------------------------------------------------------------------------------------
+_M = [0x5555555555555555, 0x3333333333333333, 0x0F0F0F0F0F0F0F0F, 0x00FF00FF00FF00FF, 0x0000FFFF0000FFFF,
+      0x00000000FFFFFFFF]
+
+
+def _compact(v):
+    v = v & _M[0]
+    for s, m in zip((1, 2, 4, 8, 16), _M[1:]):
+        v = (v | (v >> s)) & m
+    return v
+
+
+def _spread(v):
+    v = v & _M[5]
+    for s, m in zip((16, 8, 4, 2, 1), reversed(_M[:5])):
+        v = (v | (v << s)) & m
+    return v
+
+
+def morton_decode(keys):
+    """int64 keys -> (block row, block col)."""
+    return _compact(keys), _compact(keys >> 1)
+
+
+def morton_encode(bi, bj):
+    return _spread(bi) | (_spread(bj) << 1)
+
+
+def slab_bounds(grid_side, world, rank):
+    """Block rows [lo, hi) owned by `rank`: top-level quadtree block rows for world in {2,4,8}."""
+    if grid_side % world != 0:
+        raise ValueError("block grid side %d is not divisible by the world size %d" % (grid_side, world))
+    rows = grid_side // world
+    return rank * rows, (rank + 1) * rows
+
+
+def owner_of(line, grid_side, world):
+    return line // (grid_side // world)
+
+
+# ---------------------------------------------------------------------------------------------------
+# steps 1-3: plan + exchange (device-agnostic)
+# ---------------------------------------------------------------------------------------------------
+def request_thresholds(a_keys, a_norms, tA, grid_side):
+    """Per contraction index k: max leaf norm^2 over this rank's op(A) tiles (., k); -1 where no tile has that k."""
+    ar, ac = morton_decode(a_keys)
+    k = ar if tA else ac
+    thr = torch.full((grid_side,), -1.0, dtype=a_norms.dtype, device=a_norms.device)
+    if k.numel():
+        thr.scatter_reduce_(0, k, a_norms, reduce="amax", include_self=True)
+    return thr
+
+
+def select_for_peers(b_keys, b_norms, tB, thr_from_peers, lo, spamm, tau):
+    """thr_from_peers[q, k - lo] = request of rank q for my row k.  Returns (send_index, counts[q]): indices into my
+    op(B) tile list, grouped by destination rank, ascending Morton key inside a group."""
+    br, bc = morton_decode(b_keys)
+    k = (bc if tB else br) - lo
+    world = thr_from_peers.shape[0]
+    idx, counts = [], []
+    if spamm:
+        tau2 = torch.tensor(tau, dtype=b_norms.dtype, device=b_norms.device)
+        tau2 = tau2 * tau2                      # fl(tau*tau) in Treal, H:2008
+    for q in range(world):
+        t = thr_from_peers[q][k] if k.numel() else thr_from_peers[q][:0]
+        keep = t >= 0
+        if spamm:
+            keep = keep & ((t * b_norms) > tau2)   # fl(max_na * nb) > fl(tau^2): same rounding as the leaf-pair test
+        sel = torch.nonzero(keep, as_tuple=False).flatten()
+        idx.append(sel)
+        counts.append(int(sel.numel()))
+    return (torch.cat(idx) if idx else torch.zeros(0, dtype=torch.int64)), counts
+
+
+def exchange_b(a_keys, a_norms, tA, b_keys, b_norms, b_tiles, tB, grid_side, spamm, tau, group=None, timers=None):
+    """Runs steps 1-3.  Returns (keys, norms, tiles) of the op(B) tiles this rank's products can touch."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lo, hi = slab_bounds(grid_side, world, rank)
+    rows = hi - lo
+    t0 = time.perf_counter()
+    thr = request_thresholds(a_keys, a_norms, tA, grid_side)              # [g] -> slice p goes to rank p
+    thr_in = torch.empty_like(thr)
+    dist.all_to_all_single(thr_in, thr, group=group)                      # equal splits of `rows`
+    send_idx, counts = select_for_peers(b_keys, b_norms, tB, thr_in.view(world, rows), lo, spamm, tau)
+    cnt_out = torch.tensor(counts, dtype=torch.int64, device=b_keys.device)
+    cnt_in = torch.empty_like(cnt_out)
+    dist.all_to_all_single(cnt_in, cnt_out, group=group)
+    recv_counts = [int(x) for x in cnt_in.tolist()]                       # the one host sync of the plan
+    n_in = sum(recv_counts)
+    t1 = time.perf_counter()
+    keys_out = b_keys.index_select(0, send_idx)
+    norms_out = b_norms.index_select(0, send_idx)
+    tiles_out = b_tiles.index_select(0, send_idx)
+    keys_in = torch.empty((n_in,), dtype=b_keys.dtype, device=b_keys.device)
+    norms_in = torch.empty((n_in,), dtype=b_norms.dtype, device=b_keys.device)
+    tiles_in = torch.empty((n_in, b_tiles.shape[1]), dtype=b_tiles.dtype, device=b_keys.device)
+    dist.all_to_all_single(keys_in, keys_out, recv_counts, counts, group=group)
+    dist.all_to_all_single(norms_in, norms_out, recv_counts, counts, group=group)
+    dist.all_to_all_single(tiles_in, tiles_out, recv_counts, counts, group=group)
+    if timers is not None:
+        timers["plan_s"] = t1 - t0
+        timers["sent_tiles"] = sum(counts) - counts[rank]
+        timers["recv_tiles"] = n_in - recv_counts[rank]
+    return keys_in, norms_in, tiles_in
+
+
+# ---------------------------------------------------------------------------------------------------
+# engine glue (GPU only)
+# ---------------------------------------------------------------------------------------------------
+class _DevArray:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def device_views(Mx):
+    """Zero-copy torch views (keys int64 [L], norms [L], tiles [L, b*b]) of an engine matrix's block table."""
+    from . import _capi
+    n = C.c_size_t(0); pk = C.c_void_p(); pn = C.c_void_p(); pt = C.c_void_p()
+    _capi.check(_capi.lib().hbsm_device_table(Mx._h, C.byref(n), C.byref(pk), C.byref(pn), C.byref(pt)))
+    L = n.value
+    b = Mx.get_params().blocksize
+    ts = "<f8" if Mx.dtype == np.float64 else "<f4"
+    dt = torch.float64 if Mx.dtype == np.float64 else torch.float32
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if L == 0:
+        return (torch.zeros(0, dtype=torch.int64, device=dev), torch.zeros(0, dtype=dt, device=dev),
+                torch.zeros((0, b * b), dtype=dt, device=dev))
+    keys = torch.as_tensor(_DevArray(pk.value, (L,), "<i8"), device=dev)
+    norms = torch.as_tensor(_DevArray(pn.value, (L,), ts), device=dev)
+    tiles = torch.as_tensor(_DevArray(pt.value, (L, b * b), ts), device=dev)
+    return keys, norms, tiles
+
+
+def matrix_from_device(dtype, b, m, n, keys, norms, tiles):
+    from . import _capi
+    from .matrix import HierarchicalBlockSparseMatrix as H
+    Mx = H(dtype, b)
+    Mx.resize(m, n)
+    if keys.numel():
+        _capi.check(_capi.lib().hbsm_assign_device_tiles(Mx._h, keys.numel(), C.c_void_p(keys.data_ptr()),
+                                                         C.c_void_p(tiles.data_ptr()), C.c_void_p(norms.data_ptr())))
+    return Mx
+
+
+def sharded_product(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, group=None, timers=None):
+    """C_r = op(A)_r * op(B): A_loc / B_loc are this rank's engine matrices (full logical dims, only the slab's tiles;
+    norms refreshed).  Returns (C_loc, n_mults_local, n_blocks_local)."""
+    from .matrix import HierarchicalBlockSparseMatrix as H
+    grid_side = 1 << max(A_loc.expected_depth(), B_loc.expected_depth())
+    ak, an, _ = device_views(A_loc)
+    bk, bn, bt = device_views(B_loc)
+    from . import _capi
+    ext = torch.cuda.ExternalStream(int(_capi.lib().hbsm_stream() or 0))
+    with torch.cuda.stream(ext):
+        keys, norms, tiles = exchange_b(ak, an, tA, bk, bn, bt, tB, grid_side, spamm, tau, group, timers)
+        ext.synchronize()
+    bm, bnn = B_loc.get_n_rows(), B_loc.get_n_cols()
+    Bh = matrix_from_device(B_loc.dtype, B_loc.get_params().blocksize, bm, bnn, keys, norms, tiles)
+    Cm = H(A_loc.dtype)
+    if spamm:
+        nm, nb = H.spamm(A_loc, tA, Bh, tB, Cm, tau, True)
+    else:
+        nm, nb = H.multiply(A_loc, tA, Bh, tB, Cm)
+    return Cm, nm, nb
+
+
+# ---------------------------------------------------------------------------------------------------
+# bench.py --gpus N (N > 1): strong scaling of the BASELINE workload, one rank per GPU under torchrun
+# ---------------------------------------------------------------------------------------------------
+def bench_main(args, w, workload_config, fp64_peak, ClockSampler):
+    import json
+    import hierarchical_block_sparse_lib_b200 as hb
+    from . import _capi
+    from . import generators as G
+    H = hb.HierarchicalBlockSparseMatrix
+    world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"]); local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    hb.init(local_rank)
+    n, b, lam, tau = w["n"], w["b"], w["lam"], w["tau"]
+    W = G.decay_width(lam, w["eps"])
+    g = n // b
+    lo, hi = slab_bounds(g, world, rank)
+    A = H(np.float64, b); A.generate_decay(n, lam, W, w["seeds"][0], False, lo, hi); A.update_internal_info()
+    B = H(np.float64, b); B.generate_decay(n, lam, W, w["seeds"][1], False, lo, hi); B.update_internal_info()
+    ext = torch.cuda.ExternalStream(int(_capi.lib().hbsm_stream()))
+    timers = {}
+
+    def step():
+        Cm, nm, nb = sharded_product(A, False, B, False, True, tau, None, timers)
+        return Cm, nm, nb, hb.stage_times()
+
+    for _ in range(args.warmup):
+        Cm, nm, nb, st = step()
+        del Cm
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    l0 = hb.kernel_launch_count()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    gemm_ms, task_ms, plan_ms = [], [], []
+    ev0.record(ext)
+    for _ in range(args.steps):
+        Cm, nm, nb, st = step()
+        gemm_ms.append(st["gemm_ms"]); task_ms.append(st["tasklist_ms"]); plan_ms.append(1e3 * timers["plan_s"])
+        del Cm
+    ev1.record(ext)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    launches = hb.kernel_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_local = ev0.elapsed_time(ev1) / args.steps
+    stats = torch.tensor([ms_local, float(np.mean(gemm_ms))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    sums = torch.tensor([float(nm), float(nb), float(st["n_candidates"]), float(launches), float(timers["recv_tiles"])],
+                        dtype=torch.float64, device="cuda")
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    ms = float(stats[0]); g_ms_max = float(stats[1])
+    P = int(sums[0])
+    flops = 2.0 * b ** 3 * P
+
+    e2e = _e2e_sharded(hb, H, A, B, w, max(1, min(args.steps, 3)), lo, hi)
+
+    if rank == 0:
+        peak, peak_src = fp64_peak()
+        g_ms = float(np.mean(gemm_ms))
+        achieved = 2.0 * b ** 3 * nm / (g_ms * 1e-3) / 1e12
+        line = {"metric": "spamm_fp64_leaf_tflops", "value": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+                "products_per_multiply": P, "c_tiles": int(sums[1]), "candidates": int(sums[2]),
+                "stage_ms": {"exchange_plan_rank0": float(np.mean(plan_ms)), "tasklist_rank0": float(np.mean(task_ms)),
+                             "gemm_rank0": g_ms, "gemm_max_over_ranks": g_ms_max},
+                "halo_tiles_received_total": int(sums[4]),
+                "roofline": {"bound": "tensor", "kernel": "k_gemm_f64_tma<64,64> (FP64 DMMA leaf GEMM), rank 0's launch",
+                             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peak_src,
+                             "algorithmic": "2*b^3 flops per leaf product x %d products in rank 0's launch" % nm,
+                             "kernel_ms": g_ms, "share_of_step": g_ms / ms, "traffic": None},
+                "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(sums[3]), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
+def _e2e_sharded(hb, H, A, B, w, steps, lo, hi):
+    """Per rank: pinned host tiles of its slabs -> device, norm refresh, halo exchange, SpAMM, all local C tiles back to
+    pinned host memory.  Max over ranks of the wall time between two barriers."""
+    from . import _capi
+    b, n, tau = w["b"], w["n"], w["tau"]
+
+    def pinned_leaves(Mx):
+        bi, bj, _, t = Mx.export_leaves(norms=False)
+        pt = torch.empty(t.shape, dtype=torch.float64, pin_memory=True)
+        pt.numpy()[...] = t
+        return bi.astype(np.int32), bj.astype(np.int32), pt
+
+    abi, abj, at = pinned_leaves(A)
+    bbi, bbj, bt = pinned_leaves(B)
+    h2d = at.numel() * 8 + bt.numel() * 8 + 4 * (len(abi) + len(abj) + len(bbi) + len(bbj))
+    out = None
+    times = []
+    nm_tot = 0
+    d2h = 0
+    for i in range(steps + 1):
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        A2 = H(np.float64, b); A2.resize(n, n); A2.assign_tiles(abi, abj, at.numpy()); A2.update_internal_info()
+        B2 = H(np.float64, b); B2.resize(n, n); B2.assign_tiles(bbi, bbj, bt.numpy()); B2.update_internal_info()
+        Cm, nm, nr = sharded_product(A2, False, B2, False, True, tau)
+        if out is None or out.shape[0] < nr:
+            out = torch.empty((nr, b * b), dtype=torch.float64, pin_memory=True)
+        cbi = np.zeros(nr, np.int64); cbj = np.zeros(nr, np.int64)
+        m = C.c_size_t(0)
+        _capi.check(_capi.lib().hbsm_export_leaves(Cm._h, nr, cbi.ctypes.data_as(C.c_void_p), cbj.ctypes.data_as(C.c_void_p),
+                                                    None, C.c_void_p(out.data_ptr()), C.byref(m)))
+        torch.cuda.synchronize(); dist.barrier()
+        dt = time.perf_counter() - t0
+        del A2, B2, Cm
+        v = torch.tensor([dt, float(nm), float(h2d), float(nr * b * b * 8 + 16 * nr)], dtype=torch.float64, device="cuda")
+        mx = v.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = v.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        if i > 0:
+            times.append(float(mx[0]))
+        nm_tot = int(sm[1]); h2d_tot = int(sm[2]); d2h = int(sm[3])
+    ms = 1e3 * float(np.mean(times))
+    return {"value": 2.0 * b ** 3 * nm_tot / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ms,
+            "h2d_bytes_per_step": h2d_tot, "d2h_bytes_per_step": d2h,
+            "path": "per rank: hbsm_assign_tiles(A_r,B_r from pinned host) + hbsm_update_norms + halo exchange (NCCL) + "
+                    "hbsm_spamm + hbsm_export_leaves(C_r to pinned host); max over ranks"}

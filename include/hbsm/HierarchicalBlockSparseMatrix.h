@@ -1,0 +1,260 @@
+/* HierarchicalBlockSparseMatrix.h -- drop-in host class for the hot path of toxaart/hierarchical_block_sparse_lib.
+ *
+ * Same namespace, class name, public method names, argument order and exception behaviour as the public section of
+ * the reference's header-only template (reference source/HierarchicalBlockSparseMatrix.h:166-428, cited H:<line>),
+ * but the object is a thin owner of an opaque handle of the B200 engine: every method forwards to the C ABI in
+ * include/hbsm_b200.h (libhbsm_b200.so, hand-written sm_100a CUDA).  There is no host fallback -- when no B200 is
+ * usable every call that touches data throws std::runtime_error("hbsm_b200: no CUDA device ...").
+ *
+ * Differences a caller can observe (all documented in INTEGRATION.md):
+ *   - Treal must be double or float (the reference's BLAS shim offers exactly these, gblas.h:85-143);
+ *   - copy construction / assignment is a deep copy (the reference's implicit copy shares children by shared_ptr);
+ *   - spamm(..., updated=false) refreshes the operands' norms (the reference's path is a use-after-free, H:6294-6307);
+ *   - the serialisation, estimator, truncation and inv_chol members outside the multiply/SpAMM/add path
+ *     (SURVEY 8f "next") are declared and throw "not provided by hbsm_b200".
+ */
+#ifndef HBSM_B200_HIERARCHICAL_BLOCK_SPARSE_MATRIX_H
+#define HBSM_B200_HIERARCHICAL_BLOCK_SPARSE_MATRIX_H
+
+#include <cstddef>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../hbsm_b200.h"
+
+namespace hbsm {
+
+namespace detail {
+template <class T> struct dtype_of;
+template <> struct dtype_of<double> { enum { value = HBSM_F64 }; };
+template <> struct dtype_of<float> { enum { value = HBSM_F32 }; };
+inline void check(int rc) {
+    if (rc != HBSM_OK) throw std::runtime_error(hbsm_last_error());
+}
+}  // namespace detail
+
+template <class Treal>
+class HierarchicalBlockSparseMatrix {
+public:
+    typedef Treal real;   // H:40
+
+    struct Params {       // H:167-169
+        int blocksize;
+    };
+
+    HierarchicalBlockSparseMatrix() : h_(NULL) { detail::check(hbsm_create(detail::dtype_of<Treal>::value, &h_)); }   // H:171
+    ~HierarchicalBlockSparseMatrix() { if (h_) hbsm_destroy(h_); }                                                   // H:175
+    HierarchicalBlockSparseMatrix(const HierarchicalBlockSparseMatrix& o) : h_(NULL) {
+        detail::check(hbsm_create(detail::dtype_of<Treal>::value, &h_));
+        copy(o);
+    }
+    HierarchicalBlockSparseMatrix& operator=(const HierarchicalBlockSparseMatrix& o) {
+        if (this != &o) copy(o);
+        return *this;
+    }
+
+    int get_n_rows() const { int r = 0, c = 0; detail::check(hbsm_dims(h_, &r, &c)); return r; }   // H:181
+    int get_n_cols() const { int r = 0, c = 0; detail::check(hbsm_dims(h_, &r, &c)); return c; }   // H:184
+
+    void set_params(Params const& param) { detail::check(hbsm_set_blocksize(h_, param.blocksize)); }   // H:186, H:450
+    Params get_params() const { Params p; detail::check(hbsm_get_blocksize(h_, &p.blocksize)); return p; }   // H:188
+
+    bool children_exist() const { int v = 0; detail::check(hbsm_children_exist(h_, &v)); return v != 0; }   // H:190
+    bool empty() const { int v = 0; detail::check(hbsm_is_empty(h_, &v)); return v != 0; }                   // H:192
+
+    void resize(int nRows_, int nCols_, size_t* no_of_resizes = NULL) {   // H:194, H:544
+        detail::check(hbsm_resize(h_, nRows_, nCols_));
+        if (no_of_resizes) (*no_of_resizes)++;
+    }
+    void clear() { detail::check(hbsm_clear(h_)); }   // H:196
+
+    void assign_from_vectors_general(const std::vector<int>& rows, const std::vector<int>& cols,
+                                     const std::vector<Treal>& values, bool useMax, bool boundaries_checked) {   // H:198, H:668
+        if (rows.size() != values.size() || cols.size() != values.size())   // H:677
+            throw std::runtime_error("Error in HierarchicalBlockSparseMatrix<Treal>::assign_from_vectors: bad sizes.");
+        detail::check(hbsm_assign_coo(h_, values.size(), rows.data(), cols.data(), values.data(), useMax ? 1 : 0,
+                                      boundaries_checked ? 1 : 0));
+    }
+    void assign_from_vectors(const std::vector<int>& rows, const std::vector<int>& cols, const std::vector<Treal>& values) {
+        assign_from_vectors_general(rows, cols, values, false, false);   // H:838
+    }
+    void assign_from_vectors_max(const std::vector<int>& rows, const std::vector<int>& cols, const std::vector<Treal>& values) {
+        assign_from_vectors_general(rows, cols, values, true, false);    // H:845
+    }
+
+    Treal get_frob_squared() const { Treal v = 0; detail::check(hbsm_frob_squared(h_, &v)); return v; }   // H:214, H:641
+    Treal get_frob_norm_squared_internal() const { Treal v = 0; detail::check(hbsm_frob_squared_cached(h_, &v)); return v; }   // H:216
+    size_t get_n_block_multiplications() const { size_t n = 0; detail::check(hbsm_get_n_block_multiplications(h_, &n)); return n; }   // H:218
+    void set_n_block_multiplicaitons(size_t n) { detail::check(hbsm_set_n_block_multiplications(h_, n)); }   // H:220 (sic)
+    void update_internal_info() { detail::check(hbsm_update_norms(h_)); }   // H:223, H:3905
+    size_t get_nnz() const { size_t n = 0; detail::check(hbsm_nnz(h_, &n)); return n; }   // H:225
+    int get_depth() const { int d = 0; detail::check(hbsm_depth(h_, &d)); return d; }     // H:228
+    int expected_depth() const { int d = 0; detail::check(hbsm_expected_depth(h_, &d)); return d; }   // H:230
+
+    void get_values(const std::vector<int>& rows, const std::vector<int>& cols, std::vector<Treal>& values) const {   // H:233, H:1012
+        if (rows.size() != cols.size())
+            throw std::runtime_error("Error in HierarchicalBlockSparseMatrix<Treal>::get_values: bad sizes.");
+        values.resize(rows.size());
+        detail::check(hbsm_get_values(h_, rows.size(), rows.data(), cols.data(), values.data()));
+    }
+    void get_all_values(std::vector<int>& rows, std::vector<int>& cols, std::vector<Treal>& values) const {   // H:237, H:1034
+        size_t n = 0;
+        detail::check(hbsm_get_all_values(h_, 0, NULL, NULL, NULL, &n));
+        rows.resize(n); cols.resize(n); values.resize(n);
+        if (n) detail::check(hbsm_get_all_values(h_, n, rows.data(), cols.data(), values.data(), &n));
+    }
+
+    static void allocate_work_buffers(int /*max_dimension*/, int /*max_blocksize*/) {}   // H:248
+
+    void copy(const HierarchicalBlockSparseMatrix<Treal>& other, size_t* no_of_resizes = NULL) {   // H:251, H:1490
+        detail::check(hbsm_copy(h_, other.h_));
+        if (no_of_resizes) (*no_of_resizes)++;
+    }
+
+    static void add(HierarchicalBlockSparseMatrix<Treal> const& A, HierarchicalBlockSparseMatrix<Treal> const& B,
+                    HierarchicalBlockSparseMatrix<Treal>& C, size_t* no_of_resizes = NULL) {   // H:255, H:1644
+        detail::check(hbsm_add(A.h_, B.h_, C.h_));
+        if (no_of_resizes) (*no_of_resizes)++;
+    }
+
+    static void multiply(HierarchicalBlockSparseMatrix<Treal> const& A, bool tA, HierarchicalBlockSparseMatrix<Treal> const& B,
+                         bool tB, HierarchicalBlockSparseMatrix<Treal>& C, size_t* no_of_block_multiplies = NULL,
+                         size_t* no_of_resizes = NULL) {   // H:260, H:2142
+        size_t nm = 0, nr = 0;
+        detail::check(hbsm_multiply(A.h_, tA ? 1 : 0, B.h_, tB ? 1 : 0, C.h_, &nm, &nr));
+        if (no_of_block_multiplies) *no_of_block_multiplies = nm;   // H:2186-2190
+        if (no_of_resizes) *no_of_resizes = nr;
+    }
+
+    void rescale(HierarchicalBlockSparseMatrix<Treal> const& other, Treal alpha) {   // H:265, H:3078
+        detail::check(hbsm_rescale(h_, other.h_, (double)alpha));
+    }
+
+    static void symm_multiply(HierarchicalBlockSparseMatrix<Treal> const& A, bool sA, HierarchicalBlockSparseMatrix<Treal> const& B,
+                              bool sB, HierarchicalBlockSparseMatrix<Treal>& C) {   // H:274, H:3244
+        detail::check(hbsm_symm_multiply(A.h_, sA ? 1 : 0, B.h_, sB ? 1 : 0, C.h_));
+    }
+    static void symm_square(HierarchicalBlockSparseMatrix<Treal> const& A, HierarchicalBlockSparseMatrix<Treal>& C) {   // H:277, H:3563
+        detail::check(hbsm_symm_square(A.h_, C.h_));
+    }
+    static void symm_rk(HierarchicalBlockSparseMatrix<Treal> const& A, bool transposed, HierarchicalBlockSparseMatrix<Treal>& C) {   // H:280, H:3711
+        detail::check(hbsm_symm_rk(A.h_, transposed ? 1 : 0, C.h_));
+    }
+    static void transpose(HierarchicalBlockSparseMatrix<Treal> const& A, HierarchicalBlockSparseMatrix<Treal>& C) {   // H:282, H:3733
+        detail::check(hbsm_transpose(A.h_, C.h_));
+    }
+    void get_upper_triangle(HierarchicalBlockSparseMatrix<Treal>& A) const {   // H:284, H:3515: A = triu(*this)
+        detail::check(hbsm_upper_triangle(h_, A.h_));
+    }
+
+    void print() const {   // H:295
+        std::vector<int> rows, cols;
+        std::vector<Treal> vals;
+        get_all_values(rows, cols, vals);
+        for (size_t i = 0; i < rows.size(); ++i) std::cout << rows[i] << " " << cols[i] << " " << vals[i] << std::endl;
+    }
+
+    static void spamm(HierarchicalBlockSparseMatrix<Treal> const& A, bool tA, HierarchicalBlockSparseMatrix<Treal> const& B, bool tB,
+                      HierarchicalBlockSparseMatrix<Treal>& C, const Treal tau, bool updated,
+                      size_t* no_of_block_multiplies = NULL, size_t* no_of_resizes = NULL) {   // H:305, H:3931
+        size_t nm = 0, nr = 0;
+        detail::check(hbsm_spamm(A.h_, tA ? 1 : 0, B.h_, tB ? 1 : 0, C.h_, (double)tau, updated ? 1 : 0, &nm, &nr));
+        if (no_of_block_multiplies) *no_of_block_multiplies = nm;   // H:3976-3982
+        if (no_of_resizes) *no_of_resizes = nr;
+    }
+
+    static int get_blocksize(Params const& param, int /*max_dimension*/) { return param.blocksize; }   // H:315
+
+    bool check_if_matrix_is_consistent() const { int v = 0; detail::check(hbsm_is_consistent(h_, &v)); return v != 0; }   // H:396
+
+    static bool worth_to_multiply(HierarchicalBlockSparseMatrix<Treal> const& A, const bool tA,
+                                  HierarchicalBlockSparseMatrix<Treal> const& B, const bool tB) {   // H:399, H:1873
+        int v = 0;
+        detail::check(hbsm_worth_to_multiply(A.h_, tA ? 1 : 0, B.h_, tB ? 1 : 0, &v));
+        return v != 0;
+    }
+    static bool worth_to_spamm(HierarchicalBlockSparseMatrix<Treal> const& A, const bool tA,
+                               HierarchicalBlockSparseMatrix<Treal> const& B, const bool tB, const Treal tau) {   // H:402, H:2006
+        int v = 0;
+        detail::check(hbsm_worth_to_spamm(A.h_, tA ? 1 : 0, B.h_, tB ? 1 : 0, (double)tau, &v));
+        return v != 0;
+    }
+
+    // ---- engine extras (not in the reference): executed-product list, tile count, SpAMM-pruned symmetric square ----
+    size_t get_n_blocks() const { size_t n = 0; detail::check(hbsm_n_blocks(h_, &n)); return n; }   // reference: private, H:7311
+    static void symm_square_spamm(HierarchicalBlockSparseMatrix<Treal> const& A, HierarchicalBlockSparseMatrix<Treal>& C,
+                                  const Treal tau, size_t* no_of_block_multiplies = NULL, size_t* no_of_resizes = NULL) {
+        size_t nm = 0, nr = 0;
+        detail::check(hbsm_symm_square_spamm(A.h_, C.h_, (double)tau, &nm, &nr));
+        if (no_of_block_multiplies) *no_of_block_multiplies = nm;
+        if (no_of_resizes) *no_of_resizes = nr;
+    }
+    hbsm_handle handle() const { return h_; }
+
+    // ---- members outside the multiply / SpAMM / add path (SURVEY 2 "OUT OF SCOPE", 8f "next"): declared, throwing ----
+#define HBSM_B200_NOT_PROVIDED(name) \
+    throw std::runtime_error("Error in HierarchicalBlockSparseMatrix<Treal>::" name ": not provided by hbsm_b200 (outside the multiply/SpAMM/add path).")
+    size_t get_size() const { HBSM_B200_NOT_PROVIDED("get_size"); }                                            // H:241
+    void write_to_buffer(char*, size_t const) const { HBSM_B200_NOT_PROVIDED("write_to_buffer"); }              // H:244
+    void assign_from_buffer(const char*, size_t const) { HBSM_B200_NOT_PROVIDED("assign_from_buffer"); }        // H:245
+    void add_scaled_identity(HierarchicalBlockSparseMatrix<Treal> const&, Treal) { HBSM_B200_NOT_PROVIDED("add_scaled_identity"); }   // H:253
+    static void inv_chol(HierarchicalBlockSparseMatrix<Treal> const&, HierarchicalBlockSparseMatrix<Treal>&) { HBSM_B200_NOT_PROVIDED("inv_chol"); }   // H:268
+    static void adjust_sizes(HierarchicalBlockSparseMatrix<Treal>&, const int, const int) { HBSM_B200_NOT_PROVIDED("adjust_sizes"); }   // H:286
+    Treal get_trace() const { HBSM_B200_NOT_PROVIDED("get_trace"); }                                           // H:288
+    static void set_to_identity(HierarchicalBlockSparseMatrix<Treal>&, int) { HBSM_B200_NOT_PROVIDED("set_to_identity"); }   // H:290
+    size_t get_nnz_diag_lowest_level() const { HBSM_B200_NOT_PROVIDED("get_nnz_diag_lowest_level"); }           // H:293
+    void random_blocks(size_t) { HBSM_B200_NOT_PROVIDED("random_blocks"); }                                     // H:313
+    void get_frob_squared_of_error_matrix(std::vector<Treal>&, std::vector<Treal> const&) const { HBSM_B200_NOT_PROVIDED("get_frob_squared_of_error_matrix"); }   // H:336
+    bool frob_block_trunc(HierarchicalBlockSparseMatrix<Treal>&, Treal) const { HBSM_B200_NOT_PROVIDED("frob_block_trunc"); }   // H:352
+    static std::vector<unsigned long int> count_skips(HierarchicalBlockSparseMatrix<Treal> const&, const bool,
+                                                      HierarchicalBlockSparseMatrix<Treal> const&, const bool,
+                                                      std::vector<Treal> const&, const bool&, const bool&) { HBSM_B200_NOT_PROVIDED("count_skips"); }   // H:405
+    Treal get_max_abs_value() const { HBSM_B200_NOT_PROVIDED("get_max_abs_value"); }                            // H:410
+    static std::vector<Treal> get_errors_of_approx_multiplication(HierarchicalBlockSparseMatrix<Treal> const&, const bool,
+                                                                  HierarchicalBlockSparseMatrix<Treal> const&, const bool,
+                                                                  std::vector<Treal> const&, const bool&, const bool&) { HBSM_B200_NOT_PROVIDED("get_errors_of_approx_multiplication"); }   // H:412
+    static std::vector<Treal> get_spamm_errors(HierarchicalBlockSparseMatrix<Treal> const&, const bool,
+                                               HierarchicalBlockSparseMatrix<Treal> const&, const bool,
+                                               std::vector<Treal> const&) { HBSM_B200_NOT_PROVIDED("get_spamm_errors"); }   // H:415
+#undef HBSM_B200_NOT_PROVIDED
+
+    // ---- the reference's own "dummy function, for compatibility" stubs (H:271, H:317-427): same throwing behaviour ----
+#define HBSM_B200_STUB(name) \
+    throw std::runtime_error("Error in HierarchicalBlockSparseMatrix<Treal>::" name ": function not yet implemented.")
+    static void inv_chol_trunc(HierarchicalBlockSparseMatrix<Treal> const&, HierarchicalBlockSparseMatrix<Treal>&, Treal) { HBSM_B200_STUB("inv_chol_trunc"); }
+    void get_col_sums(std::vector<Treal>&) const { HBSM_B200_STUB("get_col_sums"); }
+    void get_col_sums_part(std::vector<Treal>&, const int, const int) const { HBSM_B200_STUB("get_col_sums_part"); }
+    void get_row_sums(std::vector<Treal>&) const { HBSM_B200_STUB("get_row_sums"); }
+    void get_row_sums_part(std::vector<Treal>&, const int, const int) const { HBSM_B200_STUB("get_row_sums_part"); }
+    void get_diag(std::vector<Treal>&) const { HBSM_B200_STUB("get_diag"); }
+    void get_diag_part(std::vector<Treal>&, int, int) const { HBSM_B200_STUB("get_diag_part"); }
+    void get_spectral_squared_of_error_matrix(std::vector<Treal>&, std::vector<Treal> const&, int, bool) const { HBSM_B200_STUB("get_spectral_squared_of_error_matrix"); }
+    Treal get_frob_squared_symm() const { HBSM_B200_STUB("get_frob_squared_symm"); }
+    void get_frob_squared_of_error_matrix_symm(std::vector<Treal>&, std::vector<Treal> const&) const { HBSM_B200_STUB("get_frob_squared_of_error_matrix_symm"); }
+    bool frob_block_trunc_symm(HierarchicalBlockSparseMatrix<Treal>&, Treal) const { HBSM_B200_STUB("frob_block_trunc_symm"); }
+    void set_neg_to_zero(const HierarchicalBlockSparseMatrix<Treal>&) { HBSM_B200_STUB("get_row_sums_part"); }
+    static void max(HierarchicalBlockSparseMatrix<Treal> const&, HierarchicalBlockSparseMatrix<Treal> const&, HierarchicalBlockSparseMatrix<Treal>&) { HBSM_B200_STUB("max"); }
+    Treal spectral_norm(int = 0, bool = false) const { HBSM_B200_STUB("spectral_norm"); }
+    void get_nnz_in_submatrix(std::vector<int>&, std::vector<int>&, std::vector<Treal>&, int, int, int, int) const { HBSM_B200_STUB("spectral_norm"); }
+    static void symm_rk_TN(HierarchicalBlockSparseMatrix<Treal> const&, HierarchicalBlockSparseMatrix<Treal>&) { HBSM_B200_STUB("symm_rk_TN"); }
+    static void symm_rk_NT(HierarchicalBlockSparseMatrix<Treal> const&, HierarchicalBlockSparseMatrix<Treal>&) { HBSM_B200_STUB("symm_rk_NT"); }
+    void symm_to_nosymm() { HBSM_B200_STUB("symm_to_nosymm"); }
+    void nosymm_to_symm() { HBSM_B200_STUB("nosymm_to_symm"); }
+    static void submatrix_inv_chol(std::vector<real> const&, std::vector<real>&, int, int) { HBSM_B200_STUB("submatrix_inv_chol"); }
+    static void anticommutator(HierarchicalBlockSparseMatrix<Treal> const&, HierarchicalBlockSparseMatrix<Treal> const&, HierarchicalBlockSparseMatrix<Treal>&) {
+        throw std::runtime_error("Error in HierarchicalBlockSparseMatrix<Treal>::anticommutator: function not applicable.");
+    }
+    static void symm_product(HierarchicalBlockSparseMatrix<Treal> const&, HierarchicalBlockSparseMatrix<Treal> const&, const bool, HierarchicalBlockSparseMatrix<Treal>&) {
+        throw std::runtime_error("Error in HierarchicalBlockSparseMatrix<Treal>::symm_product: function not applicable.");
+    }
+#undef HBSM_B200_STUB
+
+private:
+    hbsm_handle h_;
+};
+
+}  // namespace hbsm
+
+#endif

@@ -1,0 +1,228 @@
+// test_dropin.cc -- the reference's known-answer tests (test_source/test_matrix_operations.cc = TO:,
+// test_source/test_matrix_creation.cc = TC:) written against the drop-in C++ class
+// include/hbsm/HierarchicalBlockSparseMatrix.h, i.e. through the C ABI onto the B200.
+// Usage is deliberately that of a reference caller: same includes (via the umbrella header), same type name,
+// same method calls, exact `==` comparison of dense expansions.  Exit code 0 = all passed.
+#include <cmath>
+#include <cstdio>
+#include <initializer_list>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "hbsm/hierarchical_block_sparse_lib.h"
+
+template <class T>
+struct Coo {
+    std::vector<int> r, c;
+    std::vector<T> v;
+    void row(int i, std::initializer_list<double> vals) {   // like the reference's set_row: zeros are assigned too
+        int j = 0;
+        for (double x : vals) { r.push_back(i); c.push_back(j++); v.push_back((T)x); }
+    }
+};
+
+template <class M>
+void fill(M& A, int b, int m, int n, std::initializer_list<std::initializer_list<double> > rows) {
+    typename M::Params p; p.blocksize = b;
+    A.set_params(p);
+    A.resize(m, n);
+    Coo<typename M::real> s;
+    int i = 0;
+    for (auto& r : rows) s.row(i++, r);
+    A.assign_from_vectors(s.r, s.c, s.v);
+}
+
+template <class M>
+std::vector<double> dense(const M& A) {
+    std::vector<int> r, c;
+    std::vector<typename M::real> v;
+    A.get_all_values(r, c, v);
+    std::vector<double> d((size_t)A.get_n_rows() * A.get_n_cols(), 0.0);
+    for (size_t i = 0; i < r.size(); ++i) d[(size_t)r[i] * A.get_n_cols() + c[i]] = v[i];
+    return d;
+}
+
+static int g_checks = 0;
+#define REQUIRE(cond) do { ++g_checks; if (!(cond)) throw std::runtime_error(std::string("FAILED: ") + #cond + " at line " + std::to_string(__LINE__)); } while (0)
+
+template <class M>
+void expect(const M& A, int m, int n, std::initializer_list<std::initializer_list<double> > rows) {
+    REQUIRE(A.get_n_rows() == m && A.get_n_cols() == n);
+    std::vector<double> d = dense(A);
+    size_t k = 0;
+    for (auto& r : rows)
+        for (double x : r) {
+            // exact for doubles (integers / short decimals computed in a fixed order); one rounding for float inputs
+            REQUIRE(d[k] == (double)(typename M::real)x || std::fabs(d[k] - x) <= 1e-6 * std::fabs(x));
+            ++k;
+        }
+    REQUIRE(k == d.size());
+}
+
+template <class T>
+void run() {
+    typedef hbsm::HierarchicalBlockSparseMatrix<T> M;
+    // ---- creation, TC:27-128 ----
+    {
+        M A;
+        REQUIRE(A.empty());
+        typename M::Params p; p.blocksize = 4;
+        A.set_params(p);
+        REQUIRE(A.get_params().blocksize == 4);
+        A.resize(14, 14);
+        REQUIRE(!A.empty() && A.get_n_rows() == 14 && A.get_n_cols() == 14 && !A.children_exist());
+        std::vector<int> r = {0, 6}, c = {0, 7};
+        std::vector<T> v = {(T)7.7, (T)1.1};
+        A.assign_from_vectors(r, c, v);
+        REQUIRE(A.children_exist());
+        REQUIRE(std::fabs((double)A.get_frob_squared() - (7.7 * 7.7 + 1.1 * 1.1)) < 1e-5);
+        REQUIRE(A.get_nnz() == 2);
+        std::vector<int> qr = {0, 6, 3}, qc = {0, 7, 3};
+        std::vector<T> out;
+        A.get_values(qr, qc, out);
+        REQUIRE(out[0] == (T)7.7 && out[1] == (T)1.1 && out[2] == (T)0);
+        std::vector<int> ar, ac; std::vector<T> av;
+        A.get_all_values(ar, ac, av);
+        REQUIRE(ar.size() == 2 && ar[0] == 0 && ac[0] == 0 && ar[1] == 6 && ac[1] == 7);
+        A.clear();
+        REQUIRE(A.empty());
+        bool thrown = false;
+        try { A.get_frob_squared(); } catch (const std::runtime_error& e) { thrown = std::string(e.what()).find("empty matrix occured") != std::string::npos; }
+        REQUIRE(thrown);
+    }
+    // ---- transpose / add / multiply NN NT TN TT, TO:236-384 ----
+    M A, B, D;
+    fill(A, 2, 2, 3, {{2, 3, 5}, {0, 1, 2}});
+    fill(B, 2, 2, 3, {{1, 3, 2}, {6, 2, 4}});
+    fill(D, 2, 3, 2, {{2, 1}, {7, 3}, {3, 5}});
+    { M AT; M::transpose(A, AT); expect(AT, 3, 2, {{2, 0}, {3, 1}, {5, 2}}); }
+    { M C; M::add(A, B, C); expect(C, 2, 3, {{3, 6, 7}, {6, 3, 6}}); }
+    size_t nm = 0, nr = 0;
+    { M C; M::multiply(A, false, D, false, C, &nm, &nr); expect(C, 2, 2, {{40, 36}, {13, 13}}); REQUIRE(nm == 2 && nr == 1); }
+    { M C; M::multiply(D, false, A, false, C); expect(C, 3, 3, {{4, 7, 12}, {14, 24, 41}, {6, 14, 25}}); }
+    { M C; M::multiply(A, false, A, true, C); expect(C, 2, 2, {{38, 13}, {13, 5}}); }
+    { M C; M::multiply(A, true, A, false, C); expect(C, 3, 3, {{4, 6, 10}, {6, 10, 17}, {10, 17, 29}}); }
+    { M C; M::multiply(A, true, D, true, C); expect(C, 3, 3, {{4, 14, 6}, {7, 24, 14}, {12, 41, 25}}); }
+    {   // C must be empty on entry (H:5681)
+        M C; M::multiply(A, false, D, false, C);
+        bool thrown = false;
+        try { M::multiply(A, false, D, false, C); } catch (const std::runtime_error& e) { thrown = std::string(e.what()).find("non-empty matrix to write result") != std::string::npos; }
+        REQUIRE(thrown);
+        thrown = false;
+        M C2;
+        try { M::multiply(A, false, A, false, C2); } catch (const std::runtime_error& e) { thrown = std::string(e.what()).find("bad sizes") != std::string::npos; }
+        REQUIRE(thrown);
+    }
+    // ---- 2-level x 3-level at b = 3, TO:430-509 ----
+    {
+        M A5, B5;
+        fill(A5, 3, 5, 5, {{2, 2, 3, 5, 2}, {2, 1, 2, 4, 3}, {3, 2, 3, 1, 2}, {5, 4, 1, 4, 5}, {2, 3, 2, 5, 1}});
+        fill(B5, 3, 5, 7, {{5, 3, 1, 5, 0, 3, 3}, {1, 5, 5, 4, 1, 5, 1}, {2, 1, 3, 2, 1, 1, 4}, {2, 2, 3, 3, 1, 4, 2}, {5, 1, 1, 2, 1, 2, 3}});
+        REQUIRE(A5.get_depth() == 1 && B5.get_depth() == 2);
+        REQUIRE(M::worth_to_multiply(A5, false, B5, false));
+        M P; M::multiply(A5, false, B5, false, P);
+        expect(P, 5, 7, {{38, 31, 38, 43, 12, 43, 36}, {38, 24, 28, 36, 10, 35, 32}, {35, 26, 27, 36, 8, 30, 31}, {64, 49, 45, 65, 14, 62, 46}, {32, 34, 39, 43, 11, 45, 30}});
+        REQUIRE(P.get_depth() == 2);
+        M Q; M::multiply(B5, true, A5, false, Q);
+        expect(Q, 7, 5, {{38, 38, 35, 64, 32}, {31, 24, 26, 49, 34}, {38, 28, 27, 45, 39}, {43, 36, 36, 65, 43}, {12, 10, 8, 14, 11}, {43, 35, 30, 62, 45}, {36, 32, 31, 46, 30}});
+        REQUIRE(Q.get_n_block_multiplications() == 12);   // TO:507
+    }
+    // ---- rescale, TO:513-526 ----
+    { M R; R.rescale(A, (T)-1.0); expect(R, 2, 3, {{-2, -3, -5}, {0, -1, -2}}); }
+    // ---- symmetric family, TO:20-185 ----
+    {
+        M U, B7, C2;
+        fill(U, 2, 5, 5, {{2, 2, 3, 5, 2}, {0, 1, 2, 4, 3}, {0, 0, 3, 1, 2}, {0, 0, 0, 4, 5}, {0, 0, 0, 0, 1}});
+        fill(B7, 2, 5, 7, {{5, 3, 1, 5, 0, 3, 3}, {1, 5, 5, 4, 1, 5, 1}, {2, 1, 3, 2, 1, 1, 4}, {2, 2, 3, 3, 1, 4, 2}, {5, 1, 1, 2, 1, 2, 3}});
+        fill(C2, 2, 2, 5, {{5, 3, 0, 3, 3}, {1, 4, 1, 5, 1}});
+        { M P; M::symm_multiply(U, true, B7, false, P);
+          expect(P, 5, 7, {{38, 31, 38, 43, 12, 43, 36}, {38, 24, 28, 36, 10, 35, 32}, {35, 26, 27, 36, 8, 30, 31}, {64, 49, 45, 65, 14, 62, 46}, {32, 34, 39, 43, 11, 45, 30}}); }
+        { M P; M::symm_multiply(C2, false, U, true, P); expect(P, 2, 5, {{37, 34, 30, 64, 37}, {40, 31, 21, 47, 42}}); }
+        { M P; M::symm_square(U, P);
+          expect(P, 5, 5, {{46, 38, 28, 51, 43}, {0, 34, 24, 47, 34}, {0, 0, 27, 40, 25}, {0, 0, 0, 83, 49}, {0, 0, 0, 0, 43}}); }
+        { M P; M::symm_rk(A, false, P); expect(P, 2, 2, {{38, 13}, {0, 5}}); }
+        { M P; M::symm_rk(A, true, P); expect(P, 3, 3, {{4, 6, 10}, {0, 10, 17}, {0, 0, 29}}); }
+        bool thrown = false;
+        try { M P; M::symm_multiply(U, true, B7, true, P); } catch (const std::runtime_error&) { thrown = true; }
+        REQUIRE(thrown);
+    }
+    // ---- SpAMM, TO:634-742 ----
+    {
+        M As, Bs;
+        fill(As, 2, 4, 4, {{1, 2, 0.1, 0.1}, {2, 1, 0.1, 0.1}, {3, 1, 0, 0}, {5, 1, 0, 0.1}});
+        fill(Bs, 2, 4, 4, {{1, 6, 5, 0}, {0, 1, 2, 1}, {2, 1, 0.1, 0.1}, {0, 1, 0.1, 0.1}});
+        As.update_internal_info();
+        Bs.update_internal_info();
+        { M P; M::spamm(As, false, Bs, false, P, (T)0.2, true, &nm, &nr);
+          expect(P, 4, 4, {{1.2, 8.2, 9, 2}, {2.2, 13.2, 12, 1}, {3, 19, 17, 1}, {5, 31.1, 27, 1}});
+          REQUIRE(nm == 6 && nr == 4); }
+        { M P; M::spamm(As, false, Bs, true, P, (T)0.2, true, &nm, &nr); REQUIRE(nm == 6 && nr == 4); }
+        { M P; M::spamm(As, true, Bs, false, P, (T)0.2, true, &nm, &nr); REQUIRE(nm == 7 && nr == 4); }
+        { M P; M::spamm(As, true, Bs, true, P, (T)0.2, true, &nm, &nr); REQUIRE(nm == 7 && nr == 4); }
+        REQUIRE(M::worth_to_spamm(As, false, Bs, false, (T)0.2));
+        REQUIRE(!M::worth_to_spamm(As, false, Bs, false, (T)1e6));
+        // error vs tau = 0 via rescale + add + get_frob_squared (TO:714-723)
+        double prev = -1;
+        for (double tau : {0.0125, 0.025, 0.05, 0.1, 0.2, 0.4, 0.8}) {
+            M approx, exact, minus, err;
+            M::spamm(As, false, Bs, false, approx, (T)tau, true);
+            M::spamm(As, false, Bs, false, exact, (T)0.0, true);
+            minus.rescale(exact, (T)-1.0);
+            M::add(approx, minus, err);
+            double e = (double)err.get_frob_squared();
+            REQUIRE(e >= prev);
+            prev = e;
+        }
+    }
+    // ---- dummy-level squeeze and consistency, TO:782-912 ----
+    {
+        typename M::Params p; p.blocksize = 2;
+        M As, Bs;
+        As.set_params(p); As.resize(1, 4);
+        Bs.set_params(p); Bs.resize(4, 1);
+        std::vector<int> z4 = {0, 0, 0, 0}, i4 = {0, 1, 2, 3};
+        std::vector<T> v1 = {1, 2, 3, 4}, v2 = {5, 6, 7, 8};
+        As.assign_from_vectors(z4, i4, v1);
+        Bs.assign_from_vectors(i4, z4, v2);
+        M P; M::multiply(As, false, Bs, false, P);
+        expect(P, 1, 1, {{70}});
+        REQUIRE(P.get_depth() == 0);
+        M X; X.set_params(p); X.resize(4, 4);
+        REQUIRE(!X.check_if_matrix_is_consistent());
+        M Y; Y.set_params(p); Y.resize(2, 2);
+        REQUIRE(Y.check_if_matrix_is_consistent());
+        M A26, B62;
+        fill(A26, 1, 2, 6, {{1, 2, 3, 4, 5, 6}, {7, 8, 9, 10, 11, 12}});
+        fill(B62, 1, 6, 2, {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {1, 1}, {1, 1}});
+        M Q; M::multiply(A26, false, B62, false, Q);
+        expect(Q, 2, 2, {{11, 11}, {23, 23}});
+        REQUIRE(Q.get_depth() == 1);
+    }
+    // ---- value semantics of the drop-in: deep copy ----
+    {
+        M C1(A);
+        M C2; C2 = A;
+        expect(C1, 2, 3, {{2, 3, 5}, {0, 1, 2}});
+        expect(C2, 2, 3, {{2, 3, 5}, {0, 1, 2}});
+        bool thrown = false;
+        try { M U; A.get_upper_triangle(U); } catch (const std::runtime_error& e) {   // non-square: throws (H:3517)
+            thrown = std::string(e.what()).find("non-square") != std::string::npos;
+        }
+        REQUIRE(thrown);
+    }
+}
+
+int main() {
+    try {
+        if (hbsm_init(0) != HBSM_OK) { std::fprintf(stderr, "hbsm_init: %s\n", hbsm_last_error()); return 2; }
+        run<double>();
+        int nd = g_checks;
+        run<float>();
+        std::printf("test_dropin: %d checks passed (double %d, float %d)\n", g_checks, nd, g_checks - nd);
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "test_dropin: %s\n", e.what());
+        return 1;
+    }
+}
