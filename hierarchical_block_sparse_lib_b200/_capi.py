@@ -80,6 +80,8 @@ SIGNATURES = {
     "hbsm_set_gemm_variant": (_I, [_I]),
     "hbsm_device_table": (_I, [_H, C.POINTER(_sz), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "hbsm_assign_device_tiles": (_I, [_H, _sz, _P, _P, _P]),
+    "hbsm_halo_reserve": (_I, [_H, _sz, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "hbsm_halo_commit": (_I, [_H, _sz]),
     "hbsm_generate_decay": (_I, [_H, _I, _P, _I, C.c_uint64, _I, _I, _I]),
     "hbsm_morton_encode": (C.c_uint64, [C.c_uint32, C.c_uint32]),
     "hbsm_morton_decode": (None, [C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

@@ -321,6 +321,15 @@ int hbsm_assign_device_tiles(hbsm_handle h, size_t n_tiles, const uint64_t* d_mo
         assign_tiles_device(M(h), n_tiles, d_morton_keys, d_tiles, d_norms_or_null);
     });
 }
+int hbsm_halo_reserve(hbsm_handle h, size_t capacity, uint64_t** d_keys, void** d_norms, void** d_tiles) {
+    return guarded([&] { reserve_halo(M(h), capacity, d_keys, d_norms, d_tiles); });
+}
+int hbsm_halo_commit(hbsm_handle h, size_t n_halo) {
+    return guarded([&] {
+        HB_CUDA(cudaDeviceSynchronize());   // the tail was filled on the caller's (NCCL) stream: order it before ours
+        commit_halo(M(h), n_halo);
+    });
+}
 int hbsm_generate_decay(hbsm_handle h, int n, const double* table, int W, uint64_t seed, int symmetric, int row_tile_lo,
                         int row_tile_hi) {
     return guarded([&] { generate_decay(M(h), n, table, W, seed, symmetric != 0, row_tile_lo, row_tile_hi); });

@@ -52,6 +52,7 @@ void Matrix::clear() {  // H:614
     invalidate_indices();
     drop_tasks();
     L = 0; M = 0; N = 0; sized = false;
+    halo_cap = 0; n_halo = 0;
     root_norm_cached = 0.0;
 }
 
@@ -73,9 +74,43 @@ void Matrix::set_table(DevBuf<uint64_t>&& k, DevBuf<char>&& t, size_t count) {
     keys = std::move(k);
     tiles = std::move(t);
     L = count;
+    halo_cap = 0; n_halo = 0;
     norms.alloc(std::max<size_t>(count, 1) * esize());
     norms.zero();
     invalidate_indices();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// halo tail (multi-GPU op(B) operand): grow the three arrays once, hand out pointers to the tail
+// ---------------------------------------------------------------------------------------------------
+void reserve_halo(Matrix& A, size_t cap, uint64_t** d_keys, void** d_norms, void** d_tiles) {
+    if (!A.sized) throw Error(HBSM_E_ARG, "hbsm_b200: halo reserve on an unsized matrix");
+    ensure_engine();
+    if (A.vdepth() == 0 && cap > 0) throw Error(HBSM_E_ARG, "hbsm_b200: a single-leaf matrix has no halo");
+    if (cap > A.halo_cap) {
+        const size_t tot = A.L + cap;
+        DevBuf<uint64_t> k(tot);
+        DevBuf<char> t(tot * A.tile_bytes()), nr(tot * A.esize());
+        if (A.L) {
+            HB_CUDA(cudaMemcpyAsync(k.p, A.keys.p, A.L * sizeof(uint64_t), cudaMemcpyDeviceToDevice, engine().stream));
+            HB_CUDA(cudaMemcpyAsync(t.p, A.tiles.p, A.L * A.tile_bytes(), cudaMemcpyDeviceToDevice, engine().stream));
+            HB_CUDA(cudaMemcpyAsync(nr.p, A.norms.p, A.L * A.esize(), cudaMemcpyDeviceToDevice, engine().stream));
+        }
+        A.keys = std::move(k); A.tiles = std::move(t); A.norms = std::move(nr);
+        A.halo_cap = cap;
+        sync_stream();
+    }
+    A.n_halo = 0;
+    A.ext_by_row.reset(); A.ext_by_col.reset();
+    if (d_keys) *d_keys = A.keys.p + A.L;
+    if (d_norms) *d_norms = A.norms.p + A.L * A.esize();
+    if (d_tiles) *d_tiles = A.tiles.p + A.L * A.tile_bytes();
+}
+
+void commit_halo(Matrix& A, size_t n_halo) {
+    if (n_halo > A.halo_cap) throw Error(HBSM_E_ARG, "hbsm_b200: halo commit beyond the reserved capacity");
+    A.n_halo = n_halo;
+    A.ext_by_row.reset(); A.ext_by_col.reset();
 }
 
 namespace {
@@ -621,7 +656,7 @@ void assign_coo(Matrix& A, size_t n, const int* rows, const int* cols, const voi
         std::vector<uint64_t> ka = A.keys.to_host(), kn = tkeys.to_host();
         const int sh = 2 * (depth - 1);
         bool have[4] = {false, false, false, false};
-        for (uint64_t k : ka) have[(k >> sh) & 3] = true;
+        for (size_t i = 0; i < A.L; ++i) have[(ka[i] >> sh) & 3] = true;   // (a halo tail, if any, is not part of A)
         for (uint64_t k : kn)
             if (have[(k >> sh) & 3]) {
                 char msg[160];
@@ -841,23 +876,25 @@ double frob_squared(const Matrix& A) {   // H:641
 // ---------------------------------------------------------------------------------------------------
 // line indices
 // ---------------------------------------------------------------------------------------------------
-const LineIndex& line_index(const Matrix& A, bool by_col) {
-    LineIndex& ix = const_cast<LineIndex&>(by_col ? A.by_col : A.by_row);
+const LineIndex& line_index(const Matrix& A, bool by_col, bool with_halo) {
+    const bool ext = with_halo && A.n_halo > 0;
+    LineIndex& ix = const_cast<LineIndex&>(ext ? (by_col ? A.ext_by_col : A.ext_by_row) : (by_col ? A.by_col : A.by_row));
     if (ix.valid) return ix;
     ensure_engine();
     const int depth = A.vdepth();
     const int dbits = std::max(depth, 1);
+    const size_t n = ext ? A.n_ext() : A.L;   // halo keys sit behind the owned ones, in any order
     ix.n_lines = A.grid_side();
     ix.ptr.alloc((size_t)ix.n_lines + 1);
-    ix.other.alloc(std::max<size_t>(A.L, 1));
-    ix.tile.alloc(std::max<size_t>(A.L, 1));
-    if (A.L == 0) {
+    ix.other.alloc(std::max<size_t>(n, 1));
+    ix.tile.alloc(std::max<size_t>(n, 1));
+    if (n == 0) {
         ix.ptr.zero();
     } else {
-        DevBuf<uint64_t> skey(A.L);
-        HB_LAUNCH(k_line_keys, blocks_for(A.L, 256), 256, 0, A.keys.p, A.L, by_col ? 1 : 0, dbits, skey.p, ix.tile.p);
-        radix_sort_pairs(skey.p, ix.tile.p, A.L, 2 * dbits);
-        HB_LAUNCH(k_line_ptr, blocks_for(A.L, 256), 256, 0, skey.p, A.L, dbits, ix.n_lines, ix.ptr.p, ix.other.p);
+        DevBuf<uint64_t> skey(n);
+        HB_LAUNCH(k_line_keys, blocks_for(n, 256), 256, 0, A.keys.p, n, by_col ? 1 : 0, dbits, skey.p, ix.tile.p);
+        radix_sort_pairs(skey.p, ix.tile.p, n, 2 * dbits);
+        HB_LAUNCH(k_line_ptr, blocks_for(n, 256), 256, 0, skey.p, n, dbits, ix.n_lines, ix.ptr.p, ix.other.p);
     }
     ix.valid = true;
     return ix;

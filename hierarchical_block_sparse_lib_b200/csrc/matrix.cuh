@@ -34,6 +34,11 @@ struct Matrix {
     double root_norm_cached = 0.0;  // frob_norm_squared_internal of the root, stored exactly (float values fit)
     size_t n_mults = 0;
     LineIndex by_row, by_col;
+    // halo tail (multi-GPU): keys/norms/tiles have room for `halo_cap` more tiles after the L owned ones; the first
+    // `n_halo` of them hold tiles received from peer ranks for the next product in which this matrix is op(B).
+    // Halo keys are NOT merged into the sorted table: the product only needs (line, other, tile index) triples.
+    size_t halo_cap = 0, n_halo = 0;
+    LineIndex ext_by_row, ext_by_col;   // line indices over the L + n_halo tiles
     // executed products of the call that produced this matrix (parity hook, hbsm_export_tasks)
     DevBuf<uint64_t> task_begin;    // [L + 1]
     DevBuf<uint32_t> task_k;        // [P]
@@ -54,7 +59,8 @@ struct Matrix {
         return P;
     }
     uint32_t grid_side() const { return 1u << vdepth(); }
-    void invalidate_indices() { by_row.reset(); by_col.reset(); }
+    void invalidate_indices() { by_row.reset(); by_col.reset(); ext_by_row.reset(); ext_by_col.reset(); }
+    size_t n_ext() const { return L + n_halo; }
     void drop_tasks() { task_begin.release(); task_k.release(); n_tasks = 0; }
     void clear();                     // H:614
     void resize(int m, int n);        // H:544
@@ -72,7 +78,9 @@ void compute_leaf_norms(const Matrix& A, void* d_out);   // bit-exact sequential
 double hierarchical_norm(const Matrix& A, const void* d_leaf_norms);   // root value of H:3918-3923 / H:656-662
 void update_norms(Matrix& A);
 double frob_squared(const Matrix& A);
-const LineIndex& line_index(const Matrix& A, bool by_col);
+const LineIndex& line_index(const Matrix& A, bool by_col, bool with_halo = false);
+void reserve_halo(Matrix& A, size_t cap, uint64_t** d_keys, void** d_norms, void** d_tiles);   // tail pointers
+void commit_halo(Matrix& A, size_t n_halo);
 void op_add(const Matrix& A, const Matrix& B, Matrix& C);
 void op_transpose(const Matrix& A, Matrix& C);
 void op_upper(const Matrix& A, Matrix& C);

@@ -569,7 +569,7 @@ bool launch_gemm_f64_tma_inst(const Matrix& A, const Matrix& B, const uint2* ab,
     using Cfg = TmaCfg<BS, KC>;
     CUtensorMap mapA, mapB;
     if (!make_tile_map(&mapA, A.tiles.p, A.L, BS, KC, TA, 8, CU_TENSOR_MAP_DATA_TYPE_FLOAT64)) return false;
-    if (!make_tile_map(&mapB, B.tiles.p, B.L, BS, KC, !TB, 8, CU_TENSOR_MAP_DATA_TYPE_FLOAT64)) return false;
+    if (!make_tile_map(&mapB, B.tiles.p, B.n_ext(), BS, KC, !TB, 8, CU_TENSOR_MAP_DATA_TYPE_FLOAT64)) return false;
     auto kfn = k_gemm_f64_tma<BS, KC, TA, TB>;
     static bool configured = false;
     if (!configured) {
@@ -603,10 +603,10 @@ struct TaskList {
 void build_tasks(const Matrix& A, bool tA, const Matrix& B, bool tB, const ProductOpts& o, int kbits, TaskList& tl,
                  bool count_only) {
     const LineIndex& la = line_index(A, tA);   // op(A): lines are C rows
-    const LineIndex& lb = line_index(B, tB);   // op(B): lines are k
+    const LineIndex& lb = line_index(B, tB, true);   // op(B): lines are k; includes the halo tail if one is committed
     tl.n_products = tl.n_ctiles = 0;
     tl.n_candidates = 0;
-    if (A.L == 0 || B.L == 0) return;
+    if (A.L == 0 || B.n_ext() == 0) return;
     JoinArgs g{};
     g.a_ptr = la.ptr.p; g.a_other = la.other.p; g.a_tile = la.tile.p; g.a_lines = la.n_lines;
     g.b_ptr = lb.ptr.p; g.b_other = lb.other.p; g.b_tile = lb.tile.p; g.b_lines = lb.n_lines;
@@ -731,7 +731,7 @@ void op_product(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, c
     t_norm.stop();
     t_index.start();
     line_index(A, tA);
-    line_index(B, tB);
+    line_index(B, tB, true);
     t_index.stop();
 
     t_task.start();

@@ -81,28 +81,29 @@ def request_thresholds(a_keys, a_norms, tA, grid_side):
 
 
 def select_for_peers(b_keys, b_norms, tB, thr_from_peers, lo, spamm, tau):
-    """thr_from_peers[q, k - lo] = request of rank q for my row k.  Returns (send_index, counts[q]): indices into my
-    op(B) tile list, grouped by destination rank, ascending Morton key inside a group."""
+    """thr_from_peers[q, k - lo] = request of rank q for my row k (-1 = none).  Returns (send_index, counts[q]):
+    indices into my op(B) tile list, grouped by destination rank, ascending Morton key inside a group."""
     br, bc = morton_decode(b_keys)
     k = (bc if tB else br) - lo
     world = thr_from_peers.shape[0]
-    idx, counts = [], []
+    if k.numel() == 0:
+        return torch.zeros(0, dtype=torch.int64, device=b_keys.device), [0] * world
+    t = thr_from_peers[:, k]                          # [world, L_b]
+    keep = t >= 0
     if spamm:
         tau2 = torch.tensor(tau, dtype=b_norms.dtype, device=b_norms.device)
-        tau2 = tau2 * tau2                      # fl(tau*tau) in Treal, H:2008
-    for q in range(world):
-        t = thr_from_peers[q][k] if k.numel() else thr_from_peers[q][:0]
-        keep = t >= 0
-        if spamm:
-            keep = keep & ((t * b_norms) > tau2)   # fl(max_na * nb) > fl(tau^2): same rounding as the leaf-pair test
-        sel = torch.nonzero(keep, as_tuple=False).flatten()
-        idx.append(sel)
-        counts.append(int(sel.numel()))
-    return (torch.cat(idx) if idx else torch.zeros(0, dtype=torch.int64)), counts
+        tau2 = tau2 * tau2                            # fl(tau*tau) in Treal, H:2008
+        keep &= (t * b_norms.unsqueeze(0)) > tau2     # fl(max_na * nb) > fl(tau^2): same rounding as the leaf-pair test
+    nz = torch.nonzero(keep, as_tuple=False)          # row-major: grouped by peer, ascending tile index inside
+    counts = torch.bincount(nz[:, 0], minlength=world).tolist()
+    return nz[:, 1].contiguous(), [int(c) for c in counts]
 
 
-def exchange_b(a_keys, a_norms, tA, b_keys, b_norms, b_tiles, tB, grid_side, spamm, tau, group=None, timers=None):
-    """Runs steps 1-3.  Returns (keys, norms, tiles) of the op(B) tiles this rank's products can touch."""
+def exchange_b(a_keys, a_norms, tA, b_keys, b_norms, b_tiles, tB, grid_side, spamm, tau, group=None, timers=None,
+               recv_alloc=None):
+    """Runs steps 1-3.  Returns (keys, norms, tiles) of the REMOTE op(B) tiles this rank's products can touch (the
+    rank's own tiles never move).  `recv_alloc(n)` may supply the three receive buffers (the engine's halo tail, so
+    NCCL writes in place); by default they are fresh tensors."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     lo, hi = slab_bounds(grid_side, world, rank)
@@ -111,7 +112,9 @@ def exchange_b(a_keys, a_norms, tA, b_keys, b_norms, b_tiles, tB, grid_side, spa
     thr = request_thresholds(a_keys, a_norms, tA, grid_side)              # [g] -> slice p goes to rank p
     thr_in = torch.empty_like(thr)
     dist.all_to_all_single(thr_in, thr, group=group)                      # equal splits of `rows`
-    send_idx, counts = select_for_peers(b_keys, b_norms, tB, thr_in.view(world, rows), lo, spamm, tau)
+    thr_in = thr_in.view(world, rows).clone()
+    thr_in[rank] = -1.0                                                   # own tiles are already here
+    send_idx, counts = select_for_peers(b_keys, b_norms, tB, thr_in, lo, spamm, tau)
     cnt_out = torch.tensor(counts, dtype=torch.int64, device=b_keys.device)
     cnt_in = torch.empty_like(cnt_out)
     dist.all_to_all_single(cnt_in, cnt_out, group=group)
@@ -121,16 +124,19 @@ def exchange_b(a_keys, a_norms, tA, b_keys, b_norms, b_tiles, tB, grid_side, spa
     keys_out = b_keys.index_select(0, send_idx)
     norms_out = b_norms.index_select(0, send_idx)
     tiles_out = b_tiles.index_select(0, send_idx)
-    keys_in = torch.empty((n_in,), dtype=b_keys.dtype, device=b_keys.device)
-    norms_in = torch.empty((n_in,), dtype=b_norms.dtype, device=b_keys.device)
-    tiles_in = torch.empty((n_in, b_tiles.shape[1]), dtype=b_tiles.dtype, device=b_keys.device)
+    if recv_alloc is not None:
+        keys_in, norms_in, tiles_in = recv_alloc(n_in)
+    else:
+        keys_in = torch.empty((n_in,), dtype=b_keys.dtype, device=b_keys.device)
+        norms_in = torch.empty((n_in,), dtype=b_norms.dtype, device=b_keys.device)
+        tiles_in = torch.empty((n_in, b_tiles.shape[1]), dtype=b_tiles.dtype, device=b_keys.device)
     dist.all_to_all_single(keys_in, keys_out, recv_counts, counts, group=group)
     dist.all_to_all_single(norms_in, norms_out, recv_counts, counts, group=group)
     dist.all_to_all_single(tiles_in, tiles_out, recv_counts, counts, group=group)
     if timers is not None:
         timers["plan_s"] = t1 - t0
-        timers["sent_tiles"] = sum(counts) - counts[rank]
-        timers["recv_tiles"] = n_in - recv_counts[rank]
+        timers["sent_tiles"] = sum(counts)
+        timers["recv_tiles"] = n_in
     return keys_in, norms_in, tiles_in
 
 
@@ -161,36 +167,52 @@ def device_views(Mx):
     return keys, norms, tiles
 
 
-def matrix_from_device(dtype, b, m, n, keys, norms, tiles):
+def _tail_views(Mx, cap):
+    """Reserve room for `cap` halo tiles behind Mx's own tiles; zero-copy torch views of the three tail arrays."""
     from . import _capi
-    from .matrix import HierarchicalBlockSparseMatrix as H
-    Mx = H(dtype, b)
-    Mx.resize(m, n)
-    if keys.numel():
-        _capi.check(_capi.lib().hbsm_assign_device_tiles(Mx._h, keys.numel(), C.c_void_p(keys.data_ptr()),
-                                                         C.c_void_p(tiles.data_ptr()), C.c_void_p(norms.data_ptr())))
-    return Mx
+    pk = C.c_void_p(); pn = C.c_void_p(); pt = C.c_void_p()
+    _capi.check(_capi.lib().hbsm_halo_reserve(Mx._h, cap, C.byref(pk), C.byref(pn), C.byref(pt)))
+    b = Mx.get_params().blocksize
+    ts = "<f8" if Mx.dtype == np.float64 else "<f4"
+    dev = torch.device("cuda", torch.cuda.current_device())
+    return (torch.as_tensor(_DevArray(pk.value, (cap,), "<i8"), device=dev),
+            torch.as_tensor(_DevArray(pn.value, (cap,), ts), device=dev),
+            torch.as_tensor(_DevArray(pt.value, (cap, b * b), ts), device=dev))
 
 
 def sharded_product(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, group=None, timers=None):
     """C_r = op(A)_r * op(B): A_loc / B_loc are this rank's engine matrices (full logical dims, only the slab's tiles;
-    norms refreshed).  Returns (C_loc, n_mults_local, n_blocks_local)."""
+    norms refreshed).  Remote op(B) tiles are received straight into B_loc's halo tail (hbsm_halo_reserve/commit), the
+    rank's own tiles are never copied.  Returns (C_loc, n_mults_local, n_blocks_local)."""
+    from . import _capi
     from .matrix import HierarchicalBlockSparseMatrix as H
     grid_side = 1 << max(A_loc.expected_depth(), B_loc.expected_depth())
-    ak, an, _ = device_views(A_loc)
-    bk, bn, bt = device_views(B_loc)
-    from . import _capi
     ext = torch.cuda.ExternalStream(int(_capi.lib().hbsm_stream() or 0))
     with torch.cuda.stream(ext):
-        keys, norms, tiles = exchange_b(ak, an, tA, bk, bn, bt, tB, grid_side, spamm, tau, group, timers)
+        ak, an, _ = device_views(A_loc)
+        bk, bn, bt = device_views(B_loc)
+
+        def recv_alloc(n):
+            if n == 0:
+                return bk[:0], bn[:0], bt[:0]
+            cap = getattr(B_loc, "_halo_cap", 0)
+            if n > cap:                                   # grow geometrically; steady state: no reallocation
+                cap = max(n + n // 4, 64)
+                B_loc._halo_cap = cap
+            k, nr, t = _tail_views(B_loc, cap)            # (re)reads the pointers: a growth moves the arrays
+            return k[:n], nr[:n], t[:n]
+
+        keys, norms, tiles = exchange_b(ak, an, tA, bk, bn, bt, tB, grid_side, spamm, tau, group, timers, recv_alloc)
         ext.synchronize()
-    bm, bnn = B_loc.get_n_rows(), B_loc.get_n_cols()
-    Bh = matrix_from_device(B_loc.dtype, B_loc.get_params().blocksize, bm, bnn, keys, norms, tiles)
+    _capi.check(_capi.lib().hbsm_halo_commit(B_loc._h, keys.numel()))
     Cm = H(A_loc.dtype)
-    if spamm:
-        nm, nb = H.spamm(A_loc, tA, Bh, tB, Cm, tau, True)
-    else:
-        nm, nb = H.multiply(A_loc, tA, Bh, tB, Cm)
+    try:
+        if spamm:
+            nm, nb = H.spamm(A_loc, tA, B_loc, tB, Cm, tau, True)
+        else:
+            nm, nb = H.multiply(A_loc, tA, B_loc, tB, Cm)
+    finally:
+        _capi.check(_capi.lib().hbsm_halo_commit(B_loc._h, 0))
     return Cm, nm, nb
 
 

@@ -126,6 +126,13 @@ int hbsm_device_table(hbsm_handle h, size_t* n_tiles, const uint64_t** d_morton_
 /* build a matrix from device arrays (keys need not be sorted; tiles column-major, b*b each); copies */
 int hbsm_assign_device_tiles(hbsm_handle h, size_t n_tiles, const uint64_t* d_morton_keys, const void* d_tiles,
                              const void* d_norms_or_null);
+/* Halo tail of an op(B) operand (multi-GPU): make room for `capacity` more tiles behind the matrix's own
+ * ones and return device pointers to the tail of its key / leaf-norm / tile arrays, so that tiles owned by peer ranks
+ * can be received in place (NCCL writes straight into the tail).  hbsm_halo_commit(h, n) makes the first n tail tiles
+ * part of the NEXT products in which h is the right operand (they never enter h's own block table: readback, add,
+ * norms of h are unaffected); n = 0 drops them.  Any modification of h drops the halo. */
+int hbsm_halo_reserve(hbsm_handle h, size_t capacity, uint64_t** d_keys, void** d_norms, void** d_tiles);
+int hbsm_halo_commit(hbsm_handle h, size_t n_halo);
 /* banded decay generator a_ij = (0.5+0.5u(seed,i,j)) * table[|i-j|], |i-j| <= W (table has W+1 entries, e.g.
  * exp(-lambda d)), built on device; u = splitmix64 hash -> [0,1); symmetric != 0 uses u(seed,min,max).
  * Tile rows [row_tile_lo,row_tile_hi) only (shard); full matrix with 0,-1. */

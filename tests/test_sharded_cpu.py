@@ -47,10 +47,14 @@ def _worker(rank, world, port, n, b, lam, tA, tB, spamm, tau, dtype_name, ret):
         am = (a_line >= lo) & (a_line < hi); bm = (b_line >= lo) & (b_line < hi)
         timers = {}
         keys, norms, tiles = S.exchange_b(ak[am], an[am], tA, bk[bm], bn[bm], bt[bm], tB, g, spamm, tau, None, timers)
-        # received tiles are the global ones, bit for bit
+        # received (remote) tiles are the global ones, bit for bit, and none of them is owned by this rank
         pos = torch.searchsorted(bk, keys)
         assert torch.equal(bk[pos], keys) and torch.equal(bt[pos], tiles) and torch.equal(bn[pos], norms)
         assert keys.unique().numel() == keys.numel()
+        assert not bm[pos].any()
+        n_remote = keys.numel()
+        # what the engine multiplies with: own tiles followed by the halo tail
+        keys = torch.cat([bk[bm], keys]); norms = torch.cat([bn[bm], norms])
         # local executed set by the flat leaf-pair rule on (A_r, received B)
         rr, rc = S.morton_decode(keys)
         rk, rj = (rc, rr) if tB else (rr, rc)
@@ -66,7 +70,7 @@ def _worker(rank, world, port, n, b, lam, tA, tB, spamm, tau, dtype_name, ret):
             used |= m
             for j in rjn[m]:
                 tasks.append((int(i), int(j), int(k)))
-        assert used.all(), "a tile was shipped that no product of this rank touches"
+        assert used[len(used) - n_remote:].all(), "a tile was shipped that no product of this rank touches"
         ret[rank] = (np.array(tasks, np.int64).reshape(-1, 3), timers)
     finally:
         dist.destroy_process_group()
