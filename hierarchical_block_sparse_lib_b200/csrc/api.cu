@@ -321,6 +321,16 @@ int hbsm_assign_device_tiles(hbsm_handle h, size_t n_tiles, const uint64_t* d_mo
         assign_tiles_device(M(h), n_tiles, d_morton_keys, d_tiles, d_norms_or_null);
     });
 }
+int hbsm_halo_request(hbsm_handle A, int tA, void* d_thr) {
+    return guarded([&] { halo_request(M(A), tA != 0, d_thr); });
+}
+int hbsm_halo_select(hbsm_handle B, int tB, const void* d_thr_in, int world, int rank, int lo, int rows, int spamm, double tau,
+                     int64_t* d_send_idx, size_t* counts) {
+    return guarded([&] {
+        if (world < 1 || rank < 0 || rank >= world || lo < 0 || rows < 0 || !counts) throw Error(HBSM_E_ARG, "hbsm_b200: bad halo_select arguments");
+        halo_select(M(B), tB != 0, d_thr_in, world, rank, (uint32_t)lo, (uint32_t)rows, spamm != 0, tau, d_send_idx, counts);
+    });
+}
 int hbsm_halo_reserve(hbsm_handle h, size_t capacity, uint64_t** d_keys, void** d_norms, void** d_tiles) {
     return guarded([&] { reserve_halo(M(h), capacity, d_keys, d_norms, d_tiles); });
 }

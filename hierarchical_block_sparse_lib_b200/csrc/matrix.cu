@@ -584,6 +584,53 @@ __global__ void __launch_bounds__(256) k_decay_fill(const uint64_t* __restrict__
     }
 }
 
+// ---- multi-GPU halo planning (host-side orchestration in sharded.py) ----
+// request: thr[k] = max leaf norm^2 over this rank's op(A) tiles (., k), -1 where there is none.  Non-negative IEEE
+// values order like signed integers, and -1.0 is a negative integer, so a signed atomicMax on the bit pattern works.
+template <typename T> struct Bits;
+template <> struct Bits<double> { typedef long long I; };
+template <> struct Bits<float> { typedef int I; };
+template <typename T>
+__global__ void k_halo_fill(T* __restrict__ thr, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) thr[i] = (T)-1;
+}
+template <typename T>
+__global__ void k_halo_request(const uint64_t* __restrict__ keys, const T* __restrict__ norms, size_t L, int by_row_k,
+                               T* __restrict__ thr) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L) return;
+    const uint32_t k = by_row_k ? morton_row(keys[i]) : morton_col(keys[i]);
+    typedef typename Bits<T>::I I;
+    T v = norms[i];
+    atomicMax(reinterpret_cast<I*>(thr) + k, *reinterpret_cast<I*>(&v));
+}
+// select: entry e = q * L + i asks "does peer q need my op(B) tile i?"  (k of the tile inside my slab, request >= 0,
+// and for SpAMM fl(max_na * nb) > fl(tau*tau): the leaf-pair predicate of H:2008 against the requester's best A tile)
+template <typename T>
+__global__ void k_halo_flags(const uint64_t* __restrict__ keys, const T* __restrict__ norms, size_t L, int by_col_k,
+                             const T* __restrict__ thr_in, int world, int rank, uint32_t lo, uint32_t rows, int spamm,
+                             T tau2, uint32_t* __restrict__ flags) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)world * L) return;
+    const int q = (int)(e / L);
+    const size_t i = e % L;
+    const uint32_t k = by_col_k ? morton_col(keys[i]) : morton_row(keys[i]);
+    bool keep = false;
+    if (q != rank && k >= lo && k < lo + rows) {
+        const T t = thr_in[(size_t)q * rows + (k - lo)];
+        keep = t >= (T)0;
+        if (keep && spamm) keep = DT<T>::mul(t, norms[i]) > tau2;
+    }
+    flags[e] = keep ? 1u : 0u;
+}
+__global__ void k_halo_compact(const uint32_t* __restrict__ flags, const uint64_t* __restrict__ pos, size_t n, size_t L,
+                               int64_t* __restrict__ send_idx) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n || !flags[e]) return;
+    send_idx[pos[e]] = (int64_t)(e % L);
+}
+
 template <typename F>
 void dispatch(int dtype, F&& f) {
     if (dtype == HBSM_F64) f((double)0);
@@ -871,6 +918,42 @@ double frob_squared(const Matrix& A) {   // H:641
     DevBuf<char> tmp(A.L * A.esize());
     compute_leaf_norms(A, tmp.p);
     return hierarchical_norm(A, tmp.p);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU halo planning
+// ---------------------------------------------------------------------------------------------------
+void halo_request(const Matrix& A, bool tA, void* d_thr) {
+    ensure_engine();
+    const uint32_t g = A.grid_side();
+    dispatch(A.dtype, [&](auto z) {
+        using T = decltype(z);
+        HB_LAUNCH(k_halo_fill<T>, blocks_for(g, 256), 256, 0, (T*)d_thr, g);
+        if (A.L) HB_LAUNCH(k_halo_request<T>, blocks_for(A.L, 256), 256, 0, A.keys.p, (const T*)A.norms.p, A.L, tA ? 1 : 0, (T*)d_thr);
+    });
+}
+
+void halo_select(const Matrix& B, bool tB, const void* d_thr_in, int world, int rank, uint32_t lo, uint32_t rows, bool spamm,
+                 double tau, int64_t* d_send_idx, size_t* h_counts) {
+    ensure_engine();
+    for (int q = 0; q < world; ++q) h_counts[q] = 0;
+    if (B.L == 0 || world <= 0) return;
+    const size_t n = (size_t)world * B.L;
+    DevBuf<uint32_t> flags(n);
+    dispatch(B.dtype, [&](auto z) {
+        using T = decltype(z);
+        const T tt = (T)tau;
+        HB_LAUNCH(k_halo_flags<T>, blocks_for(n, 256), 256, 0, B.keys.p, (const T*)B.norms.p, B.L, tB ? 1 : 0, (const T*)d_thr_in,
+                  world, rank, lo, rows, spamm ? 1 : 0, (T)(tt * tt), flags.p);
+    });
+    DevBuf<uint64_t> pos(n + 1);
+    exclusive_scan_u32(flags.p, pos.p, n);
+    HB_LAUNCH(k_halo_compact, blocks_for(n, 256), 256, 0, flags.p, pos.p, n, B.L, d_send_idx);
+    std::vector<uint64_t> edge((size_t)world + 1);
+    for (int q = 0; q <= world; ++q)
+        HB_CUDA(cudaMemcpyAsync(&edge[q], pos.p + (size_t)q * B.L, sizeof(uint64_t), cudaMemcpyDeviceToHost, engine().stream));
+    sync_stream();
+    for (int q = 0; q < world; ++q) h_counts[q] = (size_t)(edge[q + 1] - edge[q]);
 }
 
 // ---------------------------------------------------------------------------------------------------

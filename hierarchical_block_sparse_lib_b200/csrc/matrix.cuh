@@ -81,6 +81,9 @@ double frob_squared(const Matrix& A);
 const LineIndex& line_index(const Matrix& A, bool by_col, bool with_halo = false);
 void reserve_halo(Matrix& A, size_t cap, uint64_t** d_keys, void** d_norms, void** d_tiles);   // tail pointers
 void commit_halo(Matrix& A, size_t n_halo);
+void halo_request(const Matrix& A, bool tA, void* d_thr);
+void halo_select(const Matrix& B, bool tB, const void* d_thr_in, int world, int rank, uint32_t lo, uint32_t rows, bool spamm,
+                 double tau, int64_t* d_send_idx, size_t* h_counts);
 void op_add(const Matrix& A, const Matrix& B, Matrix& C);
 void op_transpose(const Matrix& A, Matrix& C);
 void op_upper(const Matrix& A, Matrix& C);

@@ -25,6 +25,25 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+TRACE = bool(int(os.environ.get("HBSM_SHARD_TRACE", "0")))
+
+
+class _Trace:
+    """Synchronising phase timer, only active with HBSM_SHARD_TRACE=1 (diagnosis; perturbs the timings it reports)."""
+
+    def __init__(self, sink):
+        self.sink = sink if TRACE else None
+        self.t = time.perf_counter()
+
+    def mark(self, name):
+        if self.sink is None:
+            return
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        now = time.perf_counter()
+        self.sink[name] = self.sink.get(name, 0.0) + (now - self.t)
+        self.t = now
+
 # ---------------------------------------------------------------------------------------------------
 # Morton helpers on int64 tensors (digit = 2*colbit + rowbit, H:52-56; same bit tricks as csrc/common.cuh)
 # ---------------------------------------------------------------------------------------------------
@@ -109,21 +128,27 @@ def exchange_b(a_keys, a_norms, tA, b_keys, b_norms, b_tiles, tB, grid_side, spa
     lo, hi = slab_bounds(grid_side, world, rank)
     rows = hi - lo
     t0 = time.perf_counter()
+    tr = _Trace(timers.setdefault("trace", {}) if timers is not None else None)
     thr = request_thresholds(a_keys, a_norms, tA, grid_side)              # [g] -> slice p goes to rank p
+    tr.mark("request")
     thr_in = torch.empty_like(thr)
     dist.all_to_all_single(thr_in, thr, group=group)                      # equal splits of `rows`
+    tr.mark("a2a_thr")
     thr_in = thr_in.view(world, rows).clone()
     thr_in[rank] = -1.0                                                   # own tiles are already here
     send_idx, counts = select_for_peers(b_keys, b_norms, tB, thr_in, lo, spamm, tau)
+    tr.mark("select")
     cnt_out = torch.tensor(counts, dtype=torch.int64, device=b_keys.device)
     cnt_in = torch.empty_like(cnt_out)
     dist.all_to_all_single(cnt_in, cnt_out, group=group)
     recv_counts = [int(x) for x in cnt_in.tolist()]                       # the one host sync of the plan
     n_in = sum(recv_counts)
+    tr.mark("a2a_counts")
     t1 = time.perf_counter()
     keys_out = b_keys.index_select(0, send_idx)
     norms_out = b_norms.index_select(0, send_idx)
     tiles_out = b_tiles.index_select(0, send_idx)
+    tr.mark("pack")
     if recv_alloc is not None:
         keys_in, norms_in, tiles_in = recv_alloc(n_in)
     else:
@@ -133,6 +158,7 @@ def exchange_b(a_keys, a_norms, tA, b_keys, b_norms, b_tiles, tB, grid_side, spa
     dist.all_to_all_single(keys_in, keys_out, recv_counts, counts, group=group)
     dist.all_to_all_single(norms_in, norms_out, recv_counts, counts, group=group)
     dist.all_to_all_single(tiles_in, tiles_out, recv_counts, counts, group=group)
+    tr.mark("a2a_tiles")
     if timers is not None:
         timers["plan_s"] = t1 - t0
         timers["sent_tiles"] = sum(counts)
@@ -180,6 +206,53 @@ def _tail_views(Mx, cap):
             torch.as_tensor(_DevArray(pt.value, (cap, b * b), ts), device=dev))
 
 
+def _exchange_b_engine(A_loc, tA, B_loc, tB, b_keys, b_norms, b_tiles, grid_side, spamm, tau, group, timers, recv_alloc):
+    """exchange_b with steps 1-2 done by the engine's own kernels (hbsm_halo_request / hbsm_halo_select): two launches
+    instead of ~50 small torch ops.  Must be called with the engine stream current."""
+    from . import _capi
+    L = _capi.lib()
+    world = dist.get_world_size(group); rank = dist.get_rank(group)
+    lo, hi = slab_bounds(grid_side, world, rank)
+    rows = hi - lo
+    t0 = time.perf_counter()
+    tr = _Trace(timers.setdefault("trace", {}) if timers is not None else None)
+    thr = torch.empty((grid_side,), dtype=b_norms.dtype, device=b_norms.device)
+    _capi.check(L.hbsm_halo_request(A_loc._h, int(bool(tA)), C.c_void_p(thr.data_ptr())))
+    tr.mark("request")
+    thr_in = torch.empty_like(thr)
+    dist.all_to_all_single(thr_in, thr, group=group)
+    tr.mark("a2a_thr")
+    nB = b_keys.numel()
+    send_idx = torch.empty((max(1, world * nB),), dtype=torch.int64, device=b_keys.device)
+    cnt = (C.c_size_t * world)()
+    _capi.check(L.hbsm_halo_select(B_loc._h, int(bool(tB)), C.c_void_p(thr_in.data_ptr()), world, rank, lo, rows,
+                                   int(bool(spamm)), float(tau), C.c_void_p(send_idx.data_ptr()), cnt))
+    counts = [int(c) for c in cnt]
+    send_idx = send_idx[:sum(counts)]
+    tr.mark("select")
+    cnt_out = torch.tensor(counts, dtype=torch.int64, device=b_keys.device)
+    cnt_in = torch.empty_like(cnt_out)
+    dist.all_to_all_single(cnt_in, cnt_out, group=group)
+    recv_counts = [int(x) for x in cnt_in.tolist()]
+    n_in = sum(recv_counts)
+    tr.mark("a2a_counts")
+    t1 = time.perf_counter()
+    keys_out = b_keys.index_select(0, send_idx)
+    norms_out = b_norms.index_select(0, send_idx)
+    tiles_out = b_tiles.index_select(0, send_idx)
+    tr.mark("pack")
+    keys_in, norms_in, tiles_in = recv_alloc(n_in)
+    dist.all_to_all_single(keys_in, keys_out, recv_counts, counts, group=group)
+    dist.all_to_all_single(norms_in, norms_out, recv_counts, counts, group=group)
+    dist.all_to_all_single(tiles_in, tiles_out, recv_counts, counts, group=group)
+    tr.mark("a2a_tiles")
+    if timers is not None:
+        timers["plan_s"] = t1 - t0
+        timers["sent_tiles"] = sum(counts)
+        timers["recv_tiles"] = n_in
+    return keys_in, norms_in, tiles_in
+
+
 def sharded_product(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, group=None, timers=None):
     """C_r = op(A)_r * op(B): A_loc / B_loc are this rank's engine matrices (full logical dims, only the slab's tiles;
     norms refreshed).  Remote op(B) tiles are received straight into B_loc's halo tail (hbsm_halo_reserve/commit), the
@@ -202,8 +275,13 @@ def sharded_product(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, group=None, time
             k, nr, t = _tail_views(B_loc, cap)            # (re)reads the pointers: a growth moves the arrays
             return k[:n], nr[:n], t[:n]
 
-        keys, norms, tiles = exchange_b(ak, an, tA, bk, bn, bt, tB, grid_side, spamm, tau, group, timers, recv_alloc)
+        if os.environ.get("HBSM_SHARD_TORCH_PLAN", "0") == "1":     # same plan with torch ops (what the gloo tests run)
+            keys, norms, tiles = exchange_b(ak, an, tA, bk, bn, bt, tB, grid_side, spamm, tau, group, timers, recv_alloc)
+        else:
+            keys, norms, tiles = _exchange_b_engine(A_loc, tA, B_loc, tB, bk, bn, bt, grid_side, spamm, tau, group, timers,
+                                                    recv_alloc)
         ext.synchronize()
+    tr = _Trace(timers.setdefault("trace", {}) if timers is not None else None)
     _capi.check(_capi.lib().hbsm_halo_commit(B_loc._h, keys.numel()))
     Cm = H(A_loc.dtype)
     try:
@@ -213,6 +291,7 @@ def sharded_product(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, group=None, time
             nm, nb = H.multiply(A_loc, tA, B_loc, tB, Cm)
     finally:
         _capi.check(_capi.lib().hbsm_halo_commit(B_loc._h, 0))
+    tr.mark("engine_product")
     return Cm, nm, nb
 
 
@@ -252,6 +331,7 @@ def bench_main(args, w, workload_config, fp64_peak, ClockSampler):
     l0 = hb.kernel_launch_count()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     gemm_ms, task_ms, plan_ms = [], [], []
+    timers["trace"] = {}
     ev0.record(ext)
     for _ in range(args.steps):
         Cm, nm, nb, st = step()
@@ -260,6 +340,7 @@ def bench_main(args, w, workload_config, fp64_peak, ClockSampler):
     ev1.record(ext)
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     launches = hb.kernel_launch_count() - l0
+    trace = {k: round(1e3 * v / args.steps, 4) for k, v in timers.get("trace", {}).items()} or None   # ms per step
     clocks = sampler.stop() if rank == 0 else None
     ms_local = ev0.elapsed_time(ev1) / args.steps
     stats = torch.tensor([ms_local, float(np.mean(gemm_ms))], dtype=torch.float64, device="cuda")
@@ -283,7 +364,7 @@ def bench_main(args, w, workload_config, fp64_peak, ClockSampler):
                 "products_per_multiply": P, "c_tiles": int(sums[1]), "candidates": int(sums[2]),
                 "stage_ms": {"exchange_plan_rank0": float(np.mean(plan_ms)), "tasklist_rank0": float(np.mean(task_ms)),
                              "gemm_rank0": g_ms, "gemm_max_over_ranks": g_ms_max},
-                "halo_tiles_received_total": int(sums[4]),
+                "halo_tiles_received_total": int(sums[4]), "trace_rank0_ms": trace,
                 "roofline": {"bound": "tensor", "kernel": "k_gemm_f64_tma<64,64> (FP64 DMMA leaf GEMM), rank 0's launch",
                              "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peak_src,
                              "algorithmic": "2*b^3 flops per leaf product x %d products in rank 0's launch" % nm,
@@ -317,7 +398,9 @@ def _e2e_sharded(hb, H, A, B, w, steps, lo, hi):
         t0 = time.perf_counter()
         A2 = H(np.float64, b); A2.resize(n, n); A2.assign_tiles(abi, abj, at.numpy()); A2.update_internal_info()
         B2 = H(np.float64, b); B2.resize(n, n); B2.assign_tiles(bbi, bbj, bt.numpy()); B2.update_internal_info()
+        t_up = time.perf_counter() - t0
         Cm, nm, nr = sharded_product(A2, False, B2, False, True, tau)
+        t_prod = time.perf_counter() - t0 - t_up
         if out is None or out.shape[0] < nr:
             out = torch.empty((nr, b * b), dtype=torch.float64, pin_memory=True)
         cbi = np.zeros(nr, np.int64); cbj = np.zeros(nr, np.int64)
@@ -332,9 +415,10 @@ def _e2e_sharded(hb, H, A, B, w, steps, lo, hi):
         sm = v.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         if i > 0:
             times.append(float(mx[0]))
+            phases = {"upload_assign_norms_ms": 1e3 * t_up, "product_ms": 1e3 * t_prod, "download_ms": 1e3 * (dt - t_up - t_prod)}
         nm_tot = int(sm[1]); h2d_tot = int(sm[2]); d2h = int(sm[3])
     ms = 1e3 * float(np.mean(times))
     return {"value": 2.0 * b ** 3 * nm_tot / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ms,
-            "h2d_bytes_per_step": h2d_tot, "d2h_bytes_per_step": d2h,
+            "h2d_bytes_per_step": h2d_tot, "d2h_bytes_per_step": d2h, "rank0_phases": phases,
             "path": "per rank: hbsm_assign_tiles(A_r,B_r from pinned host) + hbsm_update_norms + halo exchange (NCCL) + "
                     "hbsm_spamm + hbsm_export_leaves(C_r to pinned host); max over ranks"}

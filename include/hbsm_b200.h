@@ -131,6 +131,16 @@ int hbsm_assign_device_tiles(hbsm_handle h, size_t n_tiles, const uint64_t* d_mo
  * can be received in place (NCCL writes straight into the tail).  hbsm_halo_commit(h, n) makes the first n tail tiles
  * part of the NEXT products in which h is the right operand (they never enter h's own block table: readback, add,
  * norms of h are unaffected); n = 0 drops them.  Any modification of h drops the halo. */
+/* Halo planning kernels (run on the engine stream; device pointers belong to the caller):
+ *  request: d_thr[k] (Treal, grid_side entries) = max cached leaf norm^2 over A's tiles with contraction index k
+ *           (k = column of A, or row if tA), -1 where A has no such tile;
+ *  select : d_thr_in[q*rows + (k-lo)] is peer q's request for my k in [lo, lo+rows).  Writes to d_send_idx (room for
+ *           world * n_blocks(B) entries) the indices of B's tiles to ship, grouped by peer q != rank, ascending inside a
+ *           group, keeping tile i for q iff request >= 0 and (exact multiply or fl(request * nsq(B_i)) > fl(tau*tau));
+ *           counts[q] (host, `world` entries) = group sizes. */
+int hbsm_halo_request(hbsm_handle A, int tA, void* d_thr);
+int hbsm_halo_select(hbsm_handle B, int tB, const void* d_thr_in, int world, int rank, int lo, int rows, int spamm, double tau,
+                     int64_t* d_send_idx, size_t* counts);
 int hbsm_halo_reserve(hbsm_handle h, size_t capacity, uint64_t** d_keys, void** d_norms, void** d_tiles);
 int hbsm_halo_commit(hbsm_handle h, size_t n_halo);
 /* banded decay generator a_ij = (0.5+0.5u(seed,i,j)) * table[|i-j|], |i-j| <= W (table has W+1 entries, e.g.

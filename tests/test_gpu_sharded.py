@@ -48,7 +48,8 @@ dist.destroy_process_group()
 '''
 
 
-def test_sharded_matches_single_gpu(tmp_path):
+@pytest.mark.parametrize("torch_plan", ["0", "1"])
+def test_sharded_matches_single_gpu(tmp_path, torch_plan):
     import torch
     ngpu = torch.cuda.device_count()
     world = 1
@@ -60,6 +61,7 @@ def test_sharded_matches_single_gpu(tmp_path):
     script.write_text(SCRIPT % {"root": ROOT})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, HBSM_SHARD_TORCH_PLAN=torch_plan)   # engine kernels (default) or the torch-op plan of the gloo tests
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "sharded ok" in r.stdout
