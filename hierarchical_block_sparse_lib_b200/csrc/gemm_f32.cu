@@ -1,0 +1,382 @@
+// gemm_f32.cu -- fp32 leaf GEMM on the 5th-generation tensor cores: C_tile = sum_k op(A_ik) * op(B_kj)  (H:7273 for
+// Treal = float, G:92-98 sgemm), persistent and C-stationary like the FP64 kernel, accumulators in TMEM.
+//
+// tcgen05 has no fp32 kind and single-pass TF32 (10-bit mantissa) misses the 1e-5 parity bar, so every operand x is
+// split in shared memory into  hi = x with the 13 low mantissa bits cleared  (exactly a TF32 number) and
+// lo = x - hi  (exact in fp32), and each K-step issues three  tcgen05.mma.kind::tf32  with fp32 accumulation:
+//   D += A_lo*B_hi ; D += A_hi*B_lo ; D += A_hi*B_hi         (the dropped lo*lo term is ~2^-22 relative)
+// The tensor core truncates when it adds into its fp32 accumulator, which biases long chains (measured 1e-5 after 384
+// chained MMAs), so the TMEM accumulator only ever holds ONE leaf product (small terms issued first, then the hi*hi
+// terms); the epilogue warps add each finished product into the C tile held in registers with ordinary round-to-nearest
+// fp32 adds, in k order -- the summation order of the reference's sgemm calls (H:7273, beta = 1).
+//
+// Warp roles (one CTA per SM, 16 warps):
+//   warp 0      TMA producer + dynamic C-tile scheduler: per K-chunk one 128B-swizzled box set for op(A) and op(B)
+//   warp 1      TMEM allocator; one elected lane issues the MMAs and tcgen05.commit's
+//   warps 4-7   hi/lo split of each landed stage, in place (elementwise, so the swizzled layout is untouched)
+//   warps 8-15  epilogue: tcgen05.ld of each finished product, C tile accumulated in registers, coalesced column-major
+//               stores when the k-list of the C tile ends
+// Pipelines: smem ring  raw(TMA) -> split(converters) -> consumed(tcgen05.commit), and a 2-deep TMEM accumulator ring
+// (MMAs of product p+1 overlap the drain of product p).
+//
+// Operand layouts.  Leaves are column-major (H:715).  An operand whose MN index runs along leaf rows (A as is, B
+// transposed) is "MN-major": the K-chunk is a set of leaf columns, staged as slabs [k][32 mn] (128 B per k row).
+// An operand whose K index runs along leaf rows (A transposed, B as is) is "K-major": staged as slabs [mn][32 k].
+// K-major uses the canonical SWIZZLE_128B layout; MN-major 32-bit operands must use the 128B-swizzle-with-32B-atom
+// layout (4 k rows per atom; TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, descriptor layout type 1).  All four (tA,tB)
+// combinations therefore only differ in the tensor map and a few descriptor fields -- no transposition pass.
+// The MMA is always issued with M = 128 (for 32- and 64-row tiles the upper accumulator rows are never read; the
+// instruction costs the same as M = 64), which keeps the simple TMEM layout "row i = lane i".
+#include "gemm_common.cuh"
+
+namespace hbsm_b200 {
+
+namespace {
+
+// ---- tcgen05 / TMEM PTX wrappers ----
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_box_g2s(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+
+// UMMA shared-memory descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) |
+// layout type [61,64) (2 = SWIZZLE_128B, 1 = SWIZZLE_128B with 32-byte atoms)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+
+template <int BS>
+struct F32Cfg {
+    static constexpr int KC = BS == 128 ? 32 : BS;          // K-chunk per pipeline stage
+    static constexpr int NCHUNK = BS / KC;
+    static constexpr int OPER_BYTES = BS * KC * 4;          // one operand chunk (raw == hi), same again for lo
+    static constexpr int STAGE_BYTES = 4 * OPER_BYTES;      // A_hi | A_lo | B_hi | B_lo
+    static constexpr int NST = (196 * 1024 / STAGE_BYTES) > 8 ? 8 : (196 * 1024 / STAGE_BYTES);
+    static constexpr int TAIL_PAD = 16 * 1024;              // M=128 descriptors of a 32/64-row A may read past the last stage
+    static constexpr int HEADER_BYTES = 1024;
+    static constexpr int SMEM_BYTES = 1024 + HEADER_BYTES + NST * STAGE_BYTES + TAIL_PAD;
+    static constexpr int TMEM_COLS = BS == 128 ? 256 : (2 * BS < 32 ? 32 : 2 * BS);   // two accumulators of BS columns
+    static constexpr int THREADS = 512;
+    static constexpr int CVT_WARPS = 4;
+    static constexpr int EPI_Q = BS >= 128 ? 4 : (BS + 31) / 32;    // TMEM lane quadrants holding live C rows
+    static constexpr int EPI_H = BS >= 64 ? 2 : 1;                  // column halves: two warps share a quadrant
+    static constexpr int EPI_CW = BS / EPI_H;                       // columns per epilogue warp
+    static constexpr int EPI_WARPS = EPI_Q * EPI_H;
+    static constexpr int KSTEPS = KC / 8;
+    static_assert(NST >= 2, "pipeline needs two stages");
+};
+
+struct F32Header {
+    uint64_t full_raw[8], full_cvt[8], empty[8], tmem_full[2], tmem_empty[2];
+    GemmMeta meta[8];
+    int acc_tile[2];
+    int acc_flags[2];     // 1 = first product of its C tile, 2 = last product, 4 = no more work
+    uint32_t tmem_base;
+};
+
+template <int BS, bool TA, bool TB>
+__global__ void __launch_bounds__(F32Cfg<BS>::THREADS, 1)
+k_gemm_f32_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+              const uint2* __restrict__ ab, const uint64_t* __restrict__ begin, uint32_t n_ctiles,
+              unsigned* __restrict__ next_tile, float* __restrict__ Ct) {
+    using Cfg = F32Cfg<BS>;
+    constexpr int NST = Cfg::NST, KC = Cfg::KC;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    F32Header* hd = reinterpret_cast<F32Header*>(smem);
+    unsigned char* stages = smem + Cfg::HEADER_BYTES;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(smem_u32(&hd->full_raw[s]), 1);
+            mbar_init(smem_u32(&hd->full_cvt[s]), Cfg::CVT_WARPS);
+            mbar_init(smem_u32(&hd->empty[s]), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&hd->tmem_full[a]), 1);
+            mbar_init(smem_u32(&hd->tmem_empty[a]), Cfg::EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&hd->tmem_base), Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = hd->tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+            uint32_t it = 0;
+            for (;;) {
+                const unsigned tile = atomicAdd(next_tile, 1u);
+                if (tile >= n_ctiles) break;
+                const uint64_t p0 = begin[tile], p1 = begin[tile + 1];
+                uint2 t = ab[p0];
+                for (uint64_t p = p0; p < p1; ++p) {
+                    const uint2 tn = (p + 1 < p1) ? ab[p + 1] : t;
+#pragma unroll 1
+                    for (int ch = 0; ch < Cfg::NCHUNK; ++ch, ++it) {
+                        const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                        mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
+                        const uint32_t fb = smem_u32(&hd->full_raw[s]);
+                        int fl = 0;
+                        if (p == p0) fl |= 1;                   // product is the first of its C tile
+                        if (p + 1 == p1) fl |= 2;               // ... the last
+                        if (ch == 0) fl |= 8;                   // first K-chunk of the product
+                        if (ch == Cfg::NCHUNK - 1) fl |= 16;    // last K-chunk
+                        hd->meta[s].ctile = (int)tile;
+                        hd->meta[s].flags = fl;
+                        mbar_arrive_expect_tx(fb, 2 * Cfg::OPER_BYTES);
+                        const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
+                        const uint32_t sb = sa + 2 * Cfg::OPER_BYTES;
+                        const int k0 = ch * KC;
+                        // tensor map: dim0 = leaf row (contiguous), dim1 = leaf column + BS * tile
+                        if (TA) {   // K-major: slabs [BS mn][32 k], box {32 rows (k), BS columns (mn)}
+#pragma unroll
+                            for (int j = 0; j < KC / 32; ++j) tma_box_g2s(sa + j * (BS * 128), &mapA, k0 + 32 * j, (int)t.x * BS, fb);
+                        } else {    // MN-major: slabs [KC k][32 mn], box {32 rows (mn), KC columns (k)}
+#pragma unroll
+                            for (int j = 0; j < BS / 32; ++j) tma_box_g2s(sa + j * (KC * 128), &mapA, 32 * j, (int)t.x * BS + k0, fb);
+                        }
+                        if (TB) {   // op(B) = B^T: n runs along leaf rows -> MN-major
+#pragma unroll
+                            for (int j = 0; j < BS / 32; ++j) tma_box_g2s(sb + j * (KC * 128), &mapB, 32 * j, (int)t.y * BS + k0, fb);
+                        } else {    // op(B) = B: k runs along leaf rows -> K-major
+#pragma unroll
+                            for (int j = 0; j < KC / 32; ++j) tma_box_g2s(sb + j * (BS * 128), &mapB, k0 + 32 * j, (int)t.y * BS, fb);
+                        }
+                    }
+                    t = tn;
+                }
+            }
+            const uint32_t s = it % NST, ph = (it / NST) & 1u;
+            mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
+            hd->meta[s].ctile = -1;
+            hd->meta[s].flags = 4;
+            mbar_arrive(smem_u32(&hd->full_raw[s]));
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // instruction descriptor: D fp32 [4,6)=1, A/B tf32 [7,10)=[10,13)=2, a_major bit 15, b_major bit 16 (1 = MN-major),
+            // N>>3 at [17,23), M>>4 at [24,29)
+            constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TA ? 0u : 1u) << 15) | ((TB ? 1u : 0u) << 16) |
+                                       ((uint32_t)(BS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // K-major: SWIZZLE_128B (type 2), 8-row groups 1024 B apart.  MN-major fp32: 32-byte-atom swizzle (type 1), 4 k rows
+            // per atom (SBO = 512 B), 32-element MN chunks one slab (LBO) apart.
+            constexpr uint32_t A_LBO = TA ? 16 : KC * 128, B_LBO = TB ? KC * 128 : 16;
+            constexpr uint32_t A_SBO = TA ? 1024 : 512, B_SBO = TB ? 512 : 1024;
+            constexpr uint32_t A_LT = TA ? 2 : 1, B_LT = TB ? 1 : 2;
+            uint32_t it = 0, pc = 0;
+            bool open = false;
+            for (;; ++it) {
+                const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                mbar_wait(smem_u32(&hd->full_cvt[s]), ph);
+                const GemmMeta m = hd->meta[s];
+                const uint32_t as = pc & 1u;
+                if (m.flags & 4) {
+                    mbar_wait(smem_u32(&hd->tmem_empty[as]), ((pc >> 1) & 1u) ^ 1u);
+                    hd->acc_flags[as] = 4;
+                    __threadfence_block();
+                    mbar_arrive(smem_u32(&hd->tmem_full[as]));
+                    break;
+                }
+                if (m.flags & 8) {
+                    mbar_wait(smem_u32(&hd->tmem_empty[as]), ((pc >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
+                    open = false;
+                }
+                tc_fence_after();
+                const uint32_t d = tmem_base + as * BS;
+                const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
+                const uint32_t a_hi = sa, a_lo = sa + Cfg::OPER_BYTES, b_hi = sa + 2 * Cfg::OPER_BYTES, b_lo = sa + 3 * Cfg::OPER_BYTES;
+                // MN-major: 8 k rows = 1024 B per step; K-major: 32 B inside the 128-B row, next slab every 4 steps
+#pragma unroll
+                for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {      // small terms first ...
+                    const uint32_t ao = TA ? (uint32_t)((ks >> 2) * (BS * 128) + (ks & 3) * 32) : (uint32_t)(ks * 1024);
+                    const uint32_t bo = TB ? (uint32_t)(ks * 1024) : (uint32_t)((ks >> 2) * (BS * 128) + (ks & 3) * 32);
+                    mma_tf32(d, umma_desc(a_lo + ao, A_LBO, A_SBO, A_LT), umma_desc(b_hi + bo, B_LBO, B_SBO, B_LT), IDESC, open ? 1u : 0u);
+                    mma_tf32(d, umma_desc(a_hi + ao, A_LBO, A_SBO, A_LT), umma_desc(b_lo + bo, B_LBO, B_SBO, B_LT), IDESC, 1u);
+                    open = true;
+                }
+#pragma unroll
+                for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {      // ... then the leading hi*hi terms
+                    const uint32_t ao = TA ? (uint32_t)((ks >> 2) * (BS * 128) + (ks & 3) * 32) : (uint32_t)(ks * 1024);
+                    const uint32_t bo = TB ? (uint32_t)(ks * 1024) : (uint32_t)((ks >> 2) * (BS * 128) + (ks & 3) * 32);
+                    mma_tf32(d, umma_desc(a_hi + ao, A_LBO, A_SBO, A_LT), umma_desc(b_hi + bo, B_LBO, B_SBO, B_LT), IDESC, 1u);
+                }
+                tc_commit(smem_u32(&hd->empty[s]));             // stage free when these MMAs have read it
+                if (m.flags & 16) {                             // product complete: hand the accumulator to the epilogue
+                    hd->acc_tile[as] = m.ctile;
+                    hd->acc_flags[as] = m.flags & 3;
+                    __threadfence_block();
+                    tc_commit(smem_u32(&hd->tmem_full[as]));
+                    ++pc;
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 4 + Cfg::CVT_WARPS) {
+        // ===== hi/lo split: raw fp32 (A at +0, B at +2*OPER) -> hi in place, lo at +OPER =====
+        const unsigned tid = threadIdx.x - 128;
+        for (uint32_t it = 0;; ++it) {
+            const uint32_t s = it % NST, ph = (it / NST) & 1u;
+            mbar_wait(smem_u32(&hd->full_raw[s]), ph);
+            const int flags = hd->meta[s].flags;
+            if (!(flags & 4)) {
+                unsigned char* st = stages + (size_t)s * Cfg::STAGE_BYTES;
+#pragma unroll
+                for (int op = 0; op < 2; ++op) {
+                    float4* hi = reinterpret_cast<float4*>(st + op * 2 * Cfg::OPER_BYTES);
+                    float4* lo = reinterpret_cast<float4*>(st + op * 2 * Cfg::OPER_BYTES + Cfg::OPER_BYTES);
+#pragma unroll 4
+                    for (int i = (int)tid; i < Cfg::OPER_BYTES / 16; i += Cfg::CVT_WARPS * 32) {
+                        float4 x = hi[i], h, l;
+                        h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
+                        h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
+                        h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
+                        h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
+                        hi[i] = h;
+                        lo[i] = l;
+                    }
+                }
+                fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&hd->full_cvt[s]));
+            if (flags & 4) break;
+        }
+    } else if (warp >= 8 && ((warp - 8) & 3) < Cfg::EPI_Q && ((warp - 8) >> 2) < Cfg::EPI_H) {
+        // ===== epilogue: warp (q,h) owns TMEM lanes [32q, 32q+32) = C rows, columns [h*CW, (h+1)*CW) =====
+        const unsigned q = (warp - 8) & 3, h = (warp - 8) >> 2;
+        constexpr int CW = Cfg::EPI_CW;
+        const int row = (int)(q * 32 + lane);
+        float acc[CW];
+        for (uint32_t pc = 0;; ++pc) {
+            const uint32_t as = pc & 1u;
+            mbar_wait(smem_u32(&hd->tmem_full[as]), (pc >> 1) & 1u);
+            const int flags = hd->acc_flags[as];
+            if (flags & 4) break;
+            const int ctile = hd->acc_tile[as];
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < CW; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((q * 32u) << 16) + as * BS + h * CW + c0, r);
+                tmem_ld_wait();
+                if (flags & 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c0 + j] = __uint_as_float(r[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(r[j]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&hd->tmem_empty[as]));
+            if ((flags & 2) && row < BS) {
+                float* C = Ct + (size_t)ctile * BS * BS + (size_t)(h * CW) * BS + row;
+#pragma unroll
+                for (int j = 0; j < CW; ++j) C[(size_t)j * BS] = acc[j];   // 32 lanes = 32 consecutive rows: 128 B per store
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// 2-D fp32 view of a tile pool: dim0 = leaf row (contiguous), dim1 = leaf column + BS * tile; 128-B swizzled boxes
+bool make_f32_map(CUtensorMap* map, const void* tiles, size_t n_tiles, int BS, int box_rows, int box_cols, bool mn_major) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)BS, (cuuint64_t)BS * n_tiles};
+    cuuint64_t gstr[1] = {(cuuint64_t)BS * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(tiles), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BS, bool TA, bool TB>
+bool launch_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n_ctiles, unsigned* counter,
+                 float* Ct) {
+    using Cfg = F32Cfg<BS>;
+    CUtensorMap mapA, mapB;
+    // K-major operand (k along leaf rows): box {32 k, BS mn};  MN-major: box {32 mn, KC k}
+    if (!make_f32_map(&mapA, A.tiles.p, A.L, BS, 32, TA ? BS : Cfg::KC, !TA)) return false;
+    if (!make_f32_map(&mapB, B.tiles.p, B.n_ext(), BS, 32, TB ? Cfg::KC : BS, TB)) return false;
+    auto kfn = k_gemm_f32_tc<BS, TA, TB>;
+    static bool configured = false;
+    if (!configured) {
+        HB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    unsigned grid = std::min<unsigned>(n_ctiles, (unsigned)engine().sm_count);
+    HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, ab, begin, n_ctiles, counter, Ct);
+    return true;
+}
+
+template <int BS>
+bool launch_bs(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n, unsigned* counter,
+               float* Ct) {
+    if (!tA && !tB) return launch_inst<BS, false, false>(A, B, ab, begin, n, counter, Ct);
+    if (!tA && tB) return launch_inst<BS, false, true>(A, B, ab, begin, n, counter, Ct);
+    if (tA && !tB) return launch_inst<BS, true, false>(A, B, ab, begin, n, counter, Ct);
+    return launch_inst<BS, true, true>(A, B, ab, begin, n, counter, Ct);
+}
+
+}  // namespace
+
+bool launch_gemm_f32_tc(const Matrix& A, bool tA, const Matrix& B, bool tB, const uint2* ab, const uint64_t* begin,
+                        uint32_t n_ctiles, unsigned* counter, float* Ct) {
+    switch (A.b) {
+        case 32: return launch_bs<32>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
+        case 64: return launch_bs<64>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
+        case 128: return launch_bs<128>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
+        default: return false;
+    }
+}
+
+}  // namespace hbsm_b200

@@ -11,7 +11,7 @@
 // fl(nsq(A_tile) * nsq(B_tile)) > fl(tau*tau) evaluated in Treal with a strict '>' (H:2008, H:6651).  The hierarchical
 // test of the reference collapses to this flat leaf-pair rule because node norms are sums of non-negative child norms.
 #include "matrix.cuh"
-#include <cuda.h>   // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
+#include "gemm_common.cuh"
 
 namespace hbsm_b200 {
 
@@ -146,34 +146,6 @@ __global__ void __launch_bounds__(256) k_gemm_generic(const T* __restrict__ At, 
 // ---------------------------------------------------------------------------------------------------
 // FP64 leaf GEMM: persistent, warp-specialised, TMA bulk copies + mbarrier ring + DMMA
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
@@ -214,7 +186,6 @@ struct GemmCfg {
     static_assert(BS % KC == 0 && KC % 16 == 0 && BS % 32 == 0, "tile shape");
 };
 
-struct GemmMeta { int ctile; int flags; };   // flags: 1 = first chunk of a C tile, 2 = last chunk, 4 = no more work
 
 template <int BS, int KC, bool TA, bool TB>
 __global__ void __launch_bounds__(GemmCfg<BS, KC, TA, TB>::THREADS, 1)
@@ -530,24 +501,6 @@ k_gemm_f64_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-
 // tensor map of a tile pool in the interleaved-by-4-rows view; k_rows: the K-chunk runs along leaf rows
 bool make_tile_map(CUtensorMap* map, const void* tiles, size_t n_tiles, int BS, int KC, bool k_rows, int esize,
                    CUtensorMapDataType dt) {
@@ -764,17 +717,26 @@ void op_product(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, c
             }
             t_gemm.stop();   // `counter` is released in stream order
         } else {
-            if (A.dtype == HBSM_F64) {
-                auto kfn = k_gemm_generic<double>;
-                HB_LAUNCH(kfn, (unsigned)nct, 256, 0, (const double*)A.tiles.p, (const double*)B.tiles.p, tl.ab.p, tl.begin.p,
-                          A.b, tA ? 1 : 0, tB ? 1 : 0, (double*)ct.p);
-            } else {
-                auto kfn = k_gemm_generic<float>;
-                HB_LAUNCH(kfn, (unsigned)nct, 256, 0, (const float*)A.tiles.p, (const float*)B.tiles.p, tl.ab.p, tl.begin.p,
-                          A.b, tA ? 1 : 0, tB ? 1 : 0, (float*)ct.p);
+            bool done = false;
+            if (A.dtype == HBSM_F32 && e.gemm_variant != 1) {   // fp32: 3xTF32 on tcgen05 (gemm_f32.cu) for b in {32,64,128}
+                DevBuf<unsigned> counter(1);
+                counter.zero();
+                done = launch_gemm_f32_tc(A, tA, B, tB, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (float*)ct.p);
+                if (done) e.last_gemm_kernel = 3;
+            }
+            if (!done) {
+                if (A.dtype == HBSM_F64) {
+                    auto kfn = k_gemm_generic<double>;
+                    HB_LAUNCH(kfn, (unsigned)nct, 256, 0, (const double*)A.tiles.p, (const double*)B.tiles.p, tl.ab.p, tl.begin.p,
+                              A.b, tA ? 1 : 0, tB ? 1 : 0, (double*)ct.p);
+                } else {
+                    auto kfn = k_gemm_generic<float>;
+                    HB_LAUNCH(kfn, (unsigned)nct, 256, 0, (const float*)A.tiles.p, (const float*)B.tiles.p, tl.ab.p, tl.begin.p,
+                              A.b, tA ? 1 : 0, tB ? 1 : 0, (float*)ct.p);
+                }
+                e.last_gemm_kernel = 0;
             }
             t_gemm.stop();
-            e.last_gemm_kernel = 0;
         }
         C.set_table(std::move(tl.ckeys), std::move(ct), nct);
         C.task_begin = std::move(tl.begin);
