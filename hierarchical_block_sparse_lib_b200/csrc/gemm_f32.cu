@@ -110,12 +110,17 @@ struct F32Header {
     uint32_t tmem_base;
 };
 
-template <int BS, bool TA, bool TB>
+// LS = leaf size (H:167 blocksize), BS = the square compute tile one CTA accumulates (BS == LS for leaves up to 128; a
+// 256-leaf is processed as 2 x 2 C sub-tiles whose k-lists are the leaf's k-list with both 128-wide halves of each
+// operand: the tensor-map coordinates address the sub-blocks in place, ld = LS).
+template <int LS, int BS, bool TA, bool TB>
 __global__ void __launch_bounds__(F32Cfg<BS>::THREADS, 1)
 k_gemm_f32_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
               const uint2* __restrict__ ab, const uint64_t* __restrict__ begin, uint32_t n_ctiles,
               unsigned* __restrict__ next_tile, float* __restrict__ Ct) {
     using Cfg = F32Cfg<BS>;
+    constexpr int S = LS / BS;            // sub-tiles per leaf side
+    static_assert(LS % BS == 0 && (S == 1 || S == 2), "leaf / compute-tile shapes");
     constexpr int NST = Cfg::NST, KC = Cfg::KC;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -148,42 +153,47 @@ k_gemm_f32_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
             uint32_t it = 0;
             for (;;) {
-                const unsigned tile = atomicAdd(next_tile, 1u);
-                if (tile >= n_ctiles) break;
+                const unsigned unit = atomicAdd(next_tile, 1u);       // work unit = (C tile, sub-tile)
+                if (unit >= n_ctiles * (unsigned)(S * S)) break;
+                const unsigned tile = unit / (S * S), sub = unit % (S * S);
+                const int si = (int)(sub % S) * BS, sj = (int)(sub / S) * BS;   // row / column offset of the C sub-tile
                 const uint64_t p0 = begin[tile], p1 = begin[tile + 1];
                 uint2 t = ab[p0];
                 for (uint64_t p = p0; p < p1; ++p) {
                     const uint2 tn = (p + 1 < p1) ? ab[p + 1] : t;
 #pragma unroll 1
-                    for (int ch = 0; ch < Cfg::NCHUNK; ++ch, ++it) {
-                        const uint32_t s = it % NST, ph = (it / NST) & 1u;
-                        mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
-                        const uint32_t fb = smem_u32(&hd->full_raw[s]);
-                        int fl = 0;
-                        if (p == p0) fl |= 1;                   // product is the first of its C tile
-                        if (p + 1 == p1) fl |= 2;               // ... the last
-                        if (ch == 0) fl |= 8;                   // first K-chunk of the product
-                        if (ch == Cfg::NCHUNK - 1) fl |= 16;    // last K-chunk
-                        hd->meta[s].ctile = (int)tile;
-                        hd->meta[s].flags = fl;
-                        mbar_arrive_expect_tx(fb, 2 * Cfg::OPER_BYTES);
-                        const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
-                        const uint32_t sb = sa + 2 * Cfg::OPER_BYTES;
-                        const int k0 = ch * KC;
-                        // tensor map: dim0 = leaf row (contiguous), dim1 = leaf column + BS * tile
-                        if (TA) {   // K-major: slabs [BS mn][32 k], box {32 rows (k), BS columns (mn)}
+                    for (int kk = 0; kk < S; ++kk) {
+#pragma unroll 1
+                        for (int ch = 0; ch < Cfg::NCHUNK; ++ch, ++it) {
+                            const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                            mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
+                            const uint32_t fb = smem_u32(&hd->full_raw[s]);
+                            int fl = 0;
+                            if (p == p0 && kk == 0) fl |= 1;                  // first accumulator of its C (sub-)tile
+                            if (p + 1 == p1 && kk == S - 1) fl |= 2;          // ... the last
+                            if (ch == 0) fl |= 8;                             // first K-chunk of this accumulator
+                            if (ch == Cfg::NCHUNK - 1) fl |= 16;              // last K-chunk
+                            hd->meta[s].ctile = (int)unit;
+                            hd->meta[s].flags = fl;
+                            mbar_arrive_expect_tx(fb, 2 * Cfg::OPER_BYTES);
+                            const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
+                            const uint32_t sb = sa + 2 * Cfg::OPER_BYTES;
+                            const int k0 = kk * BS + ch * KC;
+                            // tensor map: dim0 = leaf row (contiguous), dim1 = leaf column + LS * tile
+                            if (TA) {   // K-major: slabs [BS mn][32 k], box {32 rows (k), BS columns (mn)}
 #pragma unroll
-                            for (int j = 0; j < KC / 32; ++j) tma_box_g2s(sa + j * (BS * 128), &mapA, k0 + 32 * j, (int)t.x * BS, fb);
-                        } else {    // MN-major: slabs [KC k][32 mn], box {32 rows (mn), KC columns (k)}
+                                for (int j = 0; j < KC / 32; ++j) tma_box_g2s(sa + j * (BS * 128), &mapA, k0 + 32 * j, (int)t.x * LS + si, fb);
+                            } else {    // MN-major: slabs [KC k][32 mn], box {32 rows (mn), KC columns (k)}
 #pragma unroll
-                            for (int j = 0; j < BS / 32; ++j) tma_box_g2s(sa + j * (KC * 128), &mapA, 32 * j, (int)t.x * BS + k0, fb);
-                        }
-                        if (TB) {   // op(B) = B^T: n runs along leaf rows -> MN-major
+                                for (int j = 0; j < BS / 32; ++j) tma_box_g2s(sa + j * (KC * 128), &mapA, si + 32 * j, (int)t.x * LS + k0, fb);
+                            }
+                            if (TB) {   // op(B) = B^T: n runs along leaf rows -> MN-major
 #pragma unroll
-                            for (int j = 0; j < BS / 32; ++j) tma_box_g2s(sb + j * (KC * 128), &mapB, 32 * j, (int)t.y * BS + k0, fb);
-                        } else {    // op(B) = B: k runs along leaf rows -> K-major
+                                for (int j = 0; j < BS / 32; ++j) tma_box_g2s(sb + j * (KC * 128), &mapB, sj + 32 * j, (int)t.y * LS + k0, fb);
+                            } else {    // op(B) = B: k runs along leaf rows -> K-major
 #pragma unroll
-                            for (int j = 0; j < KC / 32; ++j) tma_box_g2s(sb + j * (BS * 128), &mapB, k0 + 32 * j, (int)t.y * BS, fb);
+                                for (int j = 0; j < KC / 32; ++j) tma_box_g2s(sb + j * (BS * 128), &mapB, k0 + 32 * j, (int)t.y * LS + sj, fb);
+                            }
                         }
                     }
                     t = tn;
@@ -314,9 +324,10 @@ k_gemm_f32_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&hd->tmem_empty[as]));
             if ((flags & 2) && row < BS) {
-                float* C = Ct + (size_t)ctile * BS * BS + (size_t)(h * CW) * BS + row;
+                const unsigned tile = (unsigned)ctile / (S * S), sub = (unsigned)ctile % (S * S);
+                float* C = Ct + (size_t)tile * LS * LS + (size_t)((sub / S) * BS + h * CW) * LS + (sub % S) * BS + row;
 #pragma unroll
-                for (int j = 0; j < CW; ++j) C[(size_t)j * BS] = acc[j];   // 32 lanes = 32 consecutive rows: 128 B per store
+                for (int j = 0; j < CW; ++j) C[(size_t)j * LS] = acc[j];   // 32 lanes = 32 consecutive rows: 128 B per store
             }
         }
     }
@@ -327,11 +338,11 @@ k_gemm_f32_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 }
 
 // 2-D fp32 view of a tile pool: dim0 = leaf row (contiguous), dim1 = leaf column + BS * tile; 128-B swizzled boxes
-bool make_f32_map(CUtensorMap* map, const void* tiles, size_t n_tiles, int BS, int box_rows, int box_cols, bool mn_major) {
+bool make_f32_map(CUtensorMap* map, const void* tiles, size_t n_tiles, int LS, int box_rows, int box_cols, bool mn_major) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return false;
-    cuuint64_t gdim[2] = {(cuuint64_t)BS, (cuuint64_t)BS * n_tiles};
-    cuuint64_t gstr[1] = {(cuuint64_t)BS * 4};
+    cuuint64_t gdim[2] = {(cuuint64_t)LS, (cuuint64_t)LS * n_tiles};
+    cuuint64_t gstr[1] = {(cuuint64_t)LS * 4};
     cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols};
     cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(tiles), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -339,32 +350,34 @@ bool make_f32_map(CUtensorMap* map, const void* tiles, size_t n_tiles, int BS, i
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BS, bool TA, bool TB>
+template <int LS, int BS, bool TA, bool TB>
 bool launch_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n_ctiles, unsigned* counter,
                  float* Ct) {
     using Cfg = F32Cfg<BS>;
     CUtensorMap mapA, mapB;
     // K-major operand (k along leaf rows): box {32 k, BS mn};  MN-major: box {32 mn, KC k}
-    if (!make_f32_map(&mapA, A.tiles.p, A.L, BS, 32, TA ? BS : Cfg::KC, !TA)) return false;
-    if (!make_f32_map(&mapB, B.tiles.p, B.n_ext(), BS, 32, TB ? Cfg::KC : BS, TB)) return false;
-    auto kfn = k_gemm_f32_tc<BS, TA, TB>;
+    if (!make_f32_map(&mapA, A.tiles.p, A.L, LS, 32, TA ? BS : Cfg::KC, !TA)) return false;
+    if (!make_f32_map(&mapB, B.tiles.p, B.n_ext(), LS, 32, TB ? Cfg::KC : BS, TB)) return false;
+    auto kfn = k_gemm_f32_tc<LS, BS, TA, TB>;
     static bool configured = false;
     if (!configured) {
         HB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
-    unsigned grid = std::min<unsigned>(n_ctiles, (unsigned)engine().sm_count);
+    const uint64_t units = (uint64_t)n_ctiles * (LS / BS) * (LS / BS);
+    if (units >= 0x7fffffffull) return false;
+    unsigned grid = (unsigned)std::min<uint64_t>(units, (uint64_t)engine().sm_count);
     HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, ab, begin, n_ctiles, counter, Ct);
     return true;
 }
 
-template <int BS>
+template <int LS, int BS>
 bool launch_bs(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n, unsigned* counter,
                float* Ct) {
-    if (!tA && !tB) return launch_inst<BS, false, false>(A, B, ab, begin, n, counter, Ct);
-    if (!tA && tB) return launch_inst<BS, false, true>(A, B, ab, begin, n, counter, Ct);
-    if (tA && !tB) return launch_inst<BS, true, false>(A, B, ab, begin, n, counter, Ct);
-    return launch_inst<BS, true, true>(A, B, ab, begin, n, counter, Ct);
+    if (!tA && !tB) return launch_inst<LS, BS, false, false>(A, B, ab, begin, n, counter, Ct);
+    if (!tA && tB) return launch_inst<LS, BS, false, true>(A, B, ab, begin, n, counter, Ct);
+    if (tA && !tB) return launch_inst<LS, BS, true, false>(A, B, ab, begin, n, counter, Ct);
+    return launch_inst<LS, BS, true, true>(A, B, ab, begin, n, counter, Ct);
 }
 
 }  // namespace
@@ -372,9 +385,10 @@ bool launch_bs(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* 
 bool launch_gemm_f32_tc(const Matrix& A, bool tA, const Matrix& B, bool tB, const uint2* ab, const uint64_t* begin,
                         uint32_t n_ctiles, unsigned* counter, float* Ct) {
     switch (A.b) {
-        case 32: return launch_bs<32>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
-        case 64: return launch_bs<64>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
-        case 128: return launch_bs<128>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
+        case 32: return launch_bs<32, 32>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
+        case 64: return launch_bs<64, 64>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
+        case 128: return launch_bs<128, 128>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
+        case 256: return launch_bs<256, 128>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
         default: return false;
     }
 }

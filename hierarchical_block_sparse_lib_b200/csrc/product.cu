@@ -379,13 +379,16 @@ struct TmaCfg {
     static_assert(NST >= 2, "pipeline needs two stages");
 };
 
-template <int BS, int KC, bool TA, bool TB>
+// LS = leaf size, BS = compute tile of one CTA (BS == LS up to 128; a 256-leaf is 2 x 2 sub-tiles addressed in place)
+template <int LS, int BS, int KC, bool TA, bool TB>
 __global__ void __launch_bounds__(TmaCfg<BS, KC>::THREADS, 1)
 k_gemm_f64_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const uint2* __restrict__ ab, const uint64_t* __restrict__ begin, uint32_t n_ctiles,
                unsigned* __restrict__ next_tile, double* __restrict__ Ct) {
     using Cfg = TmaCfg<BS, KC>;
     constexpr int NST = Cfg::NST;
+    constexpr int S = LS / BS;
+    static_assert(LS % BS == 0 && (S == 1 || S == 2), "leaf / compute-tile shapes");
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
@@ -403,7 +406,6 @@ k_gemm_f64_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     __syncthreads();
 
-    constexpr size_t BB = (size_t)BS * BS;
     if (warp == Cfg::CONSUMER_WARPS) {
         // ===== producer: one elected lane walks the task list and issues two TMA tile copies per chunk =====
         if (lane == 0) {
@@ -411,30 +413,32 @@ k_gemm_f64_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
             uint32_t it = 0;
             for (;;) {
-                const unsigned tile = atomicAdd(next_tile, 1u);
-                if (tile >= n_ctiles) break;
+                const unsigned unit = atomicAdd(next_tile, 1u);       // work unit = (C tile, sub-tile)
+                if (unit >= n_ctiles * (unsigned)(S * S)) break;
+                const unsigned tile = unit / (S * S), sub = unit % (S * S);
+                const int si = (int)(sub % S) * BS, sj = (int)(sub / S) * BS;
                 const uint64_t p0 = begin[tile], p1 = begin[tile + 1];
                 uint2 t = ab[p0];
                 for (uint64_t p = p0; p < p1; ++p) {
                     const uint2 tn = (p + 1 < p1) ? ab[p + 1] : t;   // prefetch the next pair
 #pragma unroll 1
-                    for (int ch = 0; ch < Cfg::NCHUNK; ++ch, ++it) {
+                    for (int kc = 0; kc < S * Cfg::NCHUNK; ++kc, ++it) {
                         const uint32_t s = it % NST, ph = (it / NST) & 1u;
                         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
                         const uint32_t fb = smem_u32(&full_bar[s]);
                         int fl = 0;
-                        if (p == p0 && ch == 0) fl |= 1;
-                        if (p + 1 == p1 && ch == Cfg::NCHUNK - 1) fl |= 2;
-                        meta[s].ctile = (int)tile;
+                        if (p == p0 && kc == 0) fl |= 1;
+                        if (p + 1 == p1 && kc == S * Cfg::NCHUNK - 1) fl |= 2;
+                        meta[s].ctile = (int)unit;
                         meta[s].flags = fl;
                         mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
                         const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
                         const uint32_t sb = sa + Cfg::CHUNK_ELEMS * 8;
-                        const int k0 = ch * KC;
-                        if (TA) tma_tile_g2s(sa, &mapA, 0, 0, k0 / 4, (int)t.x, fb);   // k along leaf rows
-                        else    tma_tile_g2s(sa, &mapA, 0, k0, 0, (int)t.x, fb);       // k along leaf columns
-                        if (TB) tma_tile_g2s(sb, &mapB, 0, k0, 0, (int)t.y, fb);
-                        else    tma_tile_g2s(sb, &mapB, 0, 0, k0 / 4, (int)t.y, fb);
+                        const int k0 = kc * KC;   // position along the leaf's full contraction dimension
+                        if (TA) tma_tile_g2s(sa, &mapA, 0, si, k0 / 4, (int)t.x, fb);   // k along leaf rows
+                        else    tma_tile_g2s(sa, &mapA, 0, k0, si / 4, (int)t.x, fb);   // k along leaf columns
+                        if (TB) tma_tile_g2s(sb, &mapB, 0, k0, sj / 4, (int)t.y, fb);
+                        else    tma_tile_g2s(sb, &mapB, 0, sj, k0 / 4, (int)t.y, fb);
                     }
                     t = tn;
                 }
@@ -488,27 +492,28 @@ k_gemm_f64_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&empty_bar[s]));
         if (m.flags & 2) {
-            double* C = Ct + (size_t)m.ctile * BB;
+            const unsigned tile = (unsigned)m.ctile / (S * S), sub = (unsigned)m.ctile % (S * S);
+            double* C = Ct + (size_t)tile * LS * LS + (size_t)((sub / S) * BS) * LS + (sub % S) * BS;
 #pragma unroll
             for (int i = 0; i < Cfg::MB; ++i)
 #pragma unroll
                 for (int j = 0; j < Cfg::NB; ++j) {
                     const int row = wm0 + i * 8 + g, col = wn0 + j * 8 + 2 * t;
-                    C[(size_t)col * BS + row] = acc[i][j][0];
-                    C[(size_t)(col + 1) * BS + row] = acc[i][j][1];
+                    C[(size_t)col * LS + row] = acc[i][j][0];
+                    C[(size_t)(col + 1) * LS + row] = acc[i][j][1];
                 }
         }
     }
 }
 
 // tensor map of a tile pool in the interleaved-by-4-rows view; k_rows: the K-chunk runs along leaf rows
-bool make_tile_map(CUtensorMap* map, const void* tiles, size_t n_tiles, int BS, int KC, bool k_rows, int esize,
+bool make_tile_map(CUtensorMap* map, const void* tiles, size_t n_tiles, int LS, int BS, int KC, bool k_rows, int esize,
                    CUtensorMapDataType dt) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return false;
     const int grp = 32 / esize;   // rows per 32-byte group (4 doubles / 8 floats)
-    cuuint64_t gdim[4] = {(cuuint64_t)grp, (cuuint64_t)BS, (cuuint64_t)(BS / grp), (cuuint64_t)n_tiles};
-    cuuint64_t gstr[3] = {(cuuint64_t)BS * esize, 32ull, (cuuint64_t)BS * BS * esize};
+    cuuint64_t gdim[4] = {(cuuint64_t)grp, (cuuint64_t)LS, (cuuint64_t)(LS / grp), (cuuint64_t)n_tiles};
+    cuuint64_t gstr[3] = {(cuuint64_t)LS * esize, 32ull, (cuuint64_t)LS * LS * esize};
     cuuint32_t box[4] = {(cuuint32_t)grp, (cuuint32_t)(k_rows ? BS : KC), (cuuint32_t)(k_rows ? KC / grp : BS / grp), 1u};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(map, dt, 4, const_cast<void*>(tiles), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -516,31 +521,33 @@ bool make_tile_map(CUtensorMap* map, const void* tiles, size_t n_tiles, int BS, 
     return r == CUDA_SUCCESS;
 }
 
-template <int BS, int KC, bool TA, bool TB>
+template <int LS, int BS, int KC, bool TA, bool TB>
 bool launch_gemm_f64_tma_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n_ctiles,
                               unsigned* counter, double* Ct) {
     using Cfg = TmaCfg<BS, KC>;
     CUtensorMap mapA, mapB;
-    if (!make_tile_map(&mapA, A.tiles.p, A.L, BS, KC, TA, 8, CU_TENSOR_MAP_DATA_TYPE_FLOAT64)) return false;
-    if (!make_tile_map(&mapB, B.tiles.p, B.n_ext(), BS, KC, !TB, 8, CU_TENSOR_MAP_DATA_TYPE_FLOAT64)) return false;
-    auto kfn = k_gemm_f64_tma<BS, KC, TA, TB>;
+    if (!make_tile_map(&mapA, A.tiles.p, A.L, LS, BS, KC, TA, 8, CU_TENSOR_MAP_DATA_TYPE_FLOAT64)) return false;
+    if (!make_tile_map(&mapB, B.tiles.p, B.n_ext(), LS, BS, KC, !TB, 8, CU_TENSOR_MAP_DATA_TYPE_FLOAT64)) return false;
+    auto kfn = k_gemm_f64_tma<LS, BS, KC, TA, TB>;
     static bool configured = false;
     if (!configured) {
         HB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
-    unsigned grid = std::min<unsigned>(n_ctiles, (unsigned)engine().sm_count);
+    const uint64_t units = (uint64_t)n_ctiles * (LS / BS) * (LS / BS);
+    if (units >= 0x7fffffffull) return false;
+    unsigned grid = (unsigned)std::min<uint64_t>(units, (uint64_t)engine().sm_count);
     HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, ab, begin, n_ctiles, counter, Ct);
     return true;
 }
 
-template <int BS, int KC>
+template <int LS, int BS, int KC>
 bool launch_gemm_f64_tma(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin,
                          uint32_t n_ctiles, unsigned* counter, double* Ct) {
-    if (!tA && !tB) return launch_gemm_f64_tma_inst<BS, KC, false, false>(A, B, ab, begin, n_ctiles, counter, Ct);
-    if (!tA && tB) return launch_gemm_f64_tma_inst<BS, KC, false, true>(A, B, ab, begin, n_ctiles, counter, Ct);
-    if (tA && !tB) return launch_gemm_f64_tma_inst<BS, KC, true, false>(A, B, ab, begin, n_ctiles, counter, Ct);
-    return launch_gemm_f64_tma_inst<BS, KC, true, true>(A, B, ab, begin, n_ctiles, counter, Ct);
+    if (!tA && !tB) return launch_gemm_f64_tma_inst<LS, BS, KC, false, false>(A, B, ab, begin, n_ctiles, counter, Ct);
+    if (!tA && tB) return launch_gemm_f64_tma_inst<LS, BS, KC, false, true>(A, B, ab, begin, n_ctiles, counter, Ct);
+    if (tA && !tB) return launch_gemm_f64_tma_inst<LS, BS, KC, true, false>(A, B, ab, begin, n_ctiles, counter, Ct);
+    return launch_gemm_f64_tma_inst<LS, BS, KC, true, true>(A, B, ab, begin, n_ctiles, counter, Ct);
 }
 
 struct TaskList {
@@ -696,19 +703,21 @@ void op_product(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, c
     if (tl.n_products > 0) {
         const size_t nct = tl.n_ctiles;
         DevBuf<char> ct(nct * C.tile_bytes());
-        const bool fast64 = A.dtype == HBSM_F64 && e.gemm_variant != 1 && (A.b == 32 || A.b == 64 || A.b == 128);
+        const bool fast64 = A.dtype == HBSM_F64 && e.gemm_variant != 1 && (A.b == 32 || A.b == 64 || A.b == 128 || A.b == 256);
         if (fast64) {
             DevBuf<unsigned> counter(1);
             counter.zero();
             const double* At = (const double*)A.tiles.p;
             const double* Bt = (const double*)B.tiles.p;
             bool done = false;
-            if (e.gemm_variant == 0) {   // TMA-tiled kernel; falls back to the bulk-copy kernel if the driver refuses the map
-                if (A.b == 64) done = launch_gemm_f64_tma<64, 64>(tA, tB, A, B, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
-                else if (A.b == 32) done = launch_gemm_f64_tma<32, 32>(tA, tB, A, B, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
-                else done = launch_gemm_f64_tma<128, 32>(tA, tB, A, B, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
+            if (e.gemm_variant == 0 || A.b == 256) {   // TMA-tiled kernel; falls back to the bulk-copy kernel if the driver refuses the map
+                if (A.b == 64) done = launch_gemm_f64_tma<64, 64, 64>(tA, tB, A, B, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
+                else if (A.b == 32) done = launch_gemm_f64_tma<32, 32, 32>(tA, tB, A, B, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
+                else if (A.b == 128) done = launch_gemm_f64_tma<128, 128, 32>(tA, tB, A, B, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
+                else done = launch_gemm_f64_tma<256, 128, 32>(tA, tB, A, B, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
                 e.last_gemm_kernel = done ? 1 : 2;
             }
+            if (!done && A.b == 256) throw Error(HBSM_E_CUDA, "hbsm_b200: the driver refused the tensor map for 256-leaves");
             if (!done) {
                 if (A.b == 64) launch_gemm_f64<64, 64>(tA, tB, At, Bt, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
                 else if (A.b == 32) launch_gemm_f64<32, 32>(tA, tB, At, Bt, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
@@ -718,7 +727,7 @@ void op_product(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, c
             t_gemm.stop();   // `counter` is released in stream order
         } else {
             bool done = false;
-            if (A.dtype == HBSM_F32 && e.gemm_variant != 1) {   // fp32: 3xTF32 on tcgen05 (gemm_f32.cu) for b in {32,64,128}
+            if (A.dtype == HBSM_F32 && e.gemm_variant != 1) {   // fp32: 3xTF32 on tcgen05 (gemm_f32.cu) for b in {32,64,128,256}
                 DevBuf<unsigned> counter(1);
                 counter.zero();
                 done = launch_gemm_f32_tc(A, tA, B, tB, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (float*)ct.p);

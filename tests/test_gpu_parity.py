@@ -130,9 +130,9 @@ def test_product_task_set_and_values(dtype, b, n, lam, tA, tB, tau):
     assert st["n_products"] == onm and st["gpu_launches"] > 0
 
 
-@pytest.mark.parametrize("b", [32, 64, 128])
+@pytest.mark.parametrize("b", [32, 64, 128, 256])
 def test_dmma_kernel_matches_generic_kernel(b):
-    n = b * 16
+    n = b * (16 if b < 256 else 6)
     (ra, ca, va), (rb, cb, vb) = decay_pair(n, 0.02)
     A = gpu_from_coo(b, n, n, ra, ca, va); B = gpu_from_coo(b, n, n, rb, cb, vb)
     res = []
@@ -143,6 +143,32 @@ def test_dmma_kernel_matches_generic_kernel(b):
         res.append(C.to_dense())
     hb.set_gemm_variant(0)
     assert rel_frob(res[0], res[1]) <= 1e-14
+
+
+@pytest.mark.parametrize("b", [32, 64, 128, 256])
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_fp32_tcgen05_kernel(b, tA, tB):
+    """fp32 leaf GEMM on the tensor cores (3xTF32, gemm_kernel == 3) against the plain FMA kernel and fp64 numpy:
+    relative Frobenius error <= 1e-5 (the fp32 parity bar of BASELINE.json), for every operand orientation."""
+    n = b * (8 if b < 256 else 5)
+    lam = 0.02 * 64 / b
+    (ra, ca, va), (rb, cb, vb) = decay_pair(n, lam, np.float32)
+    A = gpu_from_coo(b, n, n, ra, ca, va, np.float32); B = gpu_from_coo(b, n, n, rb, cb, vb, np.float32)
+    res = []
+    for variant in (0, 1):
+        hb.set_gemm_variant(variant)
+        C = HBSM(np.float32)
+        try:
+            HBSM.spamm(A, tA, B, tB, C, 1e-7, True)
+        finally:
+            hb.set_gemm_variant(0)
+        res.append(C.to_dense().astype(np.float64))
+        if variant == 0:
+            assert hb.stage_times()["gemm_kernel"] == 3, "the tcgen05 kernel did not run"
+    Ad = A.to_dense().astype(np.float64); Bd = B.to_dense().astype(np.float64)
+    assert rel_frob(res[0], res[1]) <= 1e-5
+    # tau = 1e-7 prunes nothing visible at this size: compare with the dense fp64 product as well
+    assert rel_frob(res[0], (Ad.T if tA else Ad) @ (Bd.T if tB else Bd)) <= 1e-5
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
