@@ -2,8 +2,9 @@
 // Treal = float, G:92-98 sgemm), persistent and C-stationary like the FP64 kernel, accumulators in TMEM.
 //
 // tcgen05 has no fp32 kind and single-pass TF32 (10-bit mantissa) misses the 1e-5 parity bar, so every operand x is
-// split in shared memory into  hi = x with the 13 low mantissa bits cleared  (exactly a TF32 number) and
-// lo = x - hi  (exact in fp32), and each K-step issues three  tcgen05.mma.kind::tf32  with fp32 accumulation:
+// split in shared memory into  hi = x with the 13 low mantissa bits cleared  (exactly a TF32 number; the tensor core
+// drops those bits itself -- measured: feeding the raw x gives bit-identical results -- so "hi" is the raw operand left
+// in place) and lo = x - hi  (exact in fp32), and each K-step issues three  tcgen05.mma.kind::tf32  with fp32 accumulation:
 //   D += A_lo*B_hi ; D += A_hi*B_lo ; D += A_hi*B_hi         (the dropped lo*lo term is ~2^-22 relative)
 // The tensor core truncates when it adds into its fp32 accumulator, which biases long chains (measured 1e-5 after 384
 // chained MMAs), so the TMEM accumulator only ever holds ONE leaf product (small terms issued first, then the hi*hi
@@ -81,7 +82,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
            (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 
-template <int BS>
+template <int BS, int MM = 128>
 struct F32Cfg {
     static constexpr int KC = BS == 128 ? 32 : BS;          // K-chunk per pipeline stage
     static constexpr int NCHUNK = BS / KC;
@@ -91,10 +92,18 @@ struct F32Cfg {
     static constexpr int TAIL_PAD = 16 * 1024;              // M=128 descriptors of a 32/64-row A may read past the last stage
     static constexpr int HEADER_BYTES = 1024;
     static constexpr int SMEM_BYTES = 1024 + HEADER_BYTES + NST * STAGE_BYTES + TAIL_PAD;
-    static constexpr int TMEM_COLS = BS == 128 ? 256 : (2 * BS < 32 ? 32 : 2 * BS);   // two accumulators of BS columns
+    // Independent TMEM accumulators per leaf product.  Back-to-back MMAs into ONE accumulator serialise on its
+    // read-modify-write latency (measured ~100 clk per N=64 MMA instead of the 32 clk dispatch floor), so the three
+    // terms lo*hi, hi*lo, hi*hi go to separate accumulators (two for 128-tiles: TMEM has 512 columns) and the epilogue
+    // adds them.  x2 for the double-buffered hand-off to the epilogue.
+    static constexpr int NACC = BS == 128 ? 2 : 3;
+    static constexpr int ACC_COLS = NACC * BS;
+    static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : (2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512)));
+    static_assert(2 * ACC_COLS <= 512, "TMEM has 512 columns");
     static constexpr int THREADS = 512;
     static constexpr int CVT_WARPS = 4;
-    static constexpr int EPI_Q = BS >= 128 ? 4 : (BS + 31) / 32;    // TMEM lane quadrants holding live C rows
+    // TMEM lane quadrants holding live C rows: M = 128 puts row i in lane i; M = 64 puts row i in lane 32*(i/16) + i%16
+    static constexpr int EPI_Q = MM == 64 ? BS / 16 : (BS >= 128 ? 4 : (BS + 31) / 32);
     static constexpr int EPI_H = BS >= 64 ? 2 : 1;                  // column halves: two warps share a quadrant
     static constexpr int EPI_CW = BS / EPI_H;                       // columns per epilogue warp
     static constexpr int EPI_WARPS = EPI_Q * EPI_H;
@@ -113,12 +122,13 @@ struct F32Header {
 // LS = leaf size (H:167 blocksize), BS = the square compute tile one CTA accumulates (BS == LS for leaves up to 128; a
 // 256-leaf is processed as 2 x 2 C sub-tiles whose k-lists are the leaf's k-list with both 128-wide halves of each
 // operand: the tensor-map coordinates address the sub-blocks in place, ld = LS).
-template <int LS, int BS, bool TA, bool TB>
-__global__ void __launch_bounds__(F32Cfg<BS>::THREADS, 1)
+template <int LS, int BS, int MM, bool TA, bool TB>
+__global__ void __launch_bounds__(F32Cfg<BS, MM>::THREADS, 1)
 k_gemm_f32_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
               const uint2* __restrict__ ab, const uint64_t* __restrict__ begin, uint32_t n_ctiles,
-              unsigned* __restrict__ next_tile, float* __restrict__ Ct) {
-    using Cfg = F32Cfg<BS>;
+              unsigned* __restrict__ next_tile, float* __restrict__ Ct, int raw_hi /* development switches, see f32_mode() */) {
+    using Cfg = F32Cfg<BS, MM>;
+    static_assert(MM == 128 || (MM == 64 && BS <= 64), "MMA M shape");
     constexpr int S = LS / BS;            // sub-tiles per leaf side
     static_assert(LS % BS == 0 && (S == 1 || S == 2), "leaf / compute-tile shapes");
     constexpr int NST = Cfg::NST, KC = Cfg::KC;
@@ -211,7 +221,7 @@ k_gemm_f32_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             // instruction descriptor: D fp32 [4,6)=1, A/B tf32 [7,10)=[10,13)=2, a_major bit 15, b_major bit 16 (1 = MN-major),
             // N>>3 at [17,23), M>>4 at [24,29)
             constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TA ? 0u : 1u) << 15) | ((TB ? 1u : 0u) << 16) |
-                                       ((uint32_t)(BS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                                       ((uint32_t)(BS >> 3) << 17) | ((uint32_t)(MM >> 4) << 24);
             // K-major: SWIZZLE_128B (type 2), 8-row groups 1024 B apart.  MN-major fp32: 32-byte-atom swizzle (type 1), 4 k rows
             // per atom (SBO = 512 B), 32-element MN chunks one slab (LBO) apart.
             constexpr uint32_t A_LBO = TA ? 16 : KC * 128, B_LBO = TB ? KC * 128 : 16;
@@ -232,27 +242,28 @@ k_gemm_f32_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     break;
                 }
                 if (m.flags & 8) {
-                    mbar_wait(smem_u32(&hd->tmem_empty[as]), ((pc >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
+                    mbar_wait(smem_u32(&hd->tmem_empty[as]), ((pc >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator set
                     open = false;
                 }
                 tc_fence_after();
-                const uint32_t d = tmem_base + as * BS;
+                const uint32_t d_small = tmem_base + as * Cfg::ACC_COLS;                    // lo*hi (and hi*lo when NACC == 2)
+                const uint32_t d_small2 = d_small + (Cfg::NACC == 3 ? BS : 0);              // hi*lo
+                const uint32_t d_big = d_small + (Cfg::NACC - 1) * BS;                      // hi*hi
                 const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
                 const uint32_t a_hi = sa, a_lo = sa + Cfg::OPER_BYTES, b_hi = sa + 2 * Cfg::OPER_BYTES, b_lo = sa + 3 * Cfg::OPER_BYTES;
                 // MN-major: 8 k rows = 1024 B per step; K-major: 32 B inside the 128-B row, next slab every 4 steps
+                if (!(raw_hi & 16)) {
 #pragma unroll
-                for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {      // small terms first ...
+                for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
                     const uint32_t ao = TA ? (uint32_t)((ks >> 2) * (BS * 128) + (ks & 3) * 32) : (uint32_t)(ks * 1024);
                     const uint32_t bo = TB ? (uint32_t)(ks * 1024) : (uint32_t)((ks >> 2) * (BS * 128) + (ks & 3) * 32);
-                    mma_tf32(d, umma_desc(a_lo + ao, A_LBO, A_SBO, A_LT), umma_desc(b_hi + bo, B_LBO, B_SBO, B_LT), IDESC, open ? 1u : 0u);
-                    mma_tf32(d, umma_desc(a_hi + ao, A_LBO, A_SBO, A_LT), umma_desc(b_lo + bo, B_LBO, B_SBO, B_LT), IDESC, 1u);
+                    const uint64_t dah = umma_desc(a_hi + ao, A_LBO, A_SBO, A_LT), dal = umma_desc(a_lo + ao, A_LBO, A_SBO, A_LT);
+                    const uint64_t dbh = umma_desc(b_hi + bo, B_LBO, B_SBO, B_LT), dbl = umma_desc(b_lo + bo, B_LBO, B_SBO, B_LT);
+                    mma_tf32(d_small, dal, dbh, IDESC, open ? 1u : 0u);
+                    mma_tf32(d_small2, dah, dbl, IDESC, (open || Cfg::NACC == 2) ? 1u : 0u);
+                    mma_tf32(d_big, dah, dbh, IDESC, open ? 1u : 0u);
                     open = true;
                 }
-#pragma unroll
-                for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {      // ... then the leading hi*hi terms
-                    const uint32_t ao = TA ? (uint32_t)((ks >> 2) * (BS * 128) + (ks & 3) * 32) : (uint32_t)(ks * 1024);
-                    const uint32_t bo = TB ? (uint32_t)(ks * 1024) : (uint32_t)((ks >> 2) * (BS * 128) + (ks & 3) * 32);
-                    mma_tf32(d, umma_desc(a_hi + ao, A_LBO, A_SBO, A_LT), umma_desc(b_hi + bo, B_LBO, B_SBO, B_LT), IDESC, 1u);
                 }
                 tc_commit(smem_u32(&hd->empty[s]));             // stage free when these MMAs have read it
                 if (m.flags & 16) {                             // product complete: hand the accumulator to the epilogue
@@ -271,7 +282,7 @@ k_gemm_f32_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             const uint32_t s = it % NST, ph = (it / NST) & 1u;
             mbar_wait(smem_u32(&hd->full_raw[s]), ph);
             const int flags = hd->meta[s].flags;
-            if (!(flags & 4)) {
+            if (!(flags & 4) && !(raw_hi & 4)) {
                 unsigned char* st = stages + (size_t)s * Cfg::STAGE_BYTES;
 #pragma unroll
                 for (int op = 0; op < 2; ++op) {
@@ -284,7 +295,7 @@ k_gemm_f32_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                         h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
                         h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
                         h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
-                        hi[i] = h;
+                        if (!(raw_hi & 1)) hi[i] = h;   // raw_hi: the tensor core drops the 13 low mantissa bits itself
                         lo[i] = l;
                     }
                 }
@@ -298,7 +309,7 @@ k_gemm_f32_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         // ===== epilogue: warp (q,h) owns TMEM lanes [32q, 32q+32) = C rows, columns [h*CW, (h+1)*CW) =====
         const unsigned q = (warp - 8) & 3, h = (warp - 8) >> 2;
         constexpr int CW = Cfg::EPI_CW;
-        const int row = (int)(q * 32 + lane);
+        const int row = MM == 64 ? (lane < 16 ? (int)(q * 16 + lane) : BS) : (int)(q * 32 + lane);
         float acc[CW];
         for (uint32_t pc = 0;; ++pc) {
             const uint32_t as = pc & 1u;
@@ -308,16 +319,19 @@ k_gemm_f32_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             const int ctile = hd->acc_tile[as];
             tc_fence_after();
 #pragma unroll
-            for (int c0 = 0; c0 < CW; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((q * 32u) << 16) + as * BS + h * CW + c0, r);
-                tmem_ld_wait();
-                if (flags & 1) {
+            for (int c0 = 0; c0 < CW && !(raw_hi & 8); c0 += 32) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[c0 + j] = __uint_as_float(r[j]);
-                } else {
+                for (int a = 0; a < Cfg::NACC; ++a) {      // small terms first, the hi*hi accumulator last
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((q * 32u) << 16) + as * Cfg::ACC_COLS + a * BS + h * CW + c0, r);
+                    tmem_ld_wait();
+                    if (a == 0 && (flags & 1)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(r[j]));
+                        for (int j = 0; j < 32; ++j) acc[c0 + j] = __uint_as_float(r[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(r[j]));
+                    }
                 }
             }
             tc_fence_before();
@@ -337,6 +351,14 @@ k_gemm_f32_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+// development switches (HBSM_F32_MODE): bit 0 = leave the raw operand in place as "hi", bit 1 = issue M = 64 MMAs for leaves <= 64;
+// timing experiments with WRONG results: 4 = skip the hi/lo split, 8 = skip the TMEM drain, 16 = skip the MMAs
+int f32_mode() {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("HBSM_F32_MODE"); mode = e ? atoi(e) : 1; }   // default: raw operand as "hi"
+    return mode;
+}
+
 // 2-D fp32 view of a tile pool: dim0 = leaf row (contiguous), dim1 = leaf column + BS * tile; 128-B swizzled boxes
 bool make_f32_map(CUtensorMap* map, const void* tiles, size_t n_tiles, int LS, int box_rows, int box_cols, bool mn_major) {
     EncodeTiledFn enc = encode_tiled_fn();
@@ -350,15 +372,15 @@ bool make_f32_map(CUtensorMap* map, const void* tiles, size_t n_tiles, int LS, i
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int LS, int BS, bool TA, bool TB>
+template <int LS, int BS, int MM, bool TA, bool TB>
 bool launch_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n_ctiles, unsigned* counter,
                  float* Ct) {
-    using Cfg = F32Cfg<BS>;
+    using Cfg = F32Cfg<BS, MM>;
     CUtensorMap mapA, mapB;
     // K-major operand (k along leaf rows): box {32 k, BS mn};  MN-major: box {32 mn, KC k}
     if (!make_f32_map(&mapA, A.tiles.p, A.L, LS, 32, TA ? BS : Cfg::KC, !TA)) return false;
     if (!make_f32_map(&mapB, B.tiles.p, B.n_ext(), LS, 32, TB ? Cfg::KC : BS, TB)) return false;
-    auto kfn = k_gemm_f32_tc<LS, BS, TA, TB>;
+    auto kfn = k_gemm_f32_tc<LS, BS, MM, TA, TB>;
     static bool configured = false;
     if (!configured) {
         HB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -367,17 +389,17 @@ bool launch_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64
     const uint64_t units = (uint64_t)n_ctiles * (LS / BS) * (LS / BS);
     if (units >= 0x7fffffffull) return false;
     unsigned grid = (unsigned)std::min<uint64_t>(units, (uint64_t)engine().sm_count);
-    HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, ab, begin, n_ctiles, counter, Ct);
+    HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, ab, begin, n_ctiles, counter, Ct, f32_mode());
     return true;
 }
 
-template <int LS, int BS>
+template <int LS, int BS, int MM>
 bool launch_bs(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n, unsigned* counter,
                float* Ct) {
-    if (!tA && !tB) return launch_inst<LS, BS, false, false>(A, B, ab, begin, n, counter, Ct);
-    if (!tA && tB) return launch_inst<LS, BS, false, true>(A, B, ab, begin, n, counter, Ct);
-    if (tA && !tB) return launch_inst<LS, BS, true, false>(A, B, ab, begin, n, counter, Ct);
-    return launch_inst<LS, BS, true, true>(A, B, ab, begin, n, counter, Ct);
+    if (!tA && !tB) return launch_inst<LS, BS, MM, false, false>(A, B, ab, begin, n, counter, Ct);
+    if (!tA && tB) return launch_inst<LS, BS, MM, false, true>(A, B, ab, begin, n, counter, Ct);
+    if (tA && !tB) return launch_inst<LS, BS, MM, true, false>(A, B, ab, begin, n, counter, Ct);
+    return launch_inst<LS, BS, MM, true, true>(A, B, ab, begin, n, counter, Ct);
 }
 
 }  // namespace
@@ -385,10 +407,12 @@ bool launch_bs(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* 
 bool launch_gemm_f32_tc(const Matrix& A, bool tA, const Matrix& B, bool tB, const uint2* ab, const uint64_t* begin,
                         uint32_t n_ctiles, unsigned* counter, float* Ct) {
     switch (A.b) {
-        case 32: return launch_bs<32, 32>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
-        case 64: return launch_bs<64, 64>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
-        case 128: return launch_bs<128, 128>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
-        case 256: return launch_bs<256, 128>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
+        case 32: return (f32_mode() & 2) ? launch_bs<32, 32, 64>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct)
+                                          : launch_bs<32, 32, 128>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
+        case 64: return (f32_mode() & 2) ? launch_bs<64, 64, 64>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct)
+                                          : launch_bs<64, 64, 128>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
+        case 128: return launch_bs<128, 128, 128>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
+        case 256: return launch_bs<256, 128, 128>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
         default: return false;
     }
 }
