@@ -283,11 +283,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--n", type=int, default=None, help="override N (development only; the judged run uses the default)")
     ap.add_argument("--lam", type=float, default=None)
+    ap.add_argument("--leaf", type=int, default=None, help="override the leaf size (e.g. BASELINE config 4: --n 262144 --leaf 128)")
     args = ap.parse_args()
     if args.n:
         WORKLOAD["n"] = args.n
     if args.lam:
         WORKLOAD["lam"] = args.lam
+    if args.leaf:
+        WORKLOAD["b"] = args.leaf
     if args.impl == "reference":
         reference_arm(args)
     else:

@@ -351,8 +351,241 @@ k_gemm_f32_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Leaves of 32 / 64: ONE MMA per K-step computes all four hi/lo cross terms.
+//
+// Measured on B200: a kind::tf32 MMA is paced by the shared-memory fetch of its operands (~64 B/clk/SM), not by the
+// 32-clk dispatch floor.  Stacking  [A_hi ; A_lo]  along M and  [B_hi | B_lo]  along N turns the three MMAs of a K-step
+// (18 KiB of operand reads at BS = 64) into one M = N = 2*BS MMA (8 KiB) whose accumulator quadrants are
+//     D[0:BS, 0:BS] = hi*hi   D[0:BS, BS:2BS] = hi*lo   D[BS:2BS, 0:BS] = lo*hi   D[BS:2BS, BS:2BS] = lo*lo
+// (the lo*lo term comes for free).  The stacked operands are plain descriptors over the hi/lo buffers: MN-major
+// operands keep "hi slabs then lo slabs" (consecutive 32-element chunks, LBO apart), K-major operands interleave
+// "hi slab j, lo slab j" so that the 8-row groups of hi and lo are consecutive (SBO apart).
+// Epilogue: warps of TMEM lane quadrants 0,1 own the hi rows, quadrants 2,3 the lo rows of the SAME C rows; each keeps
+// its partial C tile in registers (round-to-nearest adds, one leaf product at a time) and the two halves are combined
+// through shared memory once per C tile.
+// ---------------------------------------------------------------------------------------------------
+template <int BS>
+struct Q4Cfg {
+    static constexpr int KC = BS;                            // whole leaf product per pipeline stage
+    static constexpr int OPER_BYTES = BS * KC * 4;
+    static constexpr int STAGE_BYTES = 4 * OPER_BYTES;       // A (hi+lo) | B (hi+lo)
+    static constexpr int NST = (192 * 1024 / STAGE_BYTES) > 8 ? 8 : (192 * 1024 / STAGE_BYTES);
+    static constexpr int MM = 2 * BS, NN = 2 * BS;           // stacked MMA shape
+    static constexpr int SLAB_MN = KC * 128, SLAB_K = BS * 128;
+    static constexpr int EPI_H = BS / 32;                    // 32-column groups of C
+    static constexpr int EPI_WARPS = 4 * EPI_H;
+    static constexpr int STG_BYTES = 2 * EPI_H * 32 * 32 * 4;   // lo-row partial tiles handed to the hi-row warps
+    static constexpr int HEADER_BYTES = 1024;
+    static constexpr int SMEM_BYTES = 1024 + HEADER_BYTES + NST * STAGE_BYTES + STG_BYTES;
+    static constexpr int TMEM_COLS = 2 * NN;                 // two accumulator sets (128 or 256 columns)
+    static constexpr int THREADS = 512;
+    static constexpr int CVT_WARPS = 4;
+    static constexpr int KSTEPS = KC / 8;
+};
+
+template <int BS, bool TA, bool TB>
+__global__ void __launch_bounds__(Q4Cfg<BS>::THREADS, 1)
+k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+              const uint2* __restrict__ ab, const uint64_t* __restrict__ begin, uint32_t n_ctiles,
+              unsigned* __restrict__ next_tile, float* __restrict__ Ct) {
+    using Cfg = Q4Cfg<BS>;
+    constexpr int NST = Cfg::NST, KC = Cfg::KC;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    F32Header* hd = reinterpret_cast<F32Header*>(smem);
+    unsigned char* stages = smem + Cfg::HEADER_BYTES;
+    float* stg = reinterpret_cast<float*>(stages + (size_t)NST * Cfg::STAGE_BYTES);
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(smem_u32(&hd->full_raw[s]), 1);
+            mbar_init(smem_u32(&hd->full_cvt[s]), Cfg::CVT_WARPS);
+            mbar_init(smem_u32(&hd->empty[s]), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&hd->tmem_full[a]), 1);
+            mbar_init(smem_u32(&hd->tmem_empty[a]), Cfg::EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&hd->tmem_base), Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = hd->tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer: raw operand slabs land in the "hi" positions of the stacked layout =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+            uint32_t it = 0;
+            for (;;) {
+                const unsigned tile = atomicAdd(next_tile, 1u);
+                if (tile >= n_ctiles) break;
+                const uint64_t p0 = begin[tile], p1 = begin[tile + 1];
+                uint2 t = ab[p0];
+                for (uint64_t p = p0; p < p1; ++p, ++it) {
+                    const uint2 tn = (p + 1 < p1) ? ab[p + 1] : t;
+                    const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                    mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
+                    const uint32_t fb = smem_u32(&hd->full_raw[s]);
+                    hd->meta[s].ctile = (int)tile;
+                    hd->meta[s].flags = (p == p0 ? 1 : 0) | (p + 1 == p1 ? 2 : 0);
+                    mbar_arrive_expect_tx(fb, 2 * Cfg::OPER_BYTES);
+                    const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + 2 * Cfg::OPER_BYTES;
+                    if (TA) {   // K-major: [BS mn][32 k] slabs, hi slab j at 2j * SLAB_K
+#pragma unroll
+                        for (int j = 0; j < KC / 32; ++j) tma_box_g2s(sa + 2 * j * Cfg::SLAB_K, &mapA, 32 * j, (int)t.x * BS, fb);
+                    } else {    // MN-major: [KC k][32 mn] slabs, hi slabs first
+#pragma unroll
+                        for (int j = 0; j < BS / 32; ++j) tma_box_g2s(sa + j * Cfg::SLAB_MN, &mapA, 32 * j, (int)t.x * BS, fb);
+                    }
+                    if (TB) {
+#pragma unroll
+                        for (int j = 0; j < BS / 32; ++j) tma_box_g2s(sb + j * Cfg::SLAB_MN, &mapB, 32 * j, (int)t.y * BS, fb);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < KC / 32; ++j) tma_box_g2s(sb + 2 * j * Cfg::SLAB_K, &mapB, 32 * j, (int)t.y * BS, fb);
+                    }
+                    t = tn;
+                }
+            }
+            const uint32_t s = it % NST, ph = (it / NST) & 1u;
+            mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
+            hd->meta[s].ctile = -1;
+            hd->meta[s].flags = 4;
+            mbar_arrive(smem_u32(&hd->full_raw[s]));
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one stacked MMA per K-step =====
+        if (lane == 0) {
+            constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TA ? 0u : 1u) << 15) | ((TB ? 1u : 0u) << 16) |
+                                       ((uint32_t)(Cfg::NN >> 3) << 17) | ((uint32_t)(Cfg::MM >> 4) << 24);
+            constexpr uint32_t A_LBO = TA ? 16 : Cfg::SLAB_MN, B_LBO = TB ? Cfg::SLAB_MN : 16;
+            constexpr uint32_t A_SBO = TA ? 1024 : 512, B_SBO = TB ? 512 : 1024;
+            constexpr uint32_t A_LT = TA ? 2 : 1, B_LT = TB ? 1 : 2;
+            for (uint32_t it = 0;; ++it) {
+                const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                mbar_wait(smem_u32(&hd->full_cvt[s]), ph);
+                const GemmMeta m = hd->meta[s];
+                const uint32_t as = it & 1u;
+                mbar_wait(smem_u32(&hd->tmem_empty[as]), ((it >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator set
+                if (m.flags & 4) {
+                    hd->acc_flags[as] = 4;
+                    __threadfence_block();
+                    mbar_arrive(smem_u32(&hd->tmem_full[as]));
+                    break;
+                }
+                tc_fence_after();
+                const uint32_t d = tmem_base + as * Cfg::NN;
+                const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES), sb = sa + 2 * Cfg::OPER_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+                    const uint32_t ao = TA ? (uint32_t)((ks >> 2) * 2 * Cfg::SLAB_K + (ks & 3) * 32) : (uint32_t)(ks * 1024);
+                    const uint32_t bo = TB ? (uint32_t)(ks * 1024) : (uint32_t)((ks >> 2) * 2 * Cfg::SLAB_K + (ks & 3) * 32);
+                    mma_tf32(d, umma_desc(sa + ao, A_LBO, A_SBO, A_LT), umma_desc(sb + bo, B_LBO, B_SBO, B_LT), IDESC, ks ? 1u : 0u);
+                }
+                tc_commit(smem_u32(&hd->empty[s]));
+                hd->acc_tile[as] = m.ctile;
+                hd->acc_flags[as] = m.flags & 3;
+                __threadfence_block();
+                tc_commit(smem_u32(&hd->tmem_full[as]));
+            }
+        }
+    } else if (warp >= 4 && warp < 4 + Cfg::CVT_WARPS) {
+        // ===== lo = x - trunc_tf32(x) next to every raw slab (the raw slab itself serves as hi) =====
+        const unsigned tid = threadIdx.x - 128;
+        for (uint32_t it = 0;; ++it) {
+            const uint32_t s = it % NST, ph = (it / NST) & 1u;
+            mbar_wait(smem_u32(&hd->full_raw[s]), ph);
+            const int flags = hd->meta[s].flags;
+            if (!(flags & 4)) {
+                unsigned char* st = stages + (size_t)s * Cfg::STAGE_BYTES;
+#pragma unroll
+                for (int op = 0; op < 2; ++op) {
+                    const bool kmajor = op == 0 ? TA : !TB;
+                    // K-major: KC/32 raw ranges of SLAB_K bytes, 2*SLAB_K apart, lo right behind each; MN-major: one range, lo at +OPER
+                    const int n_ranges = kmajor ? KC / 32 : 1;
+                    const int range_bytes = kmajor ? Cfg::SLAB_K : Cfg::OPER_BYTES;
+                    const int lo_off = kmajor ? Cfg::SLAB_K : Cfg::OPER_BYTES;
+                    for (int rg = 0; rg < n_ranges; ++rg) {
+                        const float4* hi = reinterpret_cast<const float4*>(st + op * 2 * Cfg::OPER_BYTES + rg * 2 * range_bytes);
+                        float4* lo = reinterpret_cast<float4*>(st + op * 2 * Cfg::OPER_BYTES + rg * 2 * range_bytes + lo_off);
+#pragma unroll 4
+                        for (int i = (int)tid; i < range_bytes / 16; i += Cfg::CVT_WARPS * 32) {
+                            const float4 x = hi[i];
+                            float4 l;
+                            l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                            l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                            l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                            l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                            lo[i] = l;
+                        }
+                    }
+                }
+                fence_proxy_async();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&hd->full_cvt[s]));
+            if (flags & 4) break;
+        }
+    } else if (warp >= 8 && (warp - 8) < Cfg::EPI_WARPS) {
+        // ===== epilogue: warp (q,h): TMEM lane quadrant q (0,1 = hi rows, 2,3 = lo rows), C columns [32h, 32h+32) =====
+        const unsigned q = (warp - 8) & 3, h = (warp - 8) >> 2;
+        const bool lo_rows = q >= 2;
+        // M = 128 (BS = 64): D row = lane index; M = 64 (BS = 32): D row i sits in lane 32*(i/16) + i%16
+        const int crow = BS == 64 ? (int)((q & 1) * 32 + lane) : (lane < 16 ? (int)((q & 1) * 16 + lane) : BS);
+        float* my_stg = stg + (size_t)(((q & 1) * Cfg::EPI_H + h) * 32 * 32);
+        float acc[32];
+        for (uint32_t pc = 0;; ++pc) {
+            const uint32_t as = pc & 1u;
+            mbar_wait(smem_u32(&hd->tmem_full[as]), (pc >> 1) & 1u);
+            const int flags = hd->acc_flags[as];
+            if (flags & 4) break;
+            const int ctile = hd->acc_tile[as];
+            tc_fence_after();
+            uint32_t r1[32], r2[32];
+            tmem_ld32(tmem_base + ((q * 32u) << 16) + as * Cfg::NN + BS + h * 32, r2);   // x * B_lo
+            tmem_ld32(tmem_base + ((q * 32u) << 16) + as * Cfg::NN + h * 32, r1);        // x * B_hi
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&hd->tmem_empty[as]));
+            if (flags & 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = __fadd_rn(__uint_as_float(r2[j]), __uint_as_float(r1[j]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = __fadd_rn(__fadd_rn(acc[j], __uint_as_float(r2[j])), __uint_as_float(r1[j]));
+            }
+            if (flags & 2) {   // k-list of this C tile done: lo-row partial sums -> hi-row warps -> global
+                if (lo_rows) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) my_stg[j * 32 + lane] = acc[j];
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(Cfg::EPI_WARPS * 32) : "memory");
+                if (!lo_rows && crow < BS) {
+                    float* C = Ct + (size_t)ctile * BS * BS + (size_t)(h * 32) * BS + crow;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) C[(size_t)j * BS] = __fadd_rn(acc[j], my_stg[j * 32 + lane]);
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(Cfg::EPI_WARPS * 32) : "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
 // development switches (HBSM_F32_MODE): bit 0 = leave the raw operand in place as "hi", bit 1 = issue M = 64 MMAs for leaves <= 64;
-// timing experiments with WRONG results: 4 = skip the hi/lo split, 8 = skip the TMEM drain, 16 = skip the MMAs
+// timing experiments with WRONG results: 4 = skip the hi/lo split, 8 = skip the TMEM drain, 16 = skip the MMAs;
+// 32 = use the three-MMA kernel for leaves of 32 / 64 as well (instead of the stacked-operand kernel)
 int f32_mode() {
     static int mode = -1;
     if (mode < 0) { const char* e = getenv("HBSM_F32_MODE"); mode = e ? atoi(e) : 1; }   // default: raw operand as "hi"
@@ -402,10 +635,41 @@ bool launch_bs(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* 
     return launch_inst<LS, BS, MM, true, true>(A, B, ab, begin, n, counter, Ct);
 }
 
+template <int BS, bool TA, bool TB>
+bool launch_q4_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n_ctiles, unsigned* counter,
+                    float* Ct) {
+    using Cfg = Q4Cfg<BS>;
+    CUtensorMap mapA, mapB;
+    if (!make_f32_map(&mapA, A.tiles.p, A.L, BS, 32, BS, !TA)) return false;
+    if (!make_f32_map(&mapB, B.tiles.p, B.n_ext(), BS, 32, BS, TB)) return false;
+    auto kfn = k_gemm_f32_q4<BS, TA, TB>;
+    static bool configured = false;
+    if (!configured) {
+        HB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    unsigned grid = std::min<unsigned>(n_ctiles, (unsigned)engine().sm_count);
+    HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, ab, begin, n_ctiles, counter, Ct);
+    return true;
+}
+
+template <int BS>
+bool launch_q4(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n, unsigned* counter,
+               float* Ct) {
+    if (!tA && !tB) return launch_q4_inst<BS, false, false>(A, B, ab, begin, n, counter, Ct);
+    if (!tA && tB) return launch_q4_inst<BS, false, true>(A, B, ab, begin, n, counter, Ct);
+    if (tA && !tB) return launch_q4_inst<BS, true, false>(A, B, ab, begin, n, counter, Ct);
+    return launch_q4_inst<BS, true, true>(A, B, ab, begin, n, counter, Ct);
+}
+
 }  // namespace
 
 bool launch_gemm_f32_tc(const Matrix& A, bool tA, const Matrix& B, bool tB, const uint2* ab, const uint64_t* begin,
                         uint32_t n_ctiles, unsigned* counter, float* Ct) {
+    if (!(f32_mode() & 32)) {   // leaves of 32 / 64: stacked hi/lo operands, one MMA per K-step
+        if (A.b == 32) return launch_q4<32>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
+        if (A.b == 64) return launch_q4<64>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
+    }
     switch (A.b) {
         case 32: return (f32_mode() & 2) ? launch_bs<32, 32, 64>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct)
                                           : launch_bs<32, 32, 128>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
