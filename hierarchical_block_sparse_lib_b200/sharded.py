@@ -167,6 +167,104 @@ def exchange_b(a_keys, a_norms, tA, b_keys, b_norms, b_tiles, tB, grid_side, spa
 
 
 # ---------------------------------------------------------------------------------------------------
+# published block tables: the two-round protocol
+# ---------------------------------------------------------------------------------------------------
+class PublishedTable:
+    """The (Morton key, leaf norm^2) table of a row-sharded matrix, gathered once on every rank -- the distributed part
+    of update_internal_info() (H:3905): like the cached norms it is valid until the matrix changes, and must be
+    refreshed by the caller (publish_table) before the matrix is used as op(B) in sharded products.
+    With it a rank decides locally which remote tiles its products touch, so one product needs only
+    (1) an all_to_all of request masks and (2) an all_to_all of the tiles themselves."""
+
+    def __init__(self, keys_all, norms_all, counts):
+        self.keys_all = keys_all                # [sum L_q] int64, rank-major, each rank's part in its local tile order
+        self.norms_all = norms_all              # [sum L_q]
+        self.counts = [int(c) for c in counts]  # L_q
+        self.offsets = [0]
+        for c in self.counts:
+            self.offsets.append(self.offsets[-1] + c)
+        self._k = {}
+
+    def k_of(self, tB):
+        """Contraction index k of every published tile of op(B)."""
+        if tB not in self._k:
+            br, bc = morton_decode(self.keys_all)
+            self._k[tB] = (bc if tB else br).contiguous()
+        return self._k[tB]
+
+
+def publish_table(b_keys, b_norms, group=None):
+    """all_gather of this rank's (keys, norms) -- variable lengths, padded to the longest."""
+    world = dist.get_world_size(group)
+    n = torch.tensor([b_keys.numel()], dtype=torch.int64, device=b_keys.device)
+    ns = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(ns, n, group=group)
+    counts = [int(x.item()) for x in ns]
+    m = max(max(counts), 1)
+    kp = torch.zeros((m,), dtype=b_keys.dtype, device=b_keys.device); kp[:b_keys.numel()] = b_keys
+    np_ = torch.zeros((m,), dtype=b_norms.dtype, device=b_norms.device); np_[:b_norms.numel()] = b_norms
+    kall = [torch.empty_like(kp) for _ in range(world)]; nall = [torch.empty_like(np_) for _ in range(world)]
+    dist.all_gather(kall, kp, group=group)
+    dist.all_gather(nall, np_, group=group)
+    keys_all = torch.cat([kall[q][:counts[q]] for q in range(world)])
+    norms_all = torch.cat([nall[q][:counts[q]] for q in range(world)])
+    return PublishedTable(keys_all, norms_all, counts)
+
+
+def exchange_b_published(thr, table, b_tiles, tB, spamm, tau, group=None, timers=None, recv_alloc=None):
+    """Two-round exchange.  `thr[k]` = this rank's request threshold per contraction index (request_thresholds or the
+    engine's hbsm_halo_request), `table` = PublishedTable of op(B), `b_tiles` = this rank's tiles (local order).
+    Returns (keys, norms, tiles) of the remote tiles this rank's products touch."""
+    world = dist.get_world_size(group); rank = dist.get_rank(group)
+    tr = _Trace(timers.setdefault("trace", {}) if timers is not None else None)
+    t0 = time.perf_counter()
+    k_all = table.k_of(bool(tB))
+    t = thr[k_all]
+    need = t >= 0
+    if spamm:
+        tau2 = torch.tensor(tau, dtype=table.norms_all.dtype, device=t.device)
+        tau2 = tau2 * tau2
+        need &= (t * table.norms_all) > tau2          # same fl(max_na*nb) > fl(tau^2) test as the three-round protocol
+    lo_r, hi_r = table.offsets[rank], table.offsets[rank + 1]
+    need[lo_r:hi_r] = False                           # own tiles are already here
+    need_u8 = need.to(torch.uint8)
+    tr.mark("mask")
+    # round 1: every owner learns which of its tiles each requester wants (fixed sizes: L_q bytes to owner q)
+    L_r = table.counts[rank]
+    asked = torch.empty((world * L_r,), dtype=torch.uint8, device=t.device)
+    dist.all_to_all_single(asked, need_u8, [L_r] * world, table.counts, group=group)
+    tr.mark("a2a_mask")
+    nz = torch.nonzero(asked.view(world, L_r), as_tuple=False)      # grouped by requester, ascending local tile index
+    recv_idx = torch.nonzero(need, as_tuple=False).flatten()        # ascending = grouped by owner, owner's tile order
+    owner_edges = torch.tensor(table.offsets, dtype=torch.int64, device=t.device)
+    cnt = torch.cat([torch.bincount(nz[:, 0], minlength=world),
+                     torch.bincount(torch.bucketize(recv_idx, owner_edges[1:], right=True), minlength=world)]).tolist()
+    send_counts = [int(c) for c in cnt[:world]]; recv_counts = [int(c) for c in cnt[world:2 * world]]
+    n_in = sum(recv_counts)
+    tr.mark("counts")
+    t1 = time.perf_counter()
+    tiles_out = b_tiles.index_select(0, nz[:, 1].contiguous())
+    tr.mark("pack")
+    if recv_alloc is not None:
+        keys_in, norms_in, tiles_in = recv_alloc(n_in)
+    else:
+        keys_in = torch.empty((n_in,), dtype=table.keys_all.dtype, device=t.device)
+        norms_in = torch.empty((n_in,), dtype=table.norms_all.dtype, device=t.device)
+        tiles_in = torch.empty((n_in, b_tiles.shape[1]), dtype=b_tiles.dtype, device=t.device)
+    # keys and norms of the incoming tiles are already known locally
+    torch.index_select(table.keys_all, 0, recv_idx, out=keys_in)
+    torch.index_select(table.norms_all, 0, recv_idx, out=norms_in)
+    # round 2: the tiles
+    dist.all_to_all_single(tiles_in, tiles_out, recv_counts, send_counts, group=group)
+    tr.mark("a2a_tiles")
+    if timers is not None:
+        timers["plan_s"] = t1 - t0
+        timers["sent_tiles"] = sum(send_counts)
+        timers["recv_tiles"] = n_in
+    return keys_in, norms_in, tiles_in
+
+
+# ---------------------------------------------------------------------------------------------------
 # engine glue (GPU only)
 # ---------------------------------------------------------------------------------------------------
 class _DevArray:
@@ -253,10 +351,24 @@ def _exchange_b_engine(A_loc, tA, B_loc, tB, b_keys, b_norms, b_tiles, grid_side
     return keys_in, norms_in, tiles_in
 
 
+def publish(B_loc, group=None):
+    """Distributed half of update_internal_info() for a matrix that will be the right operand of sharded products:
+    gathers its (key, norm) table on every rank.  Call after the norms are refreshed; valid until B_loc changes."""
+    from . import _capi
+    ext = torch.cuda.ExternalStream(int(_capi.lib().hbsm_stream() or 0))
+    with torch.cuda.stream(ext):
+        bk, bn, _ = device_views(B_loc)
+        table = publish_table(bk.clone(), bn.clone(), group)
+        ext.synchronize()
+    B_loc._published = table
+    return table
+
+
 def sharded_product(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, group=None, timers=None):
     """C_r = op(A)_r * op(B): A_loc / B_loc are this rank's engine matrices (full logical dims, only the slab's tiles;
     norms refreshed).  Remote op(B) tiles are received straight into B_loc's halo tail (hbsm_halo_reserve/commit), the
-    rank's own tiles are never copied.  Returns (C_loc, n_mults_local, n_blocks_local)."""
+    rank's own tiles are never copied.  If publish(B_loc) was called the two-round protocol is used, else the
+    self-contained three-round one.  Returns (C_loc, n_mults_local, n_blocks_local)."""
     from . import _capi
     from .matrix import HierarchicalBlockSparseMatrix as H
     grid_side = 1 << max(A_loc.expected_depth(), B_loc.expected_depth())
@@ -275,7 +387,14 @@ def sharded_product(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, group=None, time
             k, nr, t = _tail_views(B_loc, cap)            # (re)reads the pointers: a growth moves the arrays
             return k[:n], nr[:n], t[:n]
 
-        if os.environ.get("HBSM_SHARD_TORCH_PLAN", "0") == "1":     # same plan with torch ops (what the gloo tests run)
+        table = getattr(B_loc, "_published", None)
+        if table is not None and table.counts[dist.get_rank(group)] != bk.numel():
+            raise RuntimeError("sharded_product: the published table of B is stale (B changed after publish())")
+        if table is not None and os.environ.get("HBSM_SHARD_TORCH_PLAN", "0") != "1":
+            thr = torch.empty((grid_side,), dtype=bn.dtype, device=bn.device)
+            _capi.check(_capi.lib().hbsm_halo_request(A_loc._h, int(bool(tA)), C.c_void_p(thr.data_ptr())))
+            keys, norms, tiles = exchange_b_published(thr, table, bt, tB, spamm, tau, group, timers, recv_alloc)
+        elif os.environ.get("HBSM_SHARD_TORCH_PLAN", "0") == "1":     # same plan with torch ops (what the gloo tests run)
             keys, norms, tiles = exchange_b(ak, an, tA, bk, bn, bt, tB, grid_side, spamm, tau, group, timers, recv_alloc)
         else:
             keys, norms, tiles = _exchange_b_engine(A_loc, tA, B_loc, tB, bk, bn, bt, grid_side, spamm, tau, group, timers,
@@ -314,6 +433,8 @@ def bench_main(args, w, workload_config, fp64_peak, ClockSampler):
     lo, hi = slab_bounds(g, world, rank)
     A = H(np.float64, b); A.generate_decay(n, lam, W, w["seeds"][0], False, lo, hi); A.update_internal_info()
     B = H(np.float64, b); B.generate_decay(n, lam, W, w["seeds"][1], False, lo, hi); B.update_internal_info()
+    if os.environ.get("HBSM_SHARD_NO_PUBLISH", "0") != "1":
+        publish(B)     # distributed half of update_internal_info(): outside the timed region like the norm refresh itself
     ext = torch.cuda.ExternalStream(int(_capi.lib().hbsm_stream()))
     timers = {}
 
@@ -398,6 +519,8 @@ def _e2e_sharded(hb, H, A, B, w, steps, lo, hi):
         t0 = time.perf_counter()
         A2 = H(np.float64, b); A2.resize(n, n); A2.assign_tiles(abi, abj, at.numpy()); A2.update_internal_info()
         B2 = H(np.float64, b); B2.resize(n, n); B2.assign_tiles(bbi, bbj, bt.numpy()); B2.update_internal_info()
+        if os.environ.get("HBSM_SHARD_NO_PUBLISH", "0") != "1":
+            publish(B2)                      # inside the e2e region: B2 is a new matrix every step
         t_up = time.perf_counter() - t0
         Cm, nm, nr = sharded_product(A2, False, B2, False, True, tau)
         t_prod = time.perf_counter() - t0 - t_up

@@ -31,6 +31,7 @@ for (tA, tB, spamm, tau) in [(0, 0, True, 1e-6), (0, 0, False, 0.0), (0, 1, True
         m = (line >= lo) & (line < hi)
         X = H(np.float64, b); X.resize(n, n); X.assign_tiles(bi[m], bj[m], t[m]); X.update_internal_info(); return X
     Al = slab(Af, bool(tA)); Bl = slab(Bf, bool(tB))
+    if os.environ.get("HBSM_TEST_PUBLISH") == "1": S.publish(Bl)      # two-round protocol over the published table
     Cl, nm, nb = S.sharded_product(Al, tA, Bl, tB, spamm, tau)
     Cf = H(np.float64)
     nmf, nbf = (H.spamm(Af, tA, Bf, tB, Cf, tau, True) if spamm else H.multiply(Af, tA, Bf, tB, Cf))
@@ -48,7 +49,7 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("torch_plan", ["0", "1"])
+@pytest.mark.parametrize("torch_plan", ["0", "1", "published"])
 def test_sharded_matches_single_gpu(tmp_path, torch_plan):
     import torch
     ngpu = torch.cuda.device_count()
@@ -61,7 +62,8 @@ def test_sharded_matches_single_gpu(tmp_path, torch_plan):
     script.write_text(SCRIPT % {"root": ROOT})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)]
-    env = dict(os.environ, HBSM_SHARD_TORCH_PLAN=torch_plan)   # engine kernels (default) or the torch-op plan of the gloo tests
+    env = dict(os.environ, HBSM_SHARD_TORCH_PLAN="1" if torch_plan == "1" else "0",
+               HBSM_TEST_PUBLISH="1" if torch_plan == "published" else "0")   # engine kernels (default) or the torch-op plan of the gloo tests
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "sharded ok" in r.stdout

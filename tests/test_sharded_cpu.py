@@ -47,6 +47,12 @@ def _worker(rank, world, port, n, b, lam, tA, tB, spamm, tau, dtype_name, ret):
         am = (a_line >= lo) & (a_line < hi); bm = (b_line >= lo) & (b_line < hi)
         timers = {}
         keys, norms, tiles = S.exchange_b(ak[am], an[am], tA, bk[bm], bn[bm], bt[bm], tB, g, spamm, tau, None, timers)
+        # the two-round protocol over a published table must deliver exactly the same tiles
+        table = S.publish_table(bk[bm], bn[bm])
+        thr = S.request_thresholds(ak[am], an[am], tA, g)
+        k2, n2, t2 = S.exchange_b_published(thr, table, bt[bm], tB, spamm, tau)
+        o1 = torch.argsort(keys); o2 = torch.argsort(k2)
+        assert torch.equal(keys[o1], k2[o2]) and torch.equal(norms[o1], n2[o2]) and torch.equal(tiles[o1], t2[o2])
         # received (remote) tiles are the global ones, bit for bit, and none of them is owned by this rank
         pos = torch.searchsorted(bk, keys)
         assert torch.equal(bk[pos], keys) and torch.equal(bt[pos], tiles) and torch.equal(bn[pos], norms)
