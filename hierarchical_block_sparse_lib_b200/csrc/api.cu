@@ -331,6 +331,20 @@ int hbsm_halo_select(hbsm_handle B, int tB, const void* d_thr_in, int world, int
         halo_select(M(B), tB != 0, d_thr_in, world, rank, (uint32_t)lo, (uint32_t)rows, spamm != 0, tau, d_send_idx, counts);
     });
 }
+int hbsm_halo_mask(int dtype, const void* d_thr, const int64_t* d_k_all, const void* d_norms_all, size_t n_all, size_t own_lo,
+                   size_t own_hi, int spamm, double tau, uint8_t* d_need) {
+    return guarded([&] {
+        if (dtype != HBSM_F64 && dtype != HBSM_F32) throw Error(HBSM_E_ARG, "hbsm_b200: bad dtype");
+        halo_mask(dtype, d_thr, d_k_all, d_norms_all, n_all, own_lo, own_hi, spamm != 0, tau, d_need);
+    });
+}
+int hbsm_compact_flags(const uint8_t* d_flags, size_t n, size_t n_edges, const size_t* edges, size_t modulo, int64_t* d_idx,
+                       size_t* counts) {
+    return guarded([&] {
+        if (n_edges < 1 || !edges || !counts) throw Error(HBSM_E_ARG, "hbsm_b200: bad compact_flags arguments");
+        compact_flags(d_flags, n, n_edges, edges, modulo, d_idx, counts);
+    });
+}
 int hbsm_halo_reserve(hbsm_handle h, size_t capacity, uint64_t** d_keys, void** d_norms, void** d_tiles) {
     return guarded([&] { reserve_halo(M(h), capacity, d_keys, d_norms, d_tiles); });
 }

@@ -631,6 +631,32 @@ __global__ void k_halo_compact(const uint32_t* __restrict__ flags, const uint64_
     send_idx[pos[e]] = (int64_t)(e % L);
 }
 
+// published-table protocol: need[t] = 1 iff the published op(B) tile t (contraction index k_all[t], norm^2 norms_all[t])
+// is remote and touched by at least one product of this rank (request thr[k] as in k_halo_request)
+template <typename T>
+__global__ void k_halo_mask(const T* __restrict__ thr, const int64_t* __restrict__ k_all, const T* __restrict__ norms_all,
+                            size_t n_all, size_t own_lo, size_t own_hi, int spamm, T tau2, uint8_t* __restrict__ need) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_all) return;
+    bool keep = false;
+    if (i < own_lo || i >= own_hi) {
+        const T t = thr[k_all[i]];
+        keep = t >= (T)0;
+        if (keep && spamm) keep = DT<T>::mul(t, norms_all[i]) > tau2;
+    }
+    need[i] = keep ? 1 : 0;
+}
+__global__ void k_widen_u8(const uint8_t* __restrict__ in, size_t n, uint32_t* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] ? 1u : 0u;
+}
+__global__ void k_compact_idx(const uint32_t* __restrict__ flags, const uint64_t* __restrict__ pos, size_t n, size_t modulo,
+                              int64_t* __restrict__ out) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n || !flags[e]) return;
+    out[pos[e]] = (int64_t)(modulo ? e % modulo : e);
+}
+
 template <typename F>
 void dispatch(int dtype, F&& f) {
     if (dtype == HBSM_F64) f((double)0);
@@ -954,6 +980,35 @@ void halo_select(const Matrix& B, bool tB, const void* d_thr_in, int world, int 
         HB_CUDA(cudaMemcpyAsync(&edge[q], pos.p + (size_t)q * B.L, sizeof(uint64_t), cudaMemcpyDeviceToHost, engine().stream));
     sync_stream();
     for (int q = 0; q < world; ++q) h_counts[q] = (size_t)(edge[q + 1] - edge[q]);
+}
+
+void halo_mask(int dtype, const void* d_thr, const int64_t* d_k_all, const void* d_norms_all, size_t n_all, size_t own_lo,
+               size_t own_hi, bool spamm, double tau, uint8_t* d_need) {
+    ensure_engine();
+    if (n_all == 0) return;
+    dispatch(dtype, [&](auto z) {
+        using T = decltype(z);
+        const T tt = (T)tau;
+        HB_LAUNCH(k_halo_mask<T>, blocks_for(n_all, 256), 256, 0, (const T*)d_thr, d_k_all, (const T*)d_norms_all, n_all, own_lo,
+                  own_hi, spamm ? 1 : 0, (T)(tt * tt), d_need);
+    });
+}
+
+void compact_flags(const uint8_t* d_flags, size_t n, size_t n_edges, const size_t* edges, size_t modulo, int64_t* d_idx,
+                   size_t* counts) {
+    ensure_engine();
+    for (size_t q = 0; q + 1 < n_edges; ++q) counts[q] = 0;
+    if (n == 0) return;
+    DevBuf<uint32_t> wide(n);
+    HB_LAUNCH(k_widen_u8, blocks_for(n, 256), 256, 0, d_flags, n, wide.p);
+    DevBuf<uint64_t> pos(n + 1);
+    exclusive_scan_u32(wide.p, pos.p, n);
+    HB_LAUNCH(k_compact_idx, blocks_for(n, 256), 256, 0, wide.p, pos.p, n, modulo, d_idx);
+    std::vector<uint64_t> at(n_edges);
+    for (size_t q = 0; q < n_edges; ++q)
+        HB_CUDA(cudaMemcpyAsync(&at[q], pos.p + std::min(edges[q], n), sizeof(uint64_t), cudaMemcpyDeviceToHost, engine().stream));
+    sync_stream();
+    for (size_t q = 0; q + 1 < n_edges; ++q) counts[q] = (size_t)(at[q + 1] - at[q]);
 }
 
 // ---------------------------------------------------------------------------------------------------

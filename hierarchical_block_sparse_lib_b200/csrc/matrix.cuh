@@ -82,6 +82,10 @@ const LineIndex& line_index(const Matrix& A, bool by_col, bool with_halo = false
 void reserve_halo(Matrix& A, size_t cap, uint64_t** d_keys, void** d_norms, void** d_tiles);   // tail pointers
 void commit_halo(Matrix& A, size_t n_halo);
 void halo_request(const Matrix& A, bool tA, void* d_thr);
+void halo_mask(int dtype, const void* d_thr, const int64_t* d_k_all, const void* d_norms_all, size_t n_all, size_t own_lo,
+               size_t own_hi, bool spamm, double tau, uint8_t* d_need);
+void compact_flags(const uint8_t* d_flags, size_t n, size_t n_edges, const size_t* edges, size_t modulo, int64_t* d_idx,
+                   size_t* counts);
 void halo_select(const Matrix& B, bool tB, const void* d_thr_in, int world, int rank, uint32_t lo, uint32_t rows, bool spamm,
                  double tau, int64_t* d_send_idx, size_t* h_counts);
 void op_add(const Matrix& A, const Matrix& B, Matrix& C);

@@ -211,7 +211,7 @@ def publish_table(b_keys, b_norms, group=None):
     return PublishedTable(keys_all, norms_all, counts)
 
 
-def exchange_b_published(thr, table, b_tiles, tB, spamm, tau, group=None, timers=None, recv_alloc=None):
+def exchange_b_published(thr, table, b_tiles, tB, spamm, tau, group=None, timers=None, recv_alloc=None, engine=False):
     """Two-round exchange.  `thr[k]` = this rank's request threshold per contraction index (request_thresholds or the
     engine's hbsm_halo_request), `table` = PublishedTable of op(B), `b_tiles` = this rank's tiles (local order).
     Returns (keys, norms, tiles) of the remote tiles this rank's products touch."""
@@ -219,31 +219,54 @@ def exchange_b_published(thr, table, b_tiles, tB, spamm, tau, group=None, timers
     tr = _Trace(timers.setdefault("trace", {}) if timers is not None else None)
     t0 = time.perf_counter()
     k_all = table.k_of(bool(tB))
-    t = thr[k_all]
-    need = t >= 0
-    if spamm:
-        tau2 = torch.tensor(tau, dtype=table.norms_all.dtype, device=t.device)
-        tau2 = tau2 * tau2
-        need &= (t * table.norms_all) > tau2          # same fl(max_na*nb) > fl(tau^2) test as the three-round protocol
     lo_r, hi_r = table.offsets[rank], table.offsets[rank + 1]
-    need[lo_r:hi_r] = False                           # own tiles are already here
-    need_u8 = need.to(torch.uint8)
+    L_r = table.counts[rank]
+    n_all = table.offsets[-1]
+    if engine:     # the engine's kernels: 1 launch for the mask, scan + compaction for the index lists
+        from . import _capi
+        Lc = _capi.lib()
+        dt_code = _capi.HBSM_F64 if table.norms_all.dtype == torch.float64 else _capi.HBSM_F32
+        need_u8 = torch.empty((max(n_all, 1),), dtype=torch.uint8, device=thr.device)
+        _capi.check(Lc.hbsm_halo_mask(dt_code, C.c_void_p(thr.data_ptr()), C.c_void_p(k_all.data_ptr()),
+                                      C.c_void_p(table.norms_all.data_ptr()), n_all, lo_r, hi_r, int(bool(spamm)), float(tau),
+                                      C.c_void_p(need_u8.data_ptr())))
+        need_u8 = need_u8[:n_all]
+    else:
+        t = thr[k_all]
+        need = t >= 0
+        if spamm:
+            tau2 = torch.tensor(tau, dtype=table.norms_all.dtype, device=t.device)
+            tau2 = tau2 * tau2
+            need &= (t * table.norms_all) > tau2          # same fl(max_na*nb) > fl(tau^2) test as the three-round protocol
+        need[lo_r:hi_r] = False                           # own tiles are already here
+        need_u8 = need.to(torch.uint8)
+    t = thr
     tr.mark("mask")
     # round 1: every owner learns which of its tiles each requester wants (fixed sizes: L_q bytes to owner q)
-    L_r = table.counts[rank]
     asked = torch.empty((world * L_r,), dtype=torch.uint8, device=t.device)
     dist.all_to_all_single(asked, need_u8, [L_r] * world, table.counts, group=group)
     tr.mark("a2a_mask")
-    nz = torch.nonzero(asked.view(world, L_r), as_tuple=False)      # grouped by requester, ascending local tile index
-    recv_idx = torch.nonzero(need, as_tuple=False).flatten()        # ascending = grouped by owner, owner's tile order
-    owner_edges = torch.tensor(table.offsets, dtype=torch.int64, device=t.device)
-    cnt = torch.cat([torch.bincount(nz[:, 0], minlength=world),
-                     torch.bincount(torch.bucketize(recv_idx, owner_edges[1:], right=True), minlength=world)]).tolist()
-    send_counts = [int(c) for c in cnt[:world]]; recv_counts = [int(c) for c in cnt[world:2 * world]]
+    if engine:
+        send_idx = torch.empty((max(world * L_r, 1),), dtype=torch.int64, device=t.device)
+        recv_idx = torch.empty((max(n_all, 1),), dtype=torch.int64, device=t.device)
+        e1 = (C.c_size_t * (world + 1))(*[q * L_r for q in range(world + 1)]); c1 = (C.c_size_t * world)()
+        e2 = (C.c_size_t * (world + 1))(*table.offsets); c2 = (C.c_size_t * world)()
+        _capi.check(Lc.hbsm_compact_flags(C.c_void_p(asked.data_ptr()), world * L_r, world + 1, e1, L_r, C.c_void_p(send_idx.data_ptr()), c1))
+        _capi.check(Lc.hbsm_compact_flags(C.c_void_p(need_u8.data_ptr()), n_all, world + 1, e2, 0, C.c_void_p(recv_idx.data_ptr()), c2))
+        send_counts = [int(c) for c in c1]; recv_counts = [int(c) for c in c2]
+        send_idx = send_idx[:sum(send_counts)]; recv_idx = recv_idx[:sum(recv_counts)]
+    else:
+        nz = torch.nonzero(asked.view(world, L_r), as_tuple=False)      # grouped by requester, ascending local tile index
+        send_idx = nz[:, 1].contiguous()
+        recv_idx = torch.nonzero(need, as_tuple=False).flatten()        # ascending = grouped by owner, owner's tile order
+        owner_edges = torch.tensor(table.offsets, dtype=torch.int64, device=t.device)
+        cnt = torch.cat([torch.bincount(nz[:, 0], minlength=world),
+                         torch.bincount(torch.bucketize(recv_idx, owner_edges[1:], right=True), minlength=world)]).tolist()
+        send_counts = [int(c) for c in cnt[:world]]; recv_counts = [int(c) for c in cnt[world:2 * world]]
     n_in = sum(recv_counts)
     tr.mark("counts")
     t1 = time.perf_counter()
-    tiles_out = b_tiles.index_select(0, nz[:, 1].contiguous())
+    tiles_out = b_tiles.index_select(0, send_idx)
     tr.mark("pack")
     if recv_alloc is not None:
         keys_in, norms_in, tiles_in = recv_alloc(n_in)
@@ -393,7 +416,7 @@ def sharded_product(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, group=None, time
         if table is not None and os.environ.get("HBSM_SHARD_TORCH_PLAN", "0") != "1":
             thr = torch.empty((grid_side,), dtype=bn.dtype, device=bn.device)
             _capi.check(_capi.lib().hbsm_halo_request(A_loc._h, int(bool(tA)), C.c_void_p(thr.data_ptr())))
-            keys, norms, tiles = exchange_b_published(thr, table, bt, tB, spamm, tau, group, timers, recv_alloc)
+            keys, norms, tiles = exchange_b_published(thr, table, bt, tB, spamm, tau, group, timers, recv_alloc, engine=True)
         elif os.environ.get("HBSM_SHARD_TORCH_PLAN", "0") == "1":     # same plan with torch ops (what the gloo tests run)
             keys, norms, tiles = exchange_b(ak, an, tA, bk, bn, bt, tB, grid_side, spamm, tau, group, timers, recv_alloc)
         else:

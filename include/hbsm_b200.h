@@ -141,6 +141,14 @@ int hbsm_assign_device_tiles(hbsm_handle h, size_t n_tiles, const uint64_t* d_mo
 int hbsm_halo_request(hbsm_handle A, int tA, void* d_thr);
 int hbsm_halo_select(hbsm_handle B, int tB, const void* d_thr_in, int world, int rank, int lo, int rows, int spamm, double tau,
                      int64_t* d_send_idx, size_t* counts);
+/* Published-table protocol (sharded.py, PublishedTable): d_need[t] = 1 iff published tile t -- contraction index
+ * d_k_all[t], leaf norm^2 d_norms_all[t] -- lies outside [own_lo, own_hi) and d_thr[d_k_all[t]] >= 0 and (exact multiply
+ * or fl(d_thr[..] * norm) > fl(tau*tau)).  hbsm_compact_flags: indices (mod `modulo` if non-zero) of the non-zero flags,
+ * ascending, into d_idx; counts[q] = number of flags set in [edges[q], edges[q+1]) for the n_edges-1 intervals. */
+int hbsm_halo_mask(int dtype, const void* d_thr, const int64_t* d_k_all, const void* d_norms_all, size_t n_all, size_t own_lo,
+                   size_t own_hi, int spamm, double tau, uint8_t* d_need);
+int hbsm_compact_flags(const uint8_t* d_flags, size_t n, size_t n_edges, const size_t* edges, size_t modulo, int64_t* d_idx,
+                       size_t* counts);
 int hbsm_halo_reserve(hbsm_handle h, size_t capacity, uint64_t** d_keys, void** d_norms, void** d_tiles);
 int hbsm_halo_commit(hbsm_handle h, size_t n_halo);
 /* banded decay generator a_ij = (0.5+0.5u(seed,i,j)) * table[|i-j|], |i-j| <= W (table has W+1 entries, e.g.
