@@ -58,6 +58,6 @@ struct GemmMeta { int ctile; int flags; };   // flags: 1 = first chunk of a C ti
 
 // fp32 leaf GEMM on the 5th-generation tensor cores (gemm_f32.cu); false = blocksize/driver not supported
 bool launch_gemm_f32_tc(const Matrix& A, bool tA, const Matrix& B, bool tB, const uint2* ab, const uint64_t* begin,
-                        uint32_t n_ctiles, unsigned* counter, float* Ct);
+                        uint32_t n_ctiles, const uint32_t* tile_list, unsigned* counter, float* Ct);
 
 }  // namespace hbsm_b200

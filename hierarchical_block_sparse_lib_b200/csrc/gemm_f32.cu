@@ -126,7 +126,7 @@ template <int LS, int BS, int MM, bool TA, bool TB>
 __global__ void __launch_bounds__(F32Cfg<BS, MM>::THREADS, 1)
 k_gemm_f32_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
               const uint2* __restrict__ ab, const uint64_t* __restrict__ begin, uint32_t n_ctiles,
-              unsigned* __restrict__ next_tile, float* __restrict__ Ct, int raw_hi /* development switches, see f32_mode() */) {
+              const uint32_t* __restrict__ tile_list, unsigned* __restrict__ next_tile, float* __restrict__ Ct, int raw_hi /* development switches, see f32_mode() */) {
     using Cfg = F32Cfg<BS, MM>;
     static_assert(MM == 128 || (MM == 64 && BS <= 64), "MMA M shape");
     constexpr int S = LS / BS;            // sub-tiles per leaf side
@@ -165,7 +165,9 @@ k_gemm_f32_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             for (;;) {
                 const unsigned unit = atomicAdd(next_tile, 1u);       // work unit = (C tile, sub-tile)
                 if (unit >= n_ctiles * (unsigned)(S * S)) break;
-                const unsigned tile = unit / (S * S), sub = unit % (S * S);
+                const unsigned sub = unit % (S * S);
+                const unsigned tile = tile_list ? tile_list[unit / (S * S)] : unit / (S * S);
+                const int cunit = (int)(tile * (S * S) + sub);
                 const int si = (int)(sub % S) * BS, sj = (int)(sub / S) * BS;   // row / column offset of the C sub-tile
                 const uint64_t p0 = begin[tile], p1 = begin[tile + 1];
                 uint2 t = ab[p0];
@@ -183,7 +185,7 @@ k_gemm_f32_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                             if (p + 1 == p1 && kk == S - 1) fl |= 2;          // ... the last
                             if (ch == 0) fl |= 8;                             // first K-chunk of this accumulator
                             if (ch == Cfg::NCHUNK - 1) fl |= 16;              // last K-chunk
-                            hd->meta[s].ctile = (int)unit;
+                            hd->meta[s].ctile = cunit;
                             hd->meta[s].flags = fl;
                             mbar_arrive_expect_tx(fb, 2 * Cfg::OPER_BYTES);
                             const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
@@ -388,7 +390,7 @@ template <int BS, bool TA, bool TB>
 __global__ void __launch_bounds__(Q4Cfg<BS>::THREADS, 1)
 k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
               const uint2* __restrict__ ab, const uint64_t* __restrict__ begin, uint32_t n_ctiles,
-              unsigned* __restrict__ next_tile, float* __restrict__ Ct) {
+              const uint32_t* __restrict__ tile_list, unsigned* __restrict__ next_tile, float* __restrict__ Ct) {
     using Cfg = Q4Cfg<BS>;
     constexpr int NST = Cfg::NST, KC = Cfg::KC;
     extern __shared__ unsigned char smem_raw[];
@@ -423,8 +425,9 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
             uint32_t it = 0;
             for (;;) {
-                const unsigned tile = atomicAdd(next_tile, 1u);
+                unsigned tile = atomicAdd(next_tile, 1u);
                 if (tile >= n_ctiles) break;
+                if (tile_list) tile = tile_list[tile];
                 const uint64_t p0 = begin[tile], p1 = begin[tile + 1];
                 uint2 t = ab[p0];
                 for (uint64_t p = p0; p < p1; ++p, ++it) {
@@ -606,8 +609,8 @@ bool make_f32_map(CUtensorMap* map, const void* tiles, size_t n_tiles, int LS, i
 }
 
 template <int LS, int BS, int MM, bool TA, bool TB>
-bool launch_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n_ctiles, unsigned* counter,
-                 float* Ct) {
+bool launch_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n_ctiles,
+                 const uint32_t* tile_list, unsigned* counter, float* Ct) {
     using Cfg = F32Cfg<BS, MM>;
     CUtensorMap mapA, mapB;
     // K-major operand (k along leaf rows): box {32 k, BS mn};  MN-major: box {32 mn, KC k}
@@ -622,22 +625,22 @@ bool launch_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64
     const uint64_t units = (uint64_t)n_ctiles * (LS / BS) * (LS / BS);
     if (units >= 0x7fffffffull) return false;
     unsigned grid = (unsigned)std::min<uint64_t>(units, (uint64_t)engine().sm_count);
-    HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, ab, begin, n_ctiles, counter, Ct, f32_mode());
+    HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, ab, begin, n_ctiles, tile_list, counter, Ct, f32_mode());
     return true;
 }
 
 template <int LS, int BS, int MM>
-bool launch_bs(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n, unsigned* counter,
-               float* Ct) {
-    if (!tA && !tB) return launch_inst<LS, BS, MM, false, false>(A, B, ab, begin, n, counter, Ct);
-    if (!tA && tB) return launch_inst<LS, BS, MM, false, true>(A, B, ab, begin, n, counter, Ct);
-    if (tA && !tB) return launch_inst<LS, BS, MM, true, false>(A, B, ab, begin, n, counter, Ct);
-    return launch_inst<LS, BS, MM, true, true>(A, B, ab, begin, n, counter, Ct);
+bool launch_bs(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n,
+               const uint32_t* tile_list, unsigned* counter, float* Ct) {
+    if (!tA && !tB) return launch_inst<LS, BS, MM, false, false>(A, B, ab, begin, n, tile_list, counter, Ct);
+    if (!tA && tB) return launch_inst<LS, BS, MM, false, true>(A, B, ab, begin, n, tile_list, counter, Ct);
+    if (tA && !tB) return launch_inst<LS, BS, MM, true, false>(A, B, ab, begin, n, tile_list, counter, Ct);
+    return launch_inst<LS, BS, MM, true, true>(A, B, ab, begin, n, tile_list, counter, Ct);
 }
 
 template <int BS, bool TA, bool TB>
-bool launch_q4_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n_ctiles, unsigned* counter,
-                    float* Ct) {
+bool launch_q4_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n_ctiles,
+                    const uint32_t* tile_list, unsigned* counter, float* Ct) {
     using Cfg = Q4Cfg<BS>;
     CUtensorMap mapA, mapB;
     if (!make_f32_map(&mapA, A.tiles.p, A.L, BS, 32, BS, !TA)) return false;
@@ -649,34 +652,34 @@ bool launch_q4_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uin
         configured = true;
     }
     unsigned grid = std::min<unsigned>(n_ctiles, (unsigned)engine().sm_count);
-    HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, ab, begin, n_ctiles, counter, Ct);
+    HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, ab, begin, n_ctiles, tile_list, counter, Ct);
     return true;
 }
 
 template <int BS>
-bool launch_q4(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n, unsigned* counter,
-               float* Ct) {
-    if (!tA && !tB) return launch_q4_inst<BS, false, false>(A, B, ab, begin, n, counter, Ct);
-    if (!tA && tB) return launch_q4_inst<BS, false, true>(A, B, ab, begin, n, counter, Ct);
-    if (tA && !tB) return launch_q4_inst<BS, true, false>(A, B, ab, begin, n, counter, Ct);
-    return launch_q4_inst<BS, true, true>(A, B, ab, begin, n, counter, Ct);
+bool launch_q4(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n,
+               const uint32_t* tile_list, unsigned* counter, float* Ct) {
+    if (!tA && !tB) return launch_q4_inst<BS, false, false>(A, B, ab, begin, n, tile_list, counter, Ct);
+    if (!tA && tB) return launch_q4_inst<BS, false, true>(A, B, ab, begin, n, tile_list, counter, Ct);
+    if (tA && !tB) return launch_q4_inst<BS, true, false>(A, B, ab, begin, n, tile_list, counter, Ct);
+    return launch_q4_inst<BS, true, true>(A, B, ab, begin, n, tile_list, counter, Ct);
 }
 
 }  // namespace
 
 bool launch_gemm_f32_tc(const Matrix& A, bool tA, const Matrix& B, bool tB, const uint2* ab, const uint64_t* begin,
-                        uint32_t n_ctiles, unsigned* counter, float* Ct) {
+                        uint32_t n_ctiles, const uint32_t* tile_list, unsigned* counter, float* Ct) {
     if (!(f32_mode() & 32)) {   // leaves of 32 / 64: stacked hi/lo operands, one MMA per K-step
-        if (A.b == 32) return launch_q4<32>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
-        if (A.b == 64) return launch_q4<64>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
+        if (A.b == 32) return launch_q4<32>(tA, tB, A, B, ab, begin, n_ctiles, tile_list, counter, Ct);
+        if (A.b == 64) return launch_q4<64>(tA, tB, A, B, ab, begin, n_ctiles, tile_list, counter, Ct);
     }
     switch (A.b) {
-        case 32: return (f32_mode() & 2) ? launch_bs<32, 32, 64>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct)
-                                          : launch_bs<32, 32, 128>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
-        case 64: return (f32_mode() & 2) ? launch_bs<64, 64, 64>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct)
-                                          : launch_bs<64, 64, 128>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
-        case 128: return launch_bs<128, 128, 128>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
-        case 256: return launch_bs<256, 128, 128>(tA, tB, A, B, ab, begin, n_ctiles, counter, Ct);
+        case 32: return (f32_mode() & 2) ? launch_bs<32, 32, 64>(tA, tB, A, B, ab, begin, n_ctiles, tile_list, counter, Ct)
+                                          : launch_bs<32, 32, 128>(tA, tB, A, B, ab, begin, n_ctiles, tile_list, counter, Ct);
+        case 64: return (f32_mode() & 2) ? launch_bs<64, 64, 64>(tA, tB, A, B, ab, begin, n_ctiles, tile_list, counter, Ct)
+                                          : launch_bs<64, 64, 128>(tA, tB, A, B, ab, begin, n_ctiles, tile_list, counter, Ct);
+        case 128: return launch_bs<128, 128, 128>(tA, tB, A, B, ab, begin, n_ctiles, tile_list, counter, Ct);
+        case 256: return launch_bs<256, 128, 128>(tA, tB, A, B, ab, begin, n_ctiles, tile_list, counter, Ct);
         default: return false;
     }
 }

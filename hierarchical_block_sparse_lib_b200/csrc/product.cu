@@ -123,10 +123,12 @@ __global__ void k_task_finish(const uint64_t* __restrict__ keys, const uint32_t*
 template <typename T>
 __global__ void __launch_bounds__(256) k_gemm_generic(const T* __restrict__ At, const T* __restrict__ Bt,
                                                        const uint2* __restrict__ ab, const uint64_t* __restrict__ begin,
-                                                       int b, int tA, int tB, T* __restrict__ Ct) {
+                                                       const uint32_t* __restrict__ tile_list, int b, int tA, int tB,
+                                                       T* __restrict__ Ct) {
     const size_t bb = (size_t)b * b;
-    const uint64_t p0 = begin[blockIdx.x], p1 = begin[blockIdx.x + 1];
-    T* C = Ct + (size_t)blockIdx.x * bb;
+    const size_t ctile = tile_list ? tile_list[blockIdx.x] : blockIdx.x;   // optional indirection: a subset of C's tiles
+    const uint64_t p0 = begin[ctile], p1 = begin[ctile + 1];
+    T* C = Ct + ctile * bb;
     for (size_t idx = threadIdx.x; idx < bb; idx += blockDim.x) {
         const int i = (int)(idx % b), j = (int)(idx / b);
         T acc = 0;
@@ -190,8 +192,8 @@ struct GemmCfg {
 template <int BS, int KC, bool TA, bool TB>
 __global__ void __launch_bounds__(GemmCfg<BS, KC, TA, TB>::THREADS, 1)
 k_gemm_f64(const double* __restrict__ At, const double* __restrict__ Bt, const uint2* __restrict__ ab,
-           const uint64_t* __restrict__ begin, uint32_t n_ctiles, unsigned* __restrict__ next_tile,
-           double* __restrict__ Ct) {
+           const uint64_t* __restrict__ begin, uint32_t n_ctiles, const uint32_t* __restrict__ tile_list,
+           unsigned* __restrict__ next_tile, double* __restrict__ Ct) {
     using Cfg = GemmCfg<BS, KC, TA, TB>;
     constexpr int NST = Cfg::NST;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -220,6 +222,7 @@ k_gemm_f64(const double* __restrict__ At, const double* __restrict__ Bt, const u
             if (lane == 0) tile = atomicAdd(next_tile, 1u);
             tile = __shfl_sync(0xffffffffu, tile, 0);
             if (tile >= n_ctiles) break;
+            if (tile_list) tile = tile_list[tile];
             const uint64_t p0 = begin[tile], p1 = begin[tile + 1];
             for (uint64_t p = p0; p < p1; ++p) {
                 const uint2 t = ab[p];
@@ -319,7 +322,7 @@ k_gemm_f64(const double* __restrict__ At, const double* __restrict__ Bt, const u
 
 template <int BS, int KC, bool TA, bool TB>
 void launch_gemm_f64_inst(const double* At, const double* Bt, const uint2* ab, const uint64_t* begin, uint32_t n_ctiles,
-                          unsigned* counter, double* Ct) {
+                          const uint32_t* tile_list, unsigned* counter, double* Ct) {
     using Cfg = GemmCfg<BS, KC, TA, TB>;
     auto kfn = k_gemm_f64<BS, KC, TA, TB>;
     static bool configured = false;
@@ -328,16 +331,16 @@ void launch_gemm_f64_inst(const double* At, const double* Bt, const uint2* ab, c
         configured = true;
     }
     unsigned grid = std::min<unsigned>(n_ctiles, (unsigned)engine().sm_count);
-    HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, At, Bt, ab, begin, n_ctiles, counter, Ct);
+    HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, At, Bt, ab, begin, n_ctiles, tile_list, counter, Ct);
 }
 
 template <int BS, int KC>
 void launch_gemm_f64(bool tA, bool tB, const double* At, const double* Bt, const uint2* ab, const uint64_t* begin,
-                     uint32_t n_ctiles, unsigned* counter, double* Ct) {
-    if (!tA && !tB) launch_gemm_f64_inst<BS, KC, false, false>(At, Bt, ab, begin, n_ctiles, counter, Ct);
-    else if (!tA && tB) launch_gemm_f64_inst<BS, KC, false, true>(At, Bt, ab, begin, n_ctiles, counter, Ct);
-    else if (tA && !tB) launch_gemm_f64_inst<BS, KC, true, false>(At, Bt, ab, begin, n_ctiles, counter, Ct);
-    else launch_gemm_f64_inst<BS, KC, true, true>(At, Bt, ab, begin, n_ctiles, counter, Ct);
+                     uint32_t n_ctiles, const uint32_t* tile_list, unsigned* counter, double* Ct) {
+    if (!tA && !tB) launch_gemm_f64_inst<BS, KC, false, false>(At, Bt, ab, begin, n_ctiles, tile_list, counter, Ct);
+    else if (!tA && tB) launch_gemm_f64_inst<BS, KC, false, true>(At, Bt, ab, begin, n_ctiles, tile_list, counter, Ct);
+    else if (tA && !tB) launch_gemm_f64_inst<BS, KC, true, false>(At, Bt, ab, begin, n_ctiles, tile_list, counter, Ct);
+    else launch_gemm_f64_inst<BS, KC, true, true>(At, Bt, ab, begin, n_ctiles, tile_list, counter, Ct);
 }
 
 
@@ -384,7 +387,7 @@ template <int LS, int BS, int KC, bool TA, bool TB>
 __global__ void __launch_bounds__(TmaCfg<BS, KC>::THREADS, 1)
 k_gemm_f64_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const uint2* __restrict__ ab, const uint64_t* __restrict__ begin, uint32_t n_ctiles,
-               unsigned* __restrict__ next_tile, double* __restrict__ Ct) {
+               const uint32_t* __restrict__ tile_list, unsigned* __restrict__ next_tile, double* __restrict__ Ct) {
     using Cfg = TmaCfg<BS, KC>;
     constexpr int NST = Cfg::NST;
     constexpr int S = LS / BS;
@@ -415,7 +418,9 @@ k_gemm_f64_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (;;) {
                 const unsigned unit = atomicAdd(next_tile, 1u);       // work unit = (C tile, sub-tile)
                 if (unit >= n_ctiles * (unsigned)(S * S)) break;
-                const unsigned tile = unit / (S * S), sub = unit % (S * S);
+                const unsigned sub = unit % (S * S);
+                const unsigned tile = tile_list ? tile_list[unit / (S * S)] : unit / (S * S);
+                const int cunit = (int)(tile * (S * S) + sub);
                 const int si = (int)(sub % S) * BS, sj = (int)(sub / S) * BS;
                 const uint64_t p0 = begin[tile], p1 = begin[tile + 1];
                 uint2 t = ab[p0];
@@ -429,7 +434,7 @@ k_gemm_f64_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         int fl = 0;
                         if (p == p0 && kc == 0) fl |= 1;
                         if (p + 1 == p1 && kc == S * Cfg::NCHUNK - 1) fl |= 2;
-                        meta[s].ctile = (int)unit;
+                        meta[s].ctile = cunit;
                         meta[s].flags = fl;
                         mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
                         const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
@@ -523,7 +528,7 @@ bool make_tile_map(CUtensorMap* map, const void* tiles, size_t n_tiles, int LS, 
 
 template <int LS, int BS, int KC, bool TA, bool TB>
 bool launch_gemm_f64_tma_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n_ctiles,
-                              unsigned* counter, double* Ct) {
+                              const uint32_t* tile_list, unsigned* counter, double* Ct) {
     using Cfg = TmaCfg<BS, KC>;
     CUtensorMap mapA, mapB;
     if (!make_tile_map(&mapA, A.tiles.p, A.L, LS, BS, KC, TA, 8, CU_TENSOR_MAP_DATA_TYPE_FLOAT64)) return false;
@@ -537,17 +542,17 @@ bool launch_gemm_f64_tma_inst(const Matrix& A, const Matrix& B, const uint2* ab,
     const uint64_t units = (uint64_t)n_ctiles * (LS / BS) * (LS / BS);
     if (units >= 0x7fffffffull) return false;
     unsigned grid = (unsigned)std::min<uint64_t>(units, (uint64_t)engine().sm_count);
-    HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, ab, begin, n_ctiles, counter, Ct);
+    HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, ab, begin, n_ctiles, tile_list, counter, Ct);
     return true;
 }
 
 template <int LS, int BS, int KC>
 bool launch_gemm_f64_tma(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin,
-                         uint32_t n_ctiles, unsigned* counter, double* Ct) {
-    if (!tA && !tB) return launch_gemm_f64_tma_inst<LS, BS, KC, false, false>(A, B, ab, begin, n_ctiles, counter, Ct);
-    if (!tA && tB) return launch_gemm_f64_tma_inst<LS, BS, KC, false, true>(A, B, ab, begin, n_ctiles, counter, Ct);
-    if (tA && !tB) return launch_gemm_f64_tma_inst<LS, BS, KC, true, false>(A, B, ab, begin, n_ctiles, counter, Ct);
-    return launch_gemm_f64_tma_inst<LS, BS, KC, true, true>(A, B, ab, begin, n_ctiles, counter, Ct);
+                         uint32_t n_ctiles, const uint32_t* tile_list, unsigned* counter, double* Ct) {
+    if (!tA && !tB) return launch_gemm_f64_tma_inst<LS, BS, KC, false, false>(A, B, ab, begin, n_ctiles, tile_list, counter, Ct);
+    if (!tA && tB) return launch_gemm_f64_tma_inst<LS, BS, KC, false, true>(A, B, ab, begin, n_ctiles, tile_list, counter, Ct);
+    if (tA && !tB) return launch_gemm_f64_tma_inst<LS, BS, KC, true, false>(A, B, ab, begin, n_ctiles, tile_list, counter, Ct);
+    return launch_gemm_f64_tma_inst<LS, BS, KC, true, true>(A, B, ab, begin, n_ctiles, tile_list, counter, Ct);
 }
 
 struct TaskList {
@@ -667,109 +672,205 @@ bool worth_product(const Matrix& A, bool tA, const Matrix& B, bool tB, bool spam
     return tl.n_products > 0;
 }
 
-void op_product(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, const ProductOpts& o, size_t* n_mults,
-                size_t* n_blocks) {
+namespace {
+
+// per C tile: does any of its products read a halo tile of B (tile index >= n_own)?
+__global__ void k_classify_ctiles(const uint2* __restrict__ ab, const uint64_t* __restrict__ begin, size_t nct, uint32_t n_own,
+                                  uint32_t* __restrict__ own_only, uint32_t* __restrict__ needs_halo) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nct) return;
+    bool halo = false;
+    for (uint64_t p = begin[t]; p < begin[t + 1] && !halo; ++p) halo = ab[p].y >= n_own;
+    own_only[t] = halo ? 0u : 1u;
+    needs_halo[t] = halo ? 1u : 0u;
+}
+__global__ void k_list_from_flags(const uint32_t* __restrict__ flags, const uint64_t* __restrict__ pos, size_t n,
+                                  uint32_t* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) out[pos[i]] = (uint32_t)i;
+}
+
+size_t list_of(const DevBuf<uint32_t>& flags, size_t n, DevBuf<uint32_t>& out) {
+    DevBuf<uint64_t> pos(n + 1);
+    exclusive_scan_u32(flags.p, pos.p, n);
+    uint64_t total = 0;
+    HB_CUDA(cudaMemcpyAsync(&total, pos.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, engine().stream));
+    sync_stream();
+    out.alloc(std::max<size_t>((size_t)total, 1));
+    if (total) HB_LAUNCH(k_list_from_flags, blocks_for(n, 256), 256, 0, flags.p, pos.p, n, out.p);
+    return (size_t)total;
+}
+
+// one leaf-GEMM launch over `n` C tiles: all of them (tile_list == nullptr) or the listed subset
+void launch_leaf_gemm(const Matrix& A, bool tA, const Matrix& B, bool tB, const TaskList& tl, const uint32_t* tile_list, size_t n,
+                      char* ct) {
+    Engine& e = engine();
+    if (n == 0) return;
+    const uint32_t nn = (uint32_t)n;
+    const bool fast64 = A.dtype == HBSM_F64 && e.gemm_variant != 1 && (A.b == 32 || A.b == 64 || A.b == 128 || A.b == 256);
+    if (fast64) {
+        DevBuf<unsigned> counter(1);
+        counter.zero();
+        const double* At = (const double*)A.tiles.p;
+        const double* Bt = (const double*)B.tiles.p;
+        bool done = false;
+        if (e.gemm_variant == 0 || A.b == 256) {   // TMA-tiled kernel; falls back to the bulk-copy kernel if the driver refuses the map
+            if (A.b == 64) done = launch_gemm_f64_tma<64, 64, 64>(tA, tB, A, B, tl.ab.p, tl.begin.p, nn, tile_list, counter.p, (double*)ct);
+            else if (A.b == 32) done = launch_gemm_f64_tma<32, 32, 32>(tA, tB, A, B, tl.ab.p, tl.begin.p, nn, tile_list, counter.p, (double*)ct);
+            else if (A.b == 128) done = launch_gemm_f64_tma<128, 128, 32>(tA, tB, A, B, tl.ab.p, tl.begin.p, nn, tile_list, counter.p, (double*)ct);
+            else done = launch_gemm_f64_tma<256, 128, 32>(tA, tB, A, B, tl.ab.p, tl.begin.p, nn, tile_list, counter.p, (double*)ct);
+            e.last_gemm_kernel = done ? 1 : 2;
+        }
+        if (!done && A.b == 256) throw Error(HBSM_E_CUDA, "hbsm_b200: the driver refused the tensor map for 256-leaves");
+        if (!done) {
+            if (A.b == 64) launch_gemm_f64<64, 64>(tA, tB, At, Bt, tl.ab.p, tl.begin.p, nn, tile_list, counter.p, (double*)ct);
+            else if (A.b == 32) launch_gemm_f64<32, 32>(tA, tB, At, Bt, tl.ab.p, tl.begin.p, nn, tile_list, counter.p, (double*)ct);
+            else launch_gemm_f64<128, 32>(tA, tB, At, Bt, tl.ab.p, tl.begin.p, nn, tile_list, counter.p, (double*)ct);
+            e.last_gemm_kernel = 2;
+        }
+        return;   // `counter` is released in stream order
+    }
+    bool done = false;
+    if (A.dtype == HBSM_F32 && e.gemm_variant != 1) {   // fp32: split-TF32 on tcgen05 (gemm_f32.cu) for b in {32,64,128,256}
+        DevBuf<unsigned> counter(1);
+        counter.zero();
+        done = launch_gemm_f32_tc(A, tA, B, tB, tl.ab.p, tl.begin.p, nn, tile_list, counter.p, (float*)ct);
+        if (done) e.last_gemm_kernel = 3;
+    }
+    if (!done) {
+        if (A.dtype == HBSM_F64) {
+            auto kfn = k_gemm_generic<double>;
+            HB_LAUNCH(kfn, nn, 256, 0, (const double*)A.tiles.p, (const double*)B.tiles.p, tl.ab.p, tl.begin.p, tile_list, A.b,
+                      tA ? 1 : 0, tB ? 1 : 0, (double*)ct);
+        } else {
+            auto kfn = k_gemm_generic<float>;
+            HB_LAUNCH(kfn, nn, 256, 0, (const float*)A.tiles.p, (const float*)B.tiles.p, tl.ab.p, tl.begin.p, tile_list, A.b,
+                      tA ? 1 : 0, tB ? 1 : 0, (float*)ct);
+        }
+        e.last_gemm_kernel = 0;
+    }
+}
+
+// a product between op_product_begin and op_product_finish (one at a time: the engine has one stream)
+struct PendingProduct {
+    bool active = false;
+    const Matrix* A = nullptr; const Matrix* B = nullptr; Matrix* C = nullptr;
+    bool tA = false, tB = false;
+    TaskList tl;
+    DevBuf<char> ct;
+    DevBuf<uint32_t> later;      // C tiles whose products read halo tiles: computed by finish
+    size_t n_later = 0;
+    uint64_t launches0 = 0;
+    EventTimer t_total, t_norm, t_index, t_task, t_gemm, t_gemm2;
+};
+PendingProduct& pending() {
+    static PendingProduct p;
+    return p;
+}
+
+}  // namespace
+
+void op_product_begin(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, const ProductOpts& o, bool defer_halo_tiles) {
+    ensure_engine();   // before pending(): its event timers must be created on the engine's device
+    PendingProduct& P = pending();
+    if (P.active) throw Error(HBSM_E_ARG, "hbsm_b200: a product is already in flight (finish it first)");
     int AM = 0, BN = 0;
     check_operands(A, tA, B, tB, C, o.spamm, AM, BN);
-    ensure_engine();
     Engine& e = engine();
-    hbsm_stage_times st{};
-    const uint64_t launches0 = e.launches;
-    EventTimer t_total, t_norm, t_index, t_task, t_gemm;
-    t_total.start();
+    P.launches0 = e.launches;
+    P.t_total.start();
     C.dtype = A.dtype;
     C.b = A.b;
     C.resize(AM, BN);
     const int kbits = coord_bits(A, B, AM, BN, A.b);
     if (3 * kbits > 64) throw Error(HBSM_E_ARG, "hbsm_b200: block grid too deep for 64-bit task keys (depth > 21)");
 
-    t_norm.start();
+    P.t_norm.start();
     if (o.spamm && !o.updated) {   // the reference's updated=false path is a use-after-free (H:6294-6307): refresh instead
         update_norms(const_cast<Matrix&>(A));
         if (&B != &A) update_norms(const_cast<Matrix&>(B));
     }
-    t_norm.stop();
-    t_index.start();
+    P.t_norm.stop();
+    P.t_index.start();
     line_index(A, tA);
     line_index(B, tB, true);
-    t_index.stop();
+    P.t_index.stop();
 
-    t_task.start();
-    TaskList tl;
-    build_tasks(A, tA, B, tB, o, kbits, tl, false);
-    t_task.stop();
-
-    t_gemm.start();
-    if (tl.n_products > 0) {
-        const size_t nct = tl.n_ctiles;
-        DevBuf<char> ct(nct * C.tile_bytes());
-        const bool fast64 = A.dtype == HBSM_F64 && e.gemm_variant != 1 && (A.b == 32 || A.b == 64 || A.b == 128 || A.b == 256);
-        if (fast64) {
-            DevBuf<unsigned> counter(1);
-            counter.zero();
-            const double* At = (const double*)A.tiles.p;
-            const double* Bt = (const double*)B.tiles.p;
-            bool done = false;
-            if (e.gemm_variant == 0 || A.b == 256) {   // TMA-tiled kernel; falls back to the bulk-copy kernel if the driver refuses the map
-                if (A.b == 64) done = launch_gemm_f64_tma<64, 64, 64>(tA, tB, A, B, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
-                else if (A.b == 32) done = launch_gemm_f64_tma<32, 32, 32>(tA, tB, A, B, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
-                else if (A.b == 128) done = launch_gemm_f64_tma<128, 128, 32>(tA, tB, A, B, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
-                else done = launch_gemm_f64_tma<256, 128, 32>(tA, tB, A, B, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
-                e.last_gemm_kernel = done ? 1 : 2;
-            }
-            if (!done && A.b == 256) throw Error(HBSM_E_CUDA, "hbsm_b200: the driver refused the tensor map for 256-leaves");
-            if (!done) {
-                if (A.b == 64) launch_gemm_f64<64, 64>(tA, tB, At, Bt, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
-                else if (A.b == 32) launch_gemm_f64<32, 32>(tA, tB, At, Bt, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
-                else launch_gemm_f64<128, 32>(tA, tB, At, Bt, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (double*)ct.p);
-                e.last_gemm_kernel = 2;
-            }
-            t_gemm.stop();   // `counter` is released in stream order
-        } else {
-            bool done = false;
-            if (A.dtype == HBSM_F32 && e.gemm_variant != 1) {   // fp32: 3xTF32 on tcgen05 (gemm_f32.cu) for b in {32,64,128,256}
-                DevBuf<unsigned> counter(1);
-                counter.zero();
-                done = launch_gemm_f32_tc(A, tA, B, tB, tl.ab.p, tl.begin.p, (uint32_t)nct, counter.p, (float*)ct.p);
-                if (done) e.last_gemm_kernel = 3;
-            }
-            if (!done) {
-                if (A.dtype == HBSM_F64) {
-                    auto kfn = k_gemm_generic<double>;
-                    HB_LAUNCH(kfn, (unsigned)nct, 256, 0, (const double*)A.tiles.p, (const double*)B.tiles.p, tl.ab.p, tl.begin.p,
-                              A.b, tA ? 1 : 0, tB ? 1 : 0, (double*)ct.p);
-                } else {
-                    auto kfn = k_gemm_generic<float>;
-                    HB_LAUNCH(kfn, (unsigned)nct, 256, 0, (const float*)A.tiles.p, (const float*)B.tiles.p, tl.ab.p, tl.begin.p,
-                              A.b, tA ? 1 : 0, tB ? 1 : 0, (float*)ct.p);
-                }
-                e.last_gemm_kernel = 0;
-            }
-            t_gemm.stop();
-        }
-        C.set_table(std::move(tl.ckeys), std::move(ct), nct);
-        C.task_begin = std::move(tl.begin);
-        C.task_k = std::move(tl.task_k);
-        C.n_tasks = tl.n_products;
-    } else {
-        t_gemm.stop();
+    P.t_task.start();
+    P.tl = TaskList();
+    build_tasks(A, tA, B, tB, o, kbits, P.tl, false);
+    P.n_later = 0;
+    DevBuf<uint32_t> first;
+    size_t n_first = P.tl.n_ctiles;
+    const bool split = defer_halo_tiles && B.n_halo > 0 && P.tl.n_products > 0;
+    if (split) {   // C tiles that only read B's own tiles can start now; the others wait for the halo tiles
+        DevBuf<uint32_t> own(P.tl.n_ctiles), halo(P.tl.n_ctiles);
+        HB_LAUNCH(k_classify_ctiles, blocks_for(P.tl.n_ctiles, 256), 256, 0, P.tl.ab.p, P.tl.begin.p, P.tl.n_ctiles, (uint32_t)B.L,
+                  own.p, halo.p);
+        n_first = list_of(own, P.tl.n_ctiles, first);
+        P.n_later = list_of(halo, P.tl.n_ctiles, P.later);
     }
-    t_total.stop();
+    P.t_task.stop();
+
+    P.t_gemm.start();
+    if (P.tl.n_products > 0) {
+        P.ct.alloc(P.tl.n_ctiles * C.tile_bytes());
+        launch_leaf_gemm(A, tA, B, tB, P.tl, split ? first.p : nullptr, n_first, P.ct.p);
+    }
+    P.t_gemm.stop();
+    P.A = &A; P.B = &B; P.C = &C; P.tA = tA; P.tB = tB;
+    P.active = true;
+}
+
+void op_product_finish(Matrix& C, cudaEvent_t wait_for, size_t* n_mults, size_t* n_blocks) {
+    PendingProduct& P = pending();
+    if (!P.active || P.C != &C) throw Error(HBSM_E_ARG, "hbsm_b200: product_finish without a matching product_begin");
+    Engine& e = engine();
+    P.active = false;
+    if (wait_for) HB_CUDA(cudaStreamWaitEvent(e.stream, wait_for, 0));   // e.g. the NCCL transfer of the halo tiles
+    P.t_gemm2.start();
+    if (P.n_later > 0) launch_leaf_gemm(*P.A, P.tA, *P.B, P.tB, P.tl, P.later.p, P.n_later, P.ct.p);
+    P.t_gemm2.stop();
+    if (P.tl.n_products > 0) {
+        const size_t nct = P.tl.n_ctiles;
+        C.set_table(std::move(P.tl.ckeys), std::move(P.ct), nct);
+        C.task_begin = std::move(P.tl.begin);
+        C.task_k = std::move(P.tl.task_k);
+        C.n_tasks = P.tl.n_products;
+    }
+    P.t_total.stop();
     sync_stream();
-    C.n_mults = tl.n_products;   // H:2194 / H:3984
-    if (n_mults) *n_mults = tl.n_products;
+    P.later.release();
+    C.n_mults = P.tl.n_products;   // H:2194 / H:3984
+    if (n_mults) *n_mults = P.tl.n_products;
     if (n_blocks) *n_blocks = C.L;   // get_n_blocks(), H:7311
-    st.norms_ms = t_norm.ms();
-    st.index_ms = t_index.ms();
-    st.tasklist_ms = t_task.ms();
-    st.gemm_ms = t_gemm.ms();
-    st.total_ms = t_total.ms();
-    st.n_candidates = tl.n_candidates;
-    st.n_products = tl.n_products;
-    st.n_ctiles = tl.n_ctiles;
-    st.gpu_launches = e.launches - launches0;
+    hbsm_stage_times st{};
+    st.norms_ms = P.t_norm.ms();
+    st.index_ms = P.t_index.ms();
+    st.tasklist_ms = P.t_task.ms();
+    st.gemm_ms = P.t_gemm.ms() + P.t_gemm2.ms();
+    st.total_ms = P.t_total.ms();
+    st.n_candidates = P.tl.n_candidates;
+    st.n_products = P.tl.n_products;
+    st.n_ctiles = P.tl.n_ctiles;
+    st.gpu_launches = e.launches - P.launches0;
     st.gemm_kernel = (uint64_t)e.last_gemm_kernel;
     e.last = st;
+    P.tl = TaskList();
+}
+
+void op_product_abort() {
+    PendingProduct& P = pending();
+    if (!P.active) return;
+    P.active = false;
+    cudaStreamSynchronize(engine().stream);
+    P.tl = TaskList(); P.ct.release(); P.later.release();
+}
+
+void op_product(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, const ProductOpts& o, size_t* n_mults,
+                size_t* n_blocks) {
+    op_product_begin(A, tA, B, tB, C, o, false);
+    op_product_finish(C, nullptr, n_mults, n_blocks);
 }
 
 }  // namespace hbsm_b200

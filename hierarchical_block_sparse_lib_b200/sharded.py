@@ -387,6 +387,92 @@ def publish(B_loc, group=None):
     return table
 
 
+def _sharded_product_overlapped(A_loc, tA, B_loc, tB, spamm, tau, group, timers, table):
+    """Published-table protocol with the tile transfer hidden behind the leaf GEMMs that need no remote tile:
+
+      engine stream : request, mask, recv list | halo keys+norms from the table | task list | GEMM(own-only C tiles) ...... GEMM(rest)
+      comm stream   :            a2a(request masks) ............ send list, pack, a2a(tiles -> halo tail) --event--^
+
+    The task list needs only keys and norms of the halo tiles, and those are known locally from the published table."""
+    from . import _capi
+    from .matrix import HierarchicalBlockSparseMatrix as H
+    Lc = _capi.lib()
+    world = dist.get_world_size(group); rank = dist.get_rank(group)
+    grid_side = 1 << max(A_loc.expected_depth(), B_loc.expected_depth())
+    ext = torch.cuda.ExternalStream(int(Lc.hbsm_stream() or 0))
+    comm = getattr(sharded_product, "_comm_stream", None)
+    if comm is None:
+        comm = torch.cuda.Stream()
+        sharded_product._comm_stream = comm
+    tr = _Trace(timers.setdefault("trace", {}) if timers is not None else None)
+    t0 = time.perf_counter()
+    k_all = table.k_of(bool(tB))
+    lo_r, hi_r = table.offsets[rank], table.offsets[rank + 1]
+    L_r = table.counts[rank]; n_all = table.offsets[-1]
+    dt_code = _capi.HBSM_F64 if table.norms_all.dtype == torch.float64 else _capi.HBSM_F32
+    with torch.cuda.stream(ext):
+        bk, bn, bt = device_views(B_loc)
+        if bk.numel() != L_r:
+            raise RuntimeError("sharded_product: the published table of B is stale (B changed after publish())")
+        dev = bn.device
+        thr = torch.empty((grid_side,), dtype=bn.dtype, device=dev)
+        _capi.check(Lc.hbsm_halo_request(A_loc._h, int(bool(tA)), C.c_void_p(thr.data_ptr())))
+        need_u8 = torch.empty((max(n_all, 1),), dtype=torch.uint8, device=dev)
+        _capi.check(Lc.hbsm_halo_mask(dt_code, C.c_void_p(thr.data_ptr()), C.c_void_p(k_all.data_ptr()), C.c_void_p(table.norms_all.data_ptr()),
+                                      n_all, lo_r, hi_r, int(bool(spamm)), float(tau), C.c_void_p(need_u8.data_ptr())))
+        need_u8 = need_u8[:n_all]
+        ev_mask = torch.cuda.Event(); ev_mask.record(ext)
+    with torch.cuda.stream(comm):          # round 1 goes out while the engine stream keeps planning
+        comm.wait_event(ev_mask)
+        asked = torch.empty((world * L_r,), dtype=torch.uint8, device=dev)
+        dist.all_to_all_single(asked, need_u8, [L_r] * world, table.counts, group=group)
+    with torch.cuda.stream(ext):
+        recv_idx = torch.empty((max(n_all, 1),), dtype=torch.int64, device=dev)
+        e2 = (C.c_size_t * (world + 1))(*table.offsets); c2 = (C.c_size_t * world)()
+        _capi.check(Lc.hbsm_compact_flags(C.c_void_p(need_u8.data_ptr()), n_all, world + 1, e2, 0, C.c_void_p(recv_idx.data_ptr()), c2))
+        recv_counts = [int(c) for c in c2]
+        n_in = sum(recv_counts)
+        recv_idx = recv_idx[:n_in]
+        tiles_in = bt[:0]
+        if n_in:
+            cap = getattr(B_loc, "_halo_cap", 0)
+            if n_in > cap:
+                cap = max(n_in + n_in // 4, 64)
+                B_loc._halo_cap = cap
+            kt, nt, tt = _tail_views(B_loc, cap)
+            bk, bn, bt = device_views(B_loc)          # a growth moved the arrays
+            torch.index_select(table.keys_all, 0, recv_idx, out=kt[:n_in])
+            torch.index_select(table.norms_all, 0, recv_idx, out=nt[:n_in])
+            tiles_in = tt[:n_in]
+        ext.synchronize()
+    tr.mark("plan")
+    _capi.check(Lc.hbsm_halo_commit(B_loc._h, n_in))       # keys + norms valid; tiles arrive below
+    Cm = H(A_loc.dtype)
+    ok = False
+    try:
+        _capi.check(Lc.hbsm_product_begin(A_loc._h, int(bool(tA)), B_loc._h, int(bool(tB)), Cm._h, int(bool(spamm)), float(tau), 1, 1))
+        t1 = time.perf_counter()
+        with torch.cuda.stream(comm):
+            nz = torch.nonzero(asked.view(world, L_r), as_tuple=False)       # syncs the comm stream only
+            send_counts = [int(c) for c in torch.bincount(nz[:, 0], minlength=world).tolist()]
+            tiles_out = bt.index_select(0, nz[:, 1].contiguous())
+            dist.all_to_all_single(tiles_in, tiles_out, recv_counts, send_counts, group=group)
+            ev_tiles = torch.cuda.Event(); ev_tiles.record(comm)
+        nm = C.c_size_t(0); nb = C.c_size_t(0)
+        _capi.check(Lc.hbsm_product_finish(Cm._h, C.c_void_p(ev_tiles.cuda_event), C.byref(nm), C.byref(nb)))
+        ok = True
+    finally:
+        if not ok:
+            torch.cuda.synchronize()
+        _capi.check(Lc.hbsm_halo_commit(B_loc._h, 0))
+    tr.mark("engine_product")
+    if timers is not None:
+        timers["plan_s"] = t1 - t0
+        timers["sent_tiles"] = sum(send_counts)
+        timers["recv_tiles"] = n_in
+    return Cm, nm.value, nb.value
+
+
 def sharded_product(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, group=None, timers=None):
     """C_r = op(A)_r * op(B): A_loc / B_loc are this rank's engine matrices (full logical dims, only the slab's tiles;
     norms refreshed).  Remote op(B) tiles are received straight into B_loc's halo tail (hbsm_halo_reserve/commit), the
@@ -394,6 +480,10 @@ def sharded_product(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, group=None, time
     self-contained three-round one.  Returns (C_loc, n_mults_local, n_blocks_local)."""
     from . import _capi
     from .matrix import HierarchicalBlockSparseMatrix as H
+    table = getattr(B_loc, "_published", None)
+    if (table is not None and os.environ.get("HBSM_SHARD_OVERLAP", "1") == "1"
+            and os.environ.get("HBSM_SHARD_TORCH_PLAN", "0") != "1"):
+        return _sharded_product_overlapped(A_loc, tA, B_loc, tB, spamm, tau, group, timers, table)
     grid_side = 1 << max(A_loc.expected_depth(), B_loc.expected_depth())
     ext = torch.cuda.ExternalStream(int(_capi.lib().hbsm_stream() or 0))
     with torch.cuda.stream(ext):

@@ -94,6 +94,14 @@ int hbsm_multiply(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C,
                   size_t* n_block_multiplies, size_t* n_resizes);
 int hbsm_spamm(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, double tau, int updated,
                size_t* n_block_multiplies, size_t* n_resizes);
+/* The same product in two calls, for callers that overlap a transfer with it (multi-GPU): begin builds the task list and
+ * launches the leaf GEMMs of every C tile that reads only B's own tiles (defer_halo_tiles != 0 and a halo committed with
+ * hbsm_halo_commit whose keys and norms are valid but whose TILES are still arriving); finish makes the engine stream wait
+ * for `cuda_event_or_null` (a cudaEvent_t recorded after the transfer), computes the remaining C tiles and completes C
+ * exactly as hbsm_multiply / hbsm_spamm would.  One product may be in flight at a time. */
+int hbsm_product_begin(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, int spamm, double tau, int updated,
+                       int defer_halo_tiles);
+int hbsm_product_finish(hbsm_handle C, void* cuda_event_or_null, size_t* n_block_multiplies, size_t* n_resizes);
 int hbsm_worth_to_multiply(hbsm_handle A, int tA, hbsm_handle B, int tB, int* out);             /* H:1873 */
 int hbsm_worth_to_spamm(hbsm_handle A, int tA, hbsm_handle B, int tB, double tau, int* out);    /* H:2006 */
 

@@ -49,7 +49,7 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("torch_plan", ["0", "1", "published"])
+@pytest.mark.parametrize("torch_plan", ["0", "1", "published", "published_no_overlap"])
 def test_sharded_matches_single_gpu(tmp_path, torch_plan):
     import torch
     ngpu = torch.cuda.device_count()
@@ -63,7 +63,8 @@ def test_sharded_matches_single_gpu(tmp_path, torch_plan):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)]
     env = dict(os.environ, HBSM_SHARD_TORCH_PLAN="1" if torch_plan == "1" else "0",
-               HBSM_TEST_PUBLISH="1" if torch_plan == "published" else "0")   # engine kernels (default) or the torch-op plan of the gloo tests
+               HBSM_TEST_PUBLISH="1" if torch_plan.startswith("published") else "0",
+               HBSM_SHARD_OVERLAP="0" if torch_plan == "published_no_overlap" else "1")   # engine kernels (default) or the torch-op plan of the gloo tests
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "sharded ok" in r.stdout
