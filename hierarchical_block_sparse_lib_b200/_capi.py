@@ -72,6 +72,8 @@ SIGNATURES = {
     "hbsm_upper_triangle": (_I, [_H, _H]),
     "hbsm_rescale": (_I, [_H, _H, C.c_double]),
     "hbsm_copy": (_I, [_H, _H]),
+    "hbsm_frob_block_trunc": (_I, [_H, _H, C.c_double, C.POINTER(_I)]),
+    "hbsm_leaf_norms": (_I, [_H, _sz, _P, C.POINTER(_sz)]),
     "hbsm_symm_multiply": (_I, [_H, _I, _H, _I, _H]),
     "hbsm_symm_square": (_I, [_H, _H]),
     "hbsm_symm_rk": (_I, [_H, _I, _H]),

@@ -221,6 +221,23 @@ int hbsm_copy(hbsm_handle C, hbsm_handle A) {
     return guarded([&] { op_copy(M(C), M(A)); });
 }
 
+int hbsm_frob_block_trunc(hbsm_handle A, hbsm_handle C, double trunc_value, int* removed) {
+    return guarded([&] {
+        const bool r = op_trunc(M(A), M(C), trunc_value);
+        if (removed) *removed = r ? 1 : 0;
+    });
+}
+int hbsm_leaf_norms(hbsm_handle h, size_t cap, void* out, size_t* n) {
+    return guarded([&] {
+        Matrix& A = M(h);
+        *n = A.L;
+        if (cap < A.L || A.L == 0) return;
+        DevBuf<char> fresh(A.L * A.esize());
+        compute_leaf_norms(A, fresh.p);
+        HB_CUDA(cudaMemcpyAsync(out, fresh.p, A.L * A.esize(), cudaMemcpyDeviceToHost, engine().stream));
+        sync_stream();
+    });
+}
 int hbsm_symm_multiply(hbsm_handle A, int sA, hbsm_handle B, int sB, hbsm_handle C) {
     return guarded([&] {
         if (!sA && !sB)   // H:3264

@@ -657,6 +657,15 @@ __global__ void k_compact_idx(const uint32_t* __restrict__ flags, const uint64_t
     out[pos[e]] = (int64_t)(modulo ? e % modulo : e);
 }
 
+// frob_block_trunc (H:4904-4943): a subtree is dropped iff its (recomputed) norm^2 < trunc^2.  A node's norm^2 is a sum of
+// non-negative child norm^2 with monotone rounding, so a leaf survives iff its OWN norm^2 >= trunc^2 -- the flat rule.
+__global__ void k_trunc_flags(const void* __restrict__ norms, size_t n, int is_f64, double t2d, float t2f, uint32_t* __restrict__ keep) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool drop = is_f64 ? (reinterpret_cast<const double*>(norms)[i] < t2d) : (reinterpret_cast<const float*>(norms)[i] < t2f);
+    keep[i] = drop ? 0u : 1u;
+}
+
 template <typename F>
 void dispatch(int dtype, F&& f) {
     if (dtype == HBSM_F64) f((double)0);
@@ -1168,6 +1177,45 @@ void op_copy(Matrix& C, const Matrix& A) {   // H:1490
     HB_CUDA(cudaMemcpyAsync(t.p, A.tiles.p, A.L * A.tile_bytes(), cudaMemcpyDeviceToDevice, engine().stream));
     C.set_table(std::move(okeys), std::move(t), A.L);
     sync_stream();
+}
+
+bool op_trunc(const Matrix& A, Matrix& C, double trunc_value) {   // H:4935: C = copy of A without the small subtrees
+    if (&C == &A) throw Error(HBSM_E_ARG, "hbsm_b200: frob_block_trunc: target must not alias the source");
+    ensure_engine();
+    C.clear();
+    if (A.empty()) return false;    // copy of an empty matrix
+    C.dtype = A.dtype;
+    C.b = A.b;
+    C.resize(A.M, A.N);
+    C.n_mults = A.n_mults;
+    C.root_norm_cached = A.vdepth() > 0 ? A.root_norm_cached : 0.0;   // copy() keeps the (now stale) root norm, H:1507-1513
+    if (A.L == 0) return false;
+    if (A.vdepth() == 0) {   // a single leaf has no children to drop
+        HB_CUDA(cudaMemcpyAsync(C.tiles.p, A.tiles.p, A.tile_bytes(), cudaMemcpyDeviceToDevice, engine().stream));
+        sync_stream();
+        return false;
+    }
+    DevBuf<char> fresh(A.L * A.esize());
+    compute_leaf_norms(A, fresh.p);
+    DevBuf<uint32_t> keep(A.L);
+    const float tf = (float)trunc_value;
+    HB_LAUNCH(k_trunc_flags, blocks_for(A.L, 256), 256, 0, (const void*)fresh.p, A.L, A.dtype == HBSM_F64 ? 1 : 0,
+              trunc_value * trunc_value, tf * tf, keep.p);
+    DevBuf<uint64_t> pos;
+    size_t nk = scan_flags(keep, A.L, pos);
+    if (nk == 0) return true;
+    DevBuf<uint64_t> okeys(nk);
+    DevBuf<uint32_t> src(nk);
+    HB_LAUNCH(k_compact_keys, blocks_for(A.L, 256), 256, 0, A.keys.p, A.L, keep.p, pos.p, okeys.p, src.p);
+    DevBuf<char> t(nk * A.tile_bytes());
+    dispatch(A.dtype, [&](auto z) {
+        using T = decltype(z);
+        dim3 grid((unsigned)nk, slices_for(A));
+        HB_LAUNCH(k_copy_tiles<T>, grid, 256, 0, (const T*)A.tiles.p, src.p, okeys.p, A.b, 0, 0, (T)1, (T*)t.p);
+    });
+    C.set_table(std::move(okeys), std::move(t), nk);
+    sync_stream();
+    return nk < A.L;
 }
 
 void sym_expand(const Matrix& A, Matrix& S) {

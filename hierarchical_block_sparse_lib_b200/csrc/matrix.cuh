@@ -93,6 +93,7 @@ void op_transpose(const Matrix& A, Matrix& C);
 void op_upper(const Matrix& A, Matrix& C);
 void op_rescale(Matrix& C, const Matrix& A, double alpha);
 void op_copy(Matrix& C, const Matrix& A);
+bool op_trunc(const Matrix& A, Matrix& C, double trunc_value);   // frob_block_trunc, H:4935; true if something was removed
 void sym_expand(const Matrix& A, Matrix& S);             // S = triu(A) + striu(A)^T as a full matrix
 void mask_diag_upper(Matrix& C);                         // zero the strict lower part of diagonal tiles in place
 void generate_decay(Matrix& A, int n, const double* table, int W, uint64_t seed, bool symmetric, int lo, int hi);

@@ -183,6 +183,12 @@ class HierarchicalBlockSparseMatrix:
     def transpose(A, Cm):
         check(lib().hbsm_transpose(A._h, Cm._h))
 
+    def frob_block_trunc(self, matrix_truncated, trunc_value):
+        """H:4935: matrix_truncated = copy of self without the blocks of Frobenius norm < trunc_value; True if any was removed."""
+        r = C.c_int(0)
+        check(lib().hbsm_frob_block_trunc(self._h, matrix_truncated._h, float(trunc_value), C.byref(r)))
+        return bool(r.value)
+
     # ---- parity / bench hooks ----
     def export_tasks(self):
         """Executed products of the call that produced this matrix, as an (n,3) int64 array of (ci, cj, k),

@@ -16,7 +16,9 @@
 #ifndef HBSM_B200_HIERARCHICAL_BLOCK_SPARSE_MATRIX_H
 #define HBSM_B200_HIERARCHICAL_BLOCK_SPARSE_MATRIX_H
 
+#include <cmath>
 #include <cstddef>
+#include <cstdint>
 #include <iostream>
 #include <stdexcept>
 #include <string>
@@ -193,25 +195,126 @@ public:
     }
     hbsm_handle handle() const { return h_; }
 
+    // ---- host-side utilities around the hot path (SURVEY 8f "next"), built on the calls above ----
+    // add_scaled_identity H:1532: *this = other + alpha * I.  (The reference also writes alpha onto the diagonal of the
+    // zero padding of boundary leaves; that region is invisible through the element API and is left zero here.)
+    void add_scaled_identity(HierarchicalBlockSparseMatrix<Treal> const& other, Treal alpha) {
+        if (other.empty()) throw std::runtime_error("Error in HierarchicalBlockSparseMatrix::add_scaled_identity(): empty matrix as input!");
+        HierarchicalBlockSparseMatrix<Treal> I;
+        I.set_params(other.get_params());
+        const int n = other.get_n_rows() < other.get_n_cols() ? other.get_n_rows() : other.get_n_cols();
+        I.resize(other.get_n_rows(), other.get_n_cols());
+        std::vector<int> idx(n);
+        std::vector<Treal> v(n, alpha);
+        for (int i = 0; i < n; ++i) idx[i] = i;
+        I.assign_from_vectors(idx, idx, v);
+        add(other, I, *this);
+        set_n_block_multiplicaitons(0);
+    }
+
+    // set_to_identity H:3805 (params of A must be set)
+    static void set_to_identity(HierarchicalBlockSparseMatrix<Treal>& A, int nRows) {
+        A.clear();
+        A.resize(nRows, nRows);
+        std::vector<int> idx(nRows);
+        std::vector<Treal> v(nRows, (Treal)1);
+        for (int i = 0; i < nRows; ++i) idx[i] = i;
+        A.assign_from_vectors(idx, idx, v);
+    }
+
+    // get_trace H:3782: leaf diagonals summed in order, quadrants combined as child0 + child3 -- same summation tree here
+    Treal get_trace() const {
+        const int n = get_n_rows() < get_n_cols() ? get_n_rows() : get_n_cols();
+        if (n <= 0) return (Treal)0;
+        std::vector<int> idx(n);
+        for (int i = 0; i < n; ++i) idx[i] = i;
+        std::vector<Treal> d;
+        get_values(idx, idx, d);
+        const int b = get_params().blocksize;
+        long long vsize = b;
+        for (int l = expected_depth(); l > 0; --l) vsize *= 2;
+        return trace_rec(d, 0, vsize, b);
+    }
+
+    // get_nnz_diag_lowest_level H:3843: blocksize^2 per EXISTING diagonal leaf (zeros count, absent leaves do not)
+    size_t get_nnz_diag_lowest_level() const {
+        std::vector<int64_t> bi, bj;
+        leaf_coordinates(bi, bj);
+        const size_t b = (size_t)get_params().blocksize;
+        size_t n = 0;
+        for (size_t i = 0; i < bi.size(); ++i) n += (bi[i] == bj[i]) ? b * b : 0;
+        return n;
+    }
+
+    // get_max_abs_value H:5177
+    Treal get_max_abs_value() const {
+        std::vector<int> r, c;
+        std::vector<Treal> v;
+        get_all_values(r, c, v);
+        Treal m = 0;
+        for (size_t i = 0; i < v.size(); ++i) { Treal a = v[i] < 0 ? -v[i] : v[i]; if (a > m) m = a; }
+        return m;
+    }
+
+    // random_blocks H:3005: nnz_blocks distinct leaf blocks filled with uniform [-1,1) values (matrix must be resized, and
+    // empty of elements: assembly is one-shot, H:793)
+    void random_blocks(size_t nnz_blocks) {
+        const int b = get_params().blocksize, M = get_n_rows(), N = get_n_cols();
+        const int nb1 = M / b + (M % b > 0), nb2 = N / b + (N % b > 0);
+        const size_t total = (size_t)nb1 * nb2;
+        if (nnz_blocks > total) throw std::runtime_error("Error in HierarchicalBlockSparseMatrix::random_blocks():too many blocks!");
+        std::vector<size_t> order(total);
+        for (size_t i = 0; i < total; ++i) order[i] = i;
+        uint64_t state = 0x9E3779B97F4A7C15ull ^ (uint64_t)(uintptr_t)this ^ ((uint64_t)nnz_blocks << 32);
+        for (size_t i = total; i > 1; --i) { size_t j = (size_t)(next_random(state) % i); size_t t = order[i - 1]; order[i - 1] = order[j]; order[j] = t; }
+        std::vector<int> rows, cols;
+        std::vector<Treal> vals;
+        for (size_t k = 0; k < nnz_blocks; ++k) {
+            const int r0 = b * (int)(order[k] % nb1), c0 = b * (int)(order[k] / nb1);
+            for (int j = 0; j < b; ++j)
+                for (int i = 0; i < b; ++i) {
+                    if (r0 + i >= M || c0 + j >= N) continue;
+                    rows.push_back(r0 + i); cols.push_back(c0 + j);
+                    vals.push_back((Treal)(2.0 * ((double)(next_random(state) >> 11) * (1.0 / 9007199254740992.0)) - 1.0));
+                }
+        }
+        assign_from_vectors(rows, cols, vals);
+    }
+
+    // frob_block_trunc H:4935 (device): matrix_truncated = *this without the blocks of Frobenius norm < trunc_value
+    bool frob_block_trunc(HierarchicalBlockSparseMatrix<Treal>& matrix_truncated, Treal trunc_value) const {
+        int removed = 0;
+        detail::check(hbsm_frob_block_trunc(h_, matrix_truncated.h_, (double)trunc_value, &removed));
+        return removed != 0;
+    }
+
+    // get_frob_squared_of_error_matrix H:3863: entry i = norm^2 of the part that truncation at trunc_values[i] would drop,
+    // i.e. the sum over leaves with ||leaf||_F < trunc_values[i], added up the quadtree in child order 0..3
+    void get_frob_squared_of_error_matrix(std::vector<Treal>& frob_squared_of_error_matrix, std::vector<Treal> const& trunc_values) const {
+        std::vector<int64_t> bi, bj;
+        leaf_coordinates(bi, bj);
+        std::vector<Treal> nsq(bi.size());
+        size_t n = 0;
+        if (!bi.empty()) detail::check(hbsm_leaf_norms(h_, nsq.size(), nsq.data(), &n));
+        frob_squared_of_error_matrix.assign(trunc_values.size(), (Treal)0);
+        if (bi.empty()) return;
+        std::vector<uint64_t> key(bi.size());
+        for (size_t i = 0; i < bi.size(); ++i) key[i] = hbsm_morton_encode((uint32_t)bi[i], (uint32_t)bj[i]);
+        for (size_t t = 0; t < trunc_values.size(); ++t)
+            frob_squared_of_error_matrix[t] = error_rec(key, nsq, 0, key.size(), expected_depth(), trunc_values[t]);
+    }
+
     // ---- members outside the multiply / SpAMM / add path (SURVEY 2 "OUT OF SCOPE", 8f "next"): declared, throwing ----
 #define HBSM_B200_NOT_PROVIDED(name) \
     throw std::runtime_error("Error in HierarchicalBlockSparseMatrix<Treal>::" name ": not provided by hbsm_b200 (outside the multiply/SpAMM/add path).")
     size_t get_size() const { HBSM_B200_NOT_PROVIDED("get_size"); }                                            // H:241
     void write_to_buffer(char*, size_t const) const { HBSM_B200_NOT_PROVIDED("write_to_buffer"); }              // H:244
     void assign_from_buffer(const char*, size_t const) { HBSM_B200_NOT_PROVIDED("assign_from_buffer"); }        // H:245
-    void add_scaled_identity(HierarchicalBlockSparseMatrix<Treal> const&, Treal) { HBSM_B200_NOT_PROVIDED("add_scaled_identity"); }   // H:253
     static void inv_chol(HierarchicalBlockSparseMatrix<Treal> const&, HierarchicalBlockSparseMatrix<Treal>&) { HBSM_B200_NOT_PROVIDED("inv_chol"); }   // H:268
     static void adjust_sizes(HierarchicalBlockSparseMatrix<Treal>&, const int, const int) { HBSM_B200_NOT_PROVIDED("adjust_sizes"); }   // H:286
-    Treal get_trace() const { HBSM_B200_NOT_PROVIDED("get_trace"); }                                           // H:288
-    static void set_to_identity(HierarchicalBlockSparseMatrix<Treal>&, int) { HBSM_B200_NOT_PROVIDED("set_to_identity"); }   // H:290
-    size_t get_nnz_diag_lowest_level() const { HBSM_B200_NOT_PROVIDED("get_nnz_diag_lowest_level"); }           // H:293
-    void random_blocks(size_t) { HBSM_B200_NOT_PROVIDED("random_blocks"); }                                     // H:313
-    void get_frob_squared_of_error_matrix(std::vector<Treal>&, std::vector<Treal> const&) const { HBSM_B200_NOT_PROVIDED("get_frob_squared_of_error_matrix"); }   // H:336
-    bool frob_block_trunc(HierarchicalBlockSparseMatrix<Treal>&, Treal) const { HBSM_B200_NOT_PROVIDED("frob_block_trunc"); }   // H:352
     static std::vector<unsigned long int> count_skips(HierarchicalBlockSparseMatrix<Treal> const&, const bool,
                                                       HierarchicalBlockSparseMatrix<Treal> const&, const bool,
                                                       std::vector<Treal> const&, const bool&, const bool&) { HBSM_B200_NOT_PROVIDED("count_skips"); }   // H:405
-    Treal get_max_abs_value() const { HBSM_B200_NOT_PROVIDED("get_max_abs_value"); }                            // H:410
     static std::vector<Treal> get_errors_of_approx_multiplication(HierarchicalBlockSparseMatrix<Treal> const&, const bool,
                                                                   HierarchicalBlockSparseMatrix<Treal> const&, const bool,
                                                                   std::vector<Treal> const&, const bool&, const bool&) { HBSM_B200_NOT_PROVIDED("get_errors_of_approx_multiplication"); }   // H:412
@@ -253,6 +356,47 @@ public:
 
 private:
     hbsm_handle h_;
+
+    static uint64_t next_random(uint64_t& s) {   // splitmix64
+        s += 0x9E3779B97F4A7C15ull;
+        uint64_t z = s;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+    void leaf_coordinates(std::vector<int64_t>& bi, std::vector<int64_t>& bj) const {
+        size_t n = 0;
+        detail::check(hbsm_n_blocks(h_, &n));
+        bi.resize(n); bj.resize(n);
+        if (n) detail::check(hbsm_export_leaves(h_, n, bi.data(), bj.data(), NULL, NULL, &n));
+    }
+    // diagonal d[lo, lo+size) of the virtual matrix (entries past the end are zero padding)
+    static Treal trace_rec(const std::vector<Treal>& d, long long lo, long long size, int b) {
+        if (lo >= (long long)d.size()) return (Treal)0;
+        if (size <= b) {
+            Treal t = 0;
+            for (long long i = lo; i < lo + size && i < (long long)d.size(); ++i) t += d[(size_t)i];
+            return t;
+        }
+        Treal t = 0;
+        t += trace_rec(d, lo, size / 2, b);
+        t += trace_rec(d, lo + size / 2, size / 2, b);
+        return t;
+    }
+    // leaves [lo,hi) of the Morton-sorted table below a node at `level` levels above the leaves
+    static Treal error_rec(const std::vector<uint64_t>& key, const std::vector<Treal>& nsq, size_t lo, size_t hi, int level, Treal trunc) {
+        if (lo >= hi) return (Treal)0;
+        if (level == 0) return (std::sqrt(nsq[lo]) < trunc) ? nsq[lo] : (Treal)0;
+        Treal child[4] = {0, 0, 0, 0};
+        size_t p = lo;
+        for (int q = 0; q < 4; ++q) {
+            size_t e = p;
+            while (e < hi && ((key[e] >> (2 * (level - 1))) & 3u) == (uint64_t)q) ++e;
+            child[q] = error_rec(key, nsq, p, e, level - 1, trunc);
+            p = e;
+        }
+        return child[0] + child[1] + child[2] + child[3];
+    }
 };
 
 }  // namespace hbsm

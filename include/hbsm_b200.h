@@ -112,6 +112,12 @@ int hbsm_upper_triangle(hbsm_handle A, hbsm_handle C);
 int hbsm_rescale(hbsm_handle C, hbsm_handle A, double alpha);
 int hbsm_copy(hbsm_handle C, hbsm_handle A);
 
+/* frob_block_trunc H:4935: C = A without the leaves whose ||.||_F^2 < trunc_value^2 (the hierarchical rule of H:4904
+ * collapses to this flat one); *removed = 1 if any leaf was dropped.  hbsm_leaf_norms: freshly computed leaf ||.||_F^2 in
+ * ascending Morton order (the order of hbsm_export_leaves), independent of the cache; cap = 0 -> count. */
+int hbsm_frob_block_trunc(hbsm_handle A, hbsm_handle C, double trunc_value, int* removed);
+int hbsm_leaf_norms(hbsm_handle h, size_t cap, void* out, size_t* n);
+
 /* ---- symmetric family, exact (symm_multiply H:3244, symm_square H:3563, symm_rk H:3711) ---- */
 int hbsm_symm_multiply(hbsm_handle A, int sA, hbsm_handle B, int sB, hbsm_handle C);
 int hbsm_symm_square(hbsm_handle A, hbsm_handle C);
