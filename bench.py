@@ -281,7 +281,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--n", type=int, default=None, help="override N (development only; the judged run uses the default)")
+    ap.add_argument("--n", "--size", dest="n", type=int, default=None, help="override N (the judged run uses the default); use --size under torchrun")
     ap.add_argument("--lam", type=float, default=None)
     ap.add_argument("--leaf", type=int, default=None, help="override the leaf size (e.g. BASELINE config 4: --n 262144 --leaf 128)")
     args = ap.parse_args()

@@ -74,6 +74,9 @@ SIGNATURES = {
     "hbsm_copy": (_I, [_H, _H]),
     "hbsm_frob_block_trunc": (_I, [_H, _H, C.c_double, C.POINTER(_I)]),
     "hbsm_leaf_norms": (_I, [_H, _sz, _P, C.POINTER(_sz)]),
+    "hbsm_serialized_size": (_I, [_H, C.POINTER(_sz)]),
+    "hbsm_serialize": (_I, [_H, _P, _sz]),
+    "hbsm_deserialize": (_I, [_H, _P, _sz]),
     "hbsm_symm_multiply": (_I, [_H, _I, _H, _I, _H]),
     "hbsm_symm_square": (_I, [_H, _H]),
     "hbsm_symm_rk": (_I, [_H, _I, _H]),

@@ -238,6 +238,15 @@ int hbsm_leaf_norms(hbsm_handle h, size_t cap, void* out, size_t* n) {
         sync_stream();
     });
 }
+int hbsm_serialized_size(hbsm_handle h, size_t* out) {
+    return guarded([&] { *out = serialized_size(M(h)); });
+}
+int hbsm_serialize(hbsm_handle h, char* buffer, size_t capacity) {
+    return guarded([&] { serialize(M(h), buffer, capacity); });
+}
+int hbsm_deserialize(hbsm_handle h, const char* buffer, size_t size) {
+    return guarded([&] { deserialize(M(h), buffer, size); });
+}
 int hbsm_symm_multiply(hbsm_handle A, int sA, hbsm_handle B, int sB, hbsm_handle C) {
     return guarded([&] {
         if (!sA && !sB)   // H:3264

@@ -98,6 +98,11 @@ void sym_expand(const Matrix& A, Matrix& S);             // S = triu(A) + striu(
 void mask_diag_upper(Matrix& C);                         // zero the strict lower part of diagonal tiles in place
 void generate_decay(Matrix& A, int n, const double* table, int W, uint64_t seed, bool symmetric, int lo, int hi);
 
+// ---- serialize.cu: the reference's wire format (H:1124-1487) ----
+size_t serialized_size(const Matrix& A);
+void serialize(const Matrix& A, char* buf, size_t cap);
+void deserialize(Matrix& A, const char* buf, size_t size);
+
 // ---- product.cu ----
 struct ProductOpts {
     bool spamm = false;

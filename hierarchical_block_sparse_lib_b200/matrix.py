@@ -183,6 +183,20 @@ class HierarchicalBlockSparseMatrix:
     def transpose(A, Cm):
         check(lib().hbsm_transpose(A._h, Cm._h))
 
+    def get_size(self):
+        return self._size("hbsm_serialized_size")
+
+    def write_to_buffer(self):
+        """H:1159: the reference's wire format as bytes."""
+        n = self.get_size()
+        buf = np.zeros(n, np.uint8)
+        check(lib().hbsm_serialize(self._h, _ptr(buf), n))
+        return buf.tobytes()
+
+    def assign_from_buffer(self, data):
+        buf = np.frombuffer(bytes(data), np.uint8)
+        check(lib().hbsm_deserialize(self._h, _ptr(buf), len(buf)))
+
     def frob_block_trunc(self, matrix_truncated, trunc_value):
         """H:4935: matrix_truncated = copy of self without the blocks of Frobenius norm < trunc_value; True if any was removed."""
         r = C.c_int(0)

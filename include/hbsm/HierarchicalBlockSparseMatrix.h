@@ -304,12 +304,14 @@ public:
             frob_squared_of_error_matrix[t] = error_rec(key, nsq, 0, key.size(), expected_depth(), trunc_values[t]);
     }
 
+    // wire format of the reference (H:1124-1487), byte-compatible: what the Chunks-and-Tasks runtime ships
+    size_t get_size() const { size_t n = 0; detail::check(hbsm_serialized_size(h_, &n)); return n; }                       // H:241
+    void write_to_buffer(char* dataBuffer, size_t const bufferSize) const { detail::check(hbsm_serialize(h_, dataBuffer, bufferSize)); }   // H:244
+    void assign_from_buffer(const char* dataBuffer, size_t const bufferSize) { detail::check(hbsm_deserialize(h_, dataBuffer, bufferSize)); }   // H:245
+
     // ---- members outside the multiply / SpAMM / add path (SURVEY 2 "OUT OF SCOPE", 8f "next"): declared, throwing ----
 #define HBSM_B200_NOT_PROVIDED(name) \
     throw std::runtime_error("Error in HierarchicalBlockSparseMatrix<Treal>::" name ": not provided by hbsm_b200 (outside the multiply/SpAMM/add path).")
-    size_t get_size() const { HBSM_B200_NOT_PROVIDED("get_size"); }                                            // H:241
-    void write_to_buffer(char*, size_t const) const { HBSM_B200_NOT_PROVIDED("write_to_buffer"); }              // H:244
-    void assign_from_buffer(const char*, size_t const) { HBSM_B200_NOT_PROVIDED("assign_from_buffer"); }        // H:245
     static void inv_chol(HierarchicalBlockSparseMatrix<Treal> const&, HierarchicalBlockSparseMatrix<Treal>&) { HBSM_B200_NOT_PROVIDED("inv_chol"); }   // H:268
     static void adjust_sizes(HierarchicalBlockSparseMatrix<Treal>&, const int, const int) { HBSM_B200_NOT_PROVIDED("adjust_sizes"); }   // H:286
     static std::vector<unsigned long int> count_skips(HierarchicalBlockSparseMatrix<Treal> const&, const bool,

@@ -118,6 +118,11 @@ int hbsm_copy(hbsm_handle C, hbsm_handle A);
 int hbsm_frob_block_trunc(hbsm_handle A, hbsm_handle C, double trunc_value, int* removed);
 int hbsm_leaf_norms(hbsm_handle h, size_t cap, void* out, size_t* n);
 
+/* ---- wire format (get_size H:1124, write_to_buffer H:1159, assign_from_buffer H:1348): byte-compatible ---- */
+int hbsm_serialized_size(hbsm_handle h, size_t* out);
+int hbsm_serialize(hbsm_handle h, char* buffer, size_t capacity);
+int hbsm_deserialize(hbsm_handle h, const char* buffer, size_t size);
+
 /* ---- symmetric family, exact (symm_multiply H:3244, symm_square H:3563, symm_rk H:3711) ---- */
 int hbsm_symm_multiply(hbsm_handle A, int sA, hbsm_handle B, int sB, hbsm_handle C);
 int hbsm_symm_square(hbsm_handle A, hbsm_handle C);

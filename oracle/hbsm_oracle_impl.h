@@ -360,6 +360,36 @@ int F(orc_copy)(F(Mat)* C, const F(Mat)* A) {
     return 0;
 }
 
+/* frob_block_trunc H:4904-4943: copy, then drop every child subtree whose recomputed norm^2 < trunc^2 (the root itself is
+ * never tested), then drop inner nodes left without children */
+static int F(trunc_rec)(F(Node)* x, int b, REAL t2) {
+    int removed = 0;
+    for (int q = 0; q < 4; ++q)
+        if (x->ch[q]) {
+            if (F(frob_rec)(x->ch[q], b) < t2) { F(node_free)(x->ch[q]); x->ch[q] = NULL; removed = 1; }
+            else if (!x->ch[q]->leaf) removed |= F(trunc_rec)(x->ch[q], b, t2);
+        }
+    for (int q = 0; q < 4; ++q)
+        if (x->ch[q] && !x->ch[q]->leaf) {
+            int any = 0;
+            for (int r = 0; r < 4; ++r) any |= x->ch[q]->ch[r] != NULL;
+            if (!any) { F(node_free)(x->ch[q]); x->ch[q] = NULL; }
+        }
+    return removed;
+}
+int F(orc_trunc)(const F(Mat)* A, F(Mat)* C, REAL trunc, int* removed) {
+    *removed = 0;
+    int rc = F(orc_copy)(C, A);
+    if (rc) return rc;
+    if (C->root && !C->root->leaf) {
+        *removed = F(trunc_rec)(C->root, C->b, trunc * trunc);
+        int any = 0;
+        for (int q = 0; q < 4; ++q) any |= C->root->ch[q] != NULL;
+        if (!any) { F(node_free)(C->root); C->root = NULL; }   /* flat engine: sized, childless */
+    }
+    return 0;
+}
+
 /* ---- add H:1644-1722: structure union; both present -> fl(a+b), one present -> that subtree ---- */
 static F(Node)* F(add_rec)(const F(Node)* a, const F(Node)* b, int bs) {
     if (!a && !b) return NULL;

@@ -164,6 +164,14 @@ class OrcMatrix(_Base):
         return Cm
 
     @classmethod
+    def trunc(cls, A, trunc_value):
+        Cm = cls(A.b, A.dtype)
+        r = C.c_int(0)
+        rc = A._f("trunc")(A.h, Cm.h, _CT[A.dtype](trunc_value), C.byref(r))
+        if rc: raise RuntimeError("orc_trunc rc=%d" % rc)
+        return Cm, bool(r.value)
+
+    @classmethod
     def _unary(cls, name, A, *extra):
         Cm = cls(A.b, A.dtype)
         rc = A._f(name)(A.h, *extra, Cm.h) if name not in ("rescale",) else None
@@ -241,6 +249,16 @@ class RefMatrix(_Base):
     def n_mults(self): return self._f("n_mults", _L)(self.h)
     def update(self): self._ck(self._f("update")(self.h), "update")
     def size_bytes(self): return self._f("size_bytes", _L)(self.h)
+
+    def write_to_buffer(self):
+        n = self.size_bytes()
+        buf = np.zeros(n, np.uint8)
+        self._ck(self._f("write_to_buffer")(self.h, _ptr(buf), _L(n)), "write_to_buffer")
+        return buf.tobytes()
+
+    def assign_from_buffer(self, data):
+        buf = np.frombuffer(bytes(data), np.uint8)
+        self._ck(self._f("assign_from_buffer")(self.h, _ptr(buf), _L(len(buf))), "assign_from_buffer")
 
     def frob_sq(self):
         out = _CT[self.dtype](0)
@@ -323,6 +341,13 @@ class RefMatrix(_Base):
     @classmethod
     def copy(cls, A):
         Cm = cls(A.b, A.dtype); A._ck(A._f("copy")(Cm.h, A.h), "copy"); return Cm
+
+    @classmethod
+    def trunc(cls, A, trunc_value):
+        Cm = cls(A.b, A.dtype)
+        r = C.c_int(0)
+        A._ck(A._f("trunc")(A.h, Cm.h, _CT[A.dtype](trunc_value), C.byref(r)), "frob_block_trunc")
+        return Cm, bool(r.value)
 
     @classmethod
     def add(cls, A, B):

@@ -221,6 +221,12 @@ template <class T> struct Api {
         return Mat<T>::worth_to_multiply(Api<T>::M(a), tA, Api<T>::M(b), tB); }                              \
     extern "C" int ref_worth_to_spamm_##SUF(void* a, int tA, void* b, int tB, T tau) {                       \
         return Mat<T>::worth_to_spamm(Api<T>::M(a), tA, Api<T>::M(b), tB, tau); }                            \
+    extern "C" int ref_trunc_##SUF(void* a, void* c, T tau, int* removed) {                                   \
+        GUARD(*removed = Api<T>::M(a).frob_block_trunc(Api<T>::M(c), tau) ? 1 : 0) }                         \
+    extern "C" int ref_write_to_buffer_##SUF(void* h, char* buf, long cap) {                                  \
+        GUARD(Api<T>::M(h).write_to_buffer(buf, (size_t)cap)) }                                              \
+    extern "C" int ref_assign_from_buffer_##SUF(void* h, const char* buf, long n) {                           \
+        GUARD(Api<T>::M(h).assign_from_buffer(buf, (size_t)n)) }                                             \
     extern "C" long ref_size_bytes_##SUF(void* h) { return (long)Api<T>::M(h).get_size(); }
 
 DEFINE_API(d, double)

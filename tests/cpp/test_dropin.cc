@@ -199,6 +199,54 @@ void run() {
         expect(Q, 2, 2, {{11, 11}, {23, 23}});
         REQUIRE(Q.get_depth() == 1);
     }
+    // ---- frob_block_trunc(0.21), TO:746-778 ----
+    {
+        M As, Bs;
+        fill(As, 2, 4, 4, {{1, 2, 0.1, 0.1}, {2, 1, 0.1, 0.1}, {3, 1, 0, 0}, {5, 1, 0, 0.1}});
+        REQUIRE(As.frob_block_trunc(Bs, (T)0.21));
+        expect(Bs, 4, 4, {{1, 2, 0, 0}, {2, 1, 0, 0}, {3, 1, 0, 0}, {5, 1, 0, 0}});
+        REQUIRE(Bs.get_n_blocks() == 2);
+        M Cs;
+        REQUIRE(!As.frob_block_trunc(Cs, (T)0.0));     // nothing to remove
+        REQUIRE(Cs.get_n_blocks() == 4);
+        std::vector<T> errs, taus = {(T)0.05, (T)0.21, (T)100};
+        As.get_frob_squared_of_error_matrix(errs, taus);
+        REQUIRE(errs.size() == 3 && errs[0] == (T)0);
+        REQUIRE(std::fabs((double)errs[1] - 0.05) < 1e-6);   // the two 0.1-blocks: 4*0.01 + 1*0.01
+        REQUIRE(std::fabs((double)errs[2] - (double)As.get_frob_squared()) < 1e-4);
+    }
+    // ---- get_trace / set_to_identity / get_nnz_diag_lowest_level / random_blocks, TO:568-630 ----
+    {
+        M A3; fill(A3, 2, 3, 3, {{2, 3, 5}, {0, 1, 2}, {5, 8, 9}});
+        REQUIRE(A3.get_trace() == (T)12);
+        typename M::Params p; p.blocksize = 2;
+        M I17; I17.set_params(p);
+        M::set_to_identity(I17, 17);
+        REQUIRE(I17.get_trace() == (T)17 && I17.get_nnz() == 17 && I17.get_n_rows() == 17);
+        M U3; fill(U3, 2, 3, 3, {{1, 2, 3}, {0, 6, 4}, {0, 0, 5}});
+        REQUIRE(U3.get_nnz_diag_lowest_level() == 8);
+        REQUIRE(U3.get_max_abs_value() == (T)6);
+        p.blocksize = 3;
+        M X; X.set_params(p); X.resize(6, 6);
+        X.random_blocks(3);
+        REQUIRE(X.get_nnz() == 27 && X.get_n_blocks() == 3);
+    }
+    // ---- add_scaled_identity, TC:233-279 ----
+    {
+        typename M::Params p; p.blocksize = 4;
+        M E, D;
+        E.set_params(p); E.resize(33, 33);
+        std::vector<int> r = {5, 2}, c = {5, 24};
+        std::vector<T> v = {(T)2.2, (T)-2.2};
+        E.assign_from_vectors(r, c, v);
+        D.add_scaled_identity(E, (T)0.5);
+        std::vector<int> qr, qc; std::vector<T> out;
+        for (int i = 0; i < 33; ++i) { qr.push_back(i); qc.push_back(i); }
+        qr.push_back(2); qc.push_back(24); qr.push_back(3); qc.push_back(7);
+        D.get_values(qr, qc, out);
+        for (int i = 0; i < 33; ++i) REQUIRE(out[i] == (i == 5 ? (T)2.2 + (T)0.5 : (T)0.5));
+        REQUIRE(out[33] == (T)-2.2 && out[34] == (T)0 && D.get_nnz() == 34);
+    }
     // ---- value semantics of the drop-in: deep copy ----
     {
         M C1(A);

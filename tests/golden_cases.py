@@ -22,6 +22,8 @@ CASES = [
     dict(id="structure_f32", kind="structure", dtype=np.float32, n=100, b=8, lam=0.2),
     dict(id="symmetric_f64", kind="symmetric", dtype=np.float64, n=72, b=8, lam=0.15),
     dict(id="assembly_f64", kind="assembly", dtype=np.float64, m=29, n=37, b=4),
+    dict(id="wire_format_f64", kind="wire", dtype=np.float64, needs_serialize=True),
+    dict(id="wire_format_f32", kind="wire", dtype=np.float32, needs_serialize=True),
 ]
 
 
@@ -95,6 +97,11 @@ def run_case(K, case):
         out["x_upper"] = np.asarray(K.to_dense(U)); out["x_up_bi"], out["x_up_bj"] = K.leaves(U, False)[:2]
         out["x_rescale"] = np.asarray(K.to_dense(K.rescale(A, -0.37)))
         out["x_copy"] = np.asarray(K.to_dense(K.copy(A)))
+        for ti, tv in enumerate((1e-3, 0.3, 1.0)):          # frob_block_trunc, H:4935 (leaf norms here span 1e-6 .. 3)
+            Tm, removed = K.trunc(B, tv)
+            out["x_trunc%d" % ti] = np.asarray(K.to_dense(Tm))
+            out["x_trunc%d_bi" % ti], out["x_trunc%d_bj" % ti] = K.leaves(Tm, False)[:2]
+            out["x_trunc%d_removed" % ti] = np.array([int(removed), K.n_blocks(Tm)], np.int64)
         out["x_frob"] = np.array([K.frob_sq(A), K.frob_sq(B)], dt)
         out["x_counts"] = np.array([K.n_blocks(A), K.n_blocks(B), K.nnz(A), K.nnz(B)], np.int64)
     elif kind == "symmetric":
@@ -111,6 +118,29 @@ def run_case(K, case):
         out["t_symm_mul_BA"] = np.asarray(K.to_dense(K.symm_multiply(B, False, U, True)))
         out["t_symm_rk_n"] = np.asarray(K.to_dense(K.symm_rk(B, False)))
         out["t_symm_rk_t"] = np.asarray(K.to_dense(K.symm_rk(B, True)))
+    elif kind == "wire":
+        # the reference's serialisation (H:1124-1487), byte for byte: TC:131-133 size 528 (fp64), a product result with
+        # its multiply counter and stale norms, a refreshed matrix, a single-leaf matrix, sized-but-childless, empty
+        dt = case["dtype"]
+        M1 = K.coo(4, 14, 14, [0, 6], [0, 7], np.array([7.7, 1.1], dt), update=False)
+        out["x_bytes_two_leaves_stale"] = np.frombuffer(K.serialize(M1), np.uint8).copy()
+        K.update(M1)
+        out["x_bytes_two_leaves_updated"] = np.frombuffer(K.serialize(M1), np.uint8).copy()
+        rng = np.random.default_rng(5)
+        D = np.round(rng.standard_normal((11, 9)) * 3).astype(dt); D[np.abs(D) < 2] = 0
+        r, c = np.nonzero(D)
+        A = K.coo(3, 11, 9, r, c, D[r, c])
+        P, nm, nb, _ = K.product(A, 1, A, 0)                 # 9x9, integer values: exact in any order
+        out["x_bytes_product"] = np.frombuffer(K.serialize(P), np.uint8).copy()
+        out["x_product_counts"] = np.array([nm, nb], np.int64)
+        out["x_bytes_single_leaf"] = np.frombuffer(K.serialize(K.coo(4, 3, 2, [0, 2], [1, 0], np.array([1.5, -2.0], dt))), np.uint8).copy()
+        out["x_bytes_childless"] = np.frombuffer(K.serialize(K.sized(2, 8, 8)), np.uint8).copy()
+        # round trip through the reader
+        R = K.deserialize(3, out["x_bytes_product"].tobytes())
+        out["x_roundtrip_dense"] = np.asarray(K.to_dense(R))
+        out["x_roundtrip_meta"] = np.array([K.n_mults(R), K.n_blocks(R), K.depth(R), K.shape(R)[0], K.shape(R)[1]], np.int64)
+        R1 = K.deserialize(4, out["x_bytes_two_leaves_updated"].tobytes())
+        out["x_roundtrip_norm"] = np.array([R1.frob_sq_cached() if hasattr(R1, "frob_sq_cached") else R1.get_frob_norm_squared_internal()], dt)
     elif kind == "assembly":
         m, n, b = case["m"], case["n"], case["b"]
         rng = np.random.default_rng(11)

@@ -96,6 +96,10 @@ class OracleBackend:
     def upper(self, A): return self.cls.upper(A)
     def rescale(self, A, alpha): return self.cls.rescale(A, alpha)
     def copy(self, A): return self.cls.copy(A)
+    def trunc(self, A, t): return self.cls.trunc(A, t)
+    def can_serialize(self): return hasattr(self.cls, "write_to_buffer")
+    def serialize(self, A): return A.write_to_buffer()
+    def deserialize(self, b, data): A = self.cls(b, self.dtype); A.assign_from_buffer(data); return A
     def symm_multiply(self, A, sA, B, sB): return self.cls.symm_multiply(A, int(sA), B, int(sB))
     def symm_square(self, A): return self.cls.symm_square(A)
     def symm_rk(self, A, transposed): return self.cls.symm_rk(A, int(transposed))
@@ -154,6 +158,10 @@ class GpuBackend:
     def upper(self, A): Cm = HBSM(self.dtype); A.get_upper_triangle(Cm); return Cm
     def rescale(self, A, alpha): Cm = HBSM(self.dtype); Cm.rescale(A, alpha); return Cm
     def copy(self, A): Cm = HBSM(self.dtype); Cm.copy(A); return Cm
+    def trunc(self, A, t): Cm = HBSM(self.dtype); r = A.frob_block_trunc(Cm, t); return Cm, r
+    def can_serialize(self): return True
+    def serialize(self, A): return A.write_to_buffer()
+    def deserialize(self, b, data): A = HBSM(self.dtype); A.assign_from_buffer(data); return A
     def symm_multiply(self, A, sA, B, sB): return self._out(HBSM.symm_multiply, A, sA, B, sB)
     def symm_square(self, A): return self._out(HBSM.symm_square, A)
     def symm_rk(self, A, transposed): return self._out(HBSM.symm_rk, A, transposed)

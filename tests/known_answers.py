@@ -116,6 +116,13 @@ def run_all(K):
         assert err >= prev
         prev = err
         n += 1
+    # ---- frob_block_trunc(0.21), TO:746-778: the two blocks of 0.1-entries go, and only they ----
+    T, removed = K.trunc(K.dense(2, SP_A, update=False), 0.21)
+    _eq(K.to_dense(T), [[1, 2, 0, 0], [2, 1, 0, 0], [3, 1, 0, 0], [5, 1, 0, 0]], "frob_block_trunc(0.21)"); n += 1
+    assert removed and K.n_blocks(T) == 2
+    T, removed = K.trunc(K.dense(2, SP_A, update=False), 0.0)
+    assert not removed and K.n_blocks(T) == 4
+    n += 1
     # ---- dummy-level squeeze: 1x4 * 4x1 -> 1x1 at b = 2, TO:782-862 ----
     r1 = K.coo(2, 1, 4, [0, 0, 0, 0], [0, 1, 2, 3], [1, 2, 3, 4])
     c1 = K.coo(2, 4, 1, [0, 1, 2, 3], [0, 0, 0, 0], [5, 6, 7, 8])

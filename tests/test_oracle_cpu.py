@@ -39,6 +39,8 @@ def test_oracle_port_matches_golden_fixture(case):
     path = os.path.join(golden_cases.GOLDEN_DIR, case["id"] + ".npz")
     assert os.path.exists(path), "missing fixture %s: run tests/golden/make_golden.py where /root/reference exists" % path
     want = dict(np.load(path))
+    if case.get("needs_serialize"):
+        pytest.skip("the wire format is checked engine-vs-reference (fixture bytes come from the reference's own writer)")
     got = golden_cases.run_case(OracleBackend(po.OrcMatrix, case["dtype"]), case)
     golden_cases.compare(got, want, case)
 
