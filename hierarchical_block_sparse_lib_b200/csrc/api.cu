@@ -192,6 +192,21 @@ int hbsm_product_finish(hbsm_handle C, void* cuda_event_or_null, size_t* n_block
     if (rc != HBSM_OK) op_product_abort();
     return rc;
 }
+int hbsm_product_to_host(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, int spamm, double tau, int updated,
+                         void* host_tiles, size_t cap_tiles, size_t* n_block_multiplies, size_t* n_resizes) {
+    return guarded([&] {
+        ProductOpts o;
+        o.spamm = spamm != 0;
+        o.tau = tau;
+        o.updated = updated != 0;
+        try {
+            op_product_to_host(M(A), tA != 0, M(B), tB != 0, M(C), o, host_tiles, cap_tiles, 8, n_block_multiplies, n_resizes);
+        } catch (...) {
+            op_product_abort();
+            throw;
+        }
+    });
+}
 int hbsm_worth_to_multiply(hbsm_handle A, int tA, hbsm_handle B, int tB, int* out) {
     return guarded([&] { *out = worth_product(M(A), tA != 0, M(B), tB != 0, false, 0.0) ? 1 : 0; });
 }

@@ -770,7 +770,8 @@ PendingProduct& pending() {
 
 }  // namespace
 
-void op_product_begin(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, const ProductOpts& o, bool defer_halo_tiles) {
+void op_product_begin(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, const ProductOpts& o, bool defer_halo_tiles,
+                      bool launch) {
     ensure_engine();   // before pending(): its event timers must be created on the engine's device
     PendingProduct& P = pending();
     if (P.active) throw Error(HBSM_E_ARG, "hbsm_b200: a product is already in flight (finish it first)");
@@ -815,7 +816,7 @@ void op_product_begin(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix
     P.t_gemm.start();
     if (P.tl.n_products > 0) {
         P.ct.alloc(P.tl.n_ctiles * C.tile_bytes());
-        launch_leaf_gemm(A, tA, B, tB, P.tl, split ? first.p : nullptr, n_first, P.ct.p);
+        if (launch) launch_leaf_gemm(A, tA, B, tB, P.tl, split ? first.p : nullptr, n_first, P.ct.p);
     }
     P.t_gemm.stop();
     P.A = &A; P.B = &B; P.C = &C; P.tA = tA; P.tB = tB;
@@ -867,9 +868,50 @@ void op_product_abort() {
     P.tl = TaskList(); P.ct.release(); P.later.release();
 }
 
+// product whose C tiles stream to HOST memory while later tiles are still being computed: the leaf GEMM is launched in
+// `n_chunks` ranges of the (Morton-ordered) C tile list; a copy stream ships each finished range (PCIe D2H overlaps the
+// remaining GEMMs).  `host_tiles` should be pinned; it receives all C tiles in table order.  C is completed as usual.
+void op_product_to_host(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, const ProductOpts& o, void* host_tiles,
+                        size_t cap_tiles, int n_chunks, size_t* n_mults, size_t* n_blocks) {
+    ensure_engine();
+    Engine& e = engine();
+    static cudaStream_t copy_stream = nullptr;
+    if (!copy_stream) HB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    op_product_begin(A, tA, B, tB, C, o, /*defer_halo_tiles=*/false, /*launch=*/false);
+    PendingProduct& P = pending();
+    const size_t nct = P.tl.n_ctiles;
+    bool streamed = false;
+    if (nct > 0 && host_tiles && cap_tiles >= nct) {
+        streamed = true;
+        n_chunks = std::max(1, std::min<int>(n_chunks, (int)((nct + 1023) / 1024)));
+        DevBuf<uint32_t> order(nct);
+        HB_LAUNCH(k_iota, blocks_for(nct, 256), 256, 0, order.p, nct);
+        std::vector<cudaEvent_t> done((size_t)n_chunks);
+        P.t_gemm.start();
+        for (int c = 0; c < n_chunks; ++c) {
+            const size_t lo = nct * (size_t)c / n_chunks, hi = nct * (size_t)(c + 1) / n_chunks;
+            launch_leaf_gemm(A, tA, B, tB, P.tl, order.p + lo, hi - lo, P.ct.p);
+            HB_CUDA(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
+            HB_CUDA(cudaEventRecord(done[c], e.stream));
+            HB_CUDA(cudaStreamWaitEvent(copy_stream, done[c], 0));
+            HB_CUDA(cudaMemcpyAsync((char*)host_tiles + lo * C.tile_bytes(), P.ct.p + lo * C.tile_bytes(), (hi - lo) * C.tile_bytes(),
+                                    cudaMemcpyDeviceToHost, copy_stream));
+        }
+        P.t_gemm.stop();
+        HB_CUDA(cudaStreamSynchronize(copy_stream));
+        for (cudaEvent_t ev : done) cudaEventDestroy(ev);
+    } else if (nct > 0) {
+        P.t_gemm.start();
+        launch_leaf_gemm(A, tA, B, tB, P.tl, nullptr, nct, P.ct.p);
+        P.t_gemm.stop();
+    }
+    op_product_finish(C, nullptr, n_mults, n_blocks);
+    if (!streamed && host_tiles && C.L && cap_tiles < C.L) throw Error(HBSM_E_ARG, "hbsm_b200: host buffer too small for the tiles of C");
+}
+
 void op_product(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, const ProductOpts& o, size_t* n_mults,
                 size_t* n_blocks) {
-    op_product_begin(A, tA, B, tB, C, o, false);
+    op_product_begin(A, tA, B, tB, C, o, false, true);
     op_product_finish(C, nullptr, n_mults, n_blocks);
 }
 

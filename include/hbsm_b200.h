@@ -102,6 +102,12 @@ int hbsm_spamm(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, doub
 int hbsm_product_begin(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, int spamm, double tau, int updated,
                        int defer_halo_tiles);
 int hbsm_product_finish(hbsm_handle C, void* cuda_event_or_null, size_t* n_block_multiplies, size_t* n_resizes);
+/* multiply (spamm = 0) or SpAMM whose result is ALSO delivered to host memory: the leaf GEMMs run in ranges of C's tile
+ * list and every finished range is copied to `host_tiles` (pinned memory recommended; room for cap_tiles tiles, in the
+ * order of hbsm_export_leaves) on a second stream while the next ranges compute.  If cap_tiles is smaller than the number
+ * of C tiles nothing is copied and HBSM_E_ARG is returned after C is complete (read *n_resizes and call again / export). */
+int hbsm_product_to_host(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, int spamm, double tau, int updated,
+                         void* host_tiles, size_t cap_tiles, size_t* n_block_multiplies, size_t* n_resizes);
 int hbsm_worth_to_multiply(hbsm_handle A, int tA, hbsm_handle B, int tB, int* out);             /* H:1873 */
 int hbsm_worth_to_spamm(hbsm_handle A, int tA, hbsm_handle B, int tB, double tau, int* out);    /* H:2006 */
 

@@ -272,3 +272,28 @@ def test_full_size_properties_cfg2():
     _, _, _, c1 = C.export_leaves(norms=False)
     _, _, _, c2 = C2.export_leaves(norms=False)
     assert np.array_equal(2.0 * c1, c2)
+
+
+def test_product_to_host_streams_the_same_tiles():
+    """hbsm_product_to_host: chunked leaf GEMMs + D2H on a second stream deliver exactly the tiles of C."""
+    import ctypes as C
+    import torch
+    from hierarchical_block_sparse_lib_b200 import _capi
+    n, b, lam, tau = 8192, 64, 0.02, 1e-6
+    W = G.decay_width(lam)
+    A = HBSM(np.float64, b); A.generate_decay(n, lam, W, 1); A.update_internal_info()
+    B = HBSM(np.float64, b); B.generate_decay(n, lam, W, 2); B.update_internal_info()
+    Cref = HBSM(np.float64); nm0, nr0 = HBSM.spamm(A, 0, B, 1, Cref, tau, True)
+    _, _, _, want = Cref.export_leaves(norms=False)
+    host = torch.zeros((nr0 + 5, b * b), dtype=torch.float64, pin_memory=True)
+    Cs = HBSM(np.float64)
+    nm = C.c_size_t(0); nr = C.c_size_t(0)
+    _capi.check(_capi.lib().hbsm_product_to_host(A._h, 0, B._h, 1, Cs._h, 1, tau, 1, C.c_void_p(host.data_ptr()), host.shape[0],
+                                                  C.byref(nm), C.byref(nr)))
+    assert (nm.value, nr.value) == (nm0, nr0)
+    assert np.array_equal(host.numpy()[:nr0], want)
+    assert np.array_equal(Cs.export_leaves(norms=False)[3], want)
+    with pytest.raises(hb.HbsmError):       # too small a buffer: C is still completed, the call reports it
+        C2 = HBSM(np.float64)
+        _capi.check(_capi.lib().hbsm_product_to_host(A._h, 0, B._h, 1, C2._h, 1, tau, 1, C.c_void_p(host.data_ptr()), 3,
+                                                      C.byref(nm), C.byref(nr)))
