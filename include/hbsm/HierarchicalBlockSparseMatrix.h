@@ -10,8 +10,8 @@
  *   - Treal must be double or float (the reference's BLAS shim offers exactly these, gblas.h:85-143);
  *   - copy construction / assignment is a deep copy (the reference's implicit copy shares children by shared_ptr);
  *   - spamm(..., updated=false) refreshes the operands' norms (the reference's path is a use-after-free, H:6294-6307);
- *   - the serialisation, estimator, truncation and inv_chol members outside the multiply/SpAMM/add path
- *     (SURVEY 8f "next") are declared and throw "not provided by hbsm_b200".
+ *   - the a-priori estimators (count_skips, get_spamm_errors, ...) and inv_chol are declared and throw
+ *     "not provided by hbsm_b200"; serialisation, truncation and the small utilities are implemented.
  */
 #ifndef HBSM_B200_HIERARCHICAL_BLOCK_SPARSE_MATRIX_H
 #define HBSM_B200_HIERARCHICAL_BLOCK_SPARSE_MATRIX_H
