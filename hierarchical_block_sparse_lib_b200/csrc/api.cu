@@ -262,6 +262,13 @@ int hbsm_serialize(hbsm_handle h, char* buffer, size_t capacity) {
 int hbsm_deserialize(hbsm_handle h, const char* buffer, size_t size) {
     return guarded([&] { deserialize(M(h), buffer, size); });
 }
+int hbsm_count_skips(hbsm_handle A, int tA, hbsm_handle B, int tB, size_t n, const double* taus, int apply_truncation, int apply_spamm,
+                     unsigned long* out) {
+    return guarded([&] { count_skips(M(A), tA != 0, M(B), tB != 0, n, taus, apply_truncation != 0, apply_spamm != 0, out); });
+}
+int hbsm_spamm_errors(hbsm_handle A, int tA, hbsm_handle B, int tB, size_t n, const double* taus, double* out, size_t* n_out) {
+    return guarded([&] { *n_out = spamm_errors(M(A), tA != 0, M(B), tB != 0, n, taus, out); });
+}
 int hbsm_symm_multiply(hbsm_handle A, int sA, hbsm_handle B, int sB, hbsm_handle C) {
     return guarded([&] {
         if (!sA && !sB)   // H:3264

@@ -904,41 +904,34 @@ void compute_leaf_norms(const Matrix& A, void* d_out) {
     }
 }
 
+// Root value of the bottom-up refresh (H:3918-3923 / H:656-662): every node = sum of its existing children in child order
+// 0..3, in Treal.  Only the root is kept (inner-node norms are never consulted: the prune rule is flat), so the
+// L leaf norms (8 B each) are brought to the host and folded there along the Morton order -- one small D2H instead of
+// ~4 launches and a host sync per tree level.
+template <typename T>
+static T fold_norms(const std::vector<uint64_t>& keys, const T* nsq, size_t lo, size_t hi, int level) {
+    if (level == 0) return nsq[lo];
+    T s = 0;
+    size_t p = lo;
+    for (int q = 0; q < 4 && p < hi; ++q) {
+        size_t e = p;
+        while (e < hi && ((keys[e] >> (2 * (level - 1))) & 3u) == (uint64_t)q) ++e;
+        if (e > p) s += fold_norms<T>(keys, nsq, p, e, level - 1);
+        p = e;
+    }
+    return s;
+}
+
 double hierarchical_norm(const Matrix& A, const void* d_leaf_norms) {
     if (A.L == 0) return 0.0;
     ensure_engine();
-    const int depth = A.vdepth();
-    size_t n = A.L;
-    DevBuf<uint64_t> k0(n), k1(n);
-    DevBuf<char> v0(n * A.esize()), v1(n * A.esize());
-    HB_CUDA(cudaMemcpyAsync(k0.p, A.keys.p, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, engine().stream));
-    HB_CUDA(cudaMemcpyAsync(v0.p, d_leaf_norms, n * A.esize(), cudaMemcpyDeviceToDevice, engine().stream));
-    DevBuf<uint32_t> head(n);
-    DevBuf<uint64_t> pos;
-    uint64_t* kin = k0.p; uint64_t* kout = k1.p;
-    char* vin = v0.p; char* vout = v1.p;
-    for (int lvl = 0; lvl < depth; ++lvl) {
-        HB_LAUNCH(k_level_heads, blocks_for(n, 256), 256, 0, kin, n, head.p);
-        size_t nn = scan_flags(head, n, pos);
-        dispatch(A.dtype, [&](auto z) {
-            using T = decltype(z);
-            HB_LAUNCH(k_level_reduce<T>, blocks_for(n, 256), 256, 0, kin, (const T*)vin, n, head.p, pos.p, kout, (T*)vout);
-        });
-        std::swap(kin, kout);
-        std::swap(vin, vout);
-        n = nn;
-    }
-    double res = 0.0;
-    if (A.dtype == HBSM_F64) {
-        HB_CUDA(cudaMemcpyAsync(&res, vin, sizeof(double), cudaMemcpyDeviceToHost, engine().stream));
-        sync_stream();
-    } else {
-        float f = 0;
-        HB_CUDA(cudaMemcpyAsync(&f, vin, sizeof(float), cudaMemcpyDeviceToHost, engine().stream));
-        sync_stream();
-        res = f;
-    }
-    return res;
+    std::vector<uint64_t> keys(A.L);
+    std::vector<char> nsq(A.L * A.esize());
+    HB_CUDA(cudaMemcpyAsync(keys.data(), A.keys.p, A.L * sizeof(uint64_t), cudaMemcpyDeviceToHost, engine().stream));
+    HB_CUDA(cudaMemcpyAsync(nsq.data(), d_leaf_norms, A.L * A.esize(), cudaMemcpyDeviceToHost, engine().stream));
+    sync_stream();
+    if (A.dtype == HBSM_F64) return fold_norms<double>(keys, reinterpret_cast<const double*>(nsq.data()), 0, A.L, A.vdepth());
+    return (double)fold_norms<float>(keys, reinterpret_cast<const float*>(nsq.data()), 0, A.L, A.vdepth());
 }
 
 void update_norms(Matrix& A) {   // H:3905

@@ -103,6 +103,11 @@ size_t serialized_size(const Matrix& A);
 void serialize(const Matrix& A, char* buf, size_t cap);
 void deserialize(Matrix& A, const char* buf, size_t size);
 
+// ---- estimators.cu: a-priori skip counts / error bounds from cached norms (H:4945, H:5236) ----
+void count_skips(const Matrix& A, bool tA, const Matrix& B, bool tB, size_t n, const double* taus, bool apply_truncation, bool apply_spamm,
+                 unsigned long* out);
+size_t spamm_errors(const Matrix& A, bool tA, const Matrix& B, bool tB, size_t n, const double* taus, double* out);   // returns 0 or n
+
 // ---- product.cu ----
 struct ProductOpts {
     bool spamm = false;

@@ -183,6 +183,19 @@ class HierarchicalBlockSparseMatrix:
     def transpose(A, Cm):
         check(lib().hbsm_transpose(A._h, Cm._h))
 
+    @staticmethod
+    def count_skips(A, tA, B, tB, taus, apply_truncation, apply_spamm):
+        t = np.ascontiguousarray(taus, np.float64); out = np.zeros(len(t), np.uint64)
+        check(lib().hbsm_count_skips(A._h, int(bool(tA)), B._h, int(bool(tB)), len(t), _ptr(t), int(bool(apply_truncation)),
+                                     int(bool(apply_spamm)), _ptr(out)))
+        return out
+
+    @staticmethod
+    def get_spamm_errors(A, tA, B, tB, taus):
+        t = np.ascontiguousarray(taus, np.float64); out = np.zeros(len(t), np.float64); n = C.c_size_t(0)
+        check(lib().hbsm_spamm_errors(A._h, int(bool(tA)), B._h, int(bool(tB)), len(t), _ptr(t), _ptr(out), C.byref(n)))
+        return out[:n.value].astype(A.dtype)
+
     def get_size(self):
         return self._size("hbsm_serialized_size")
 

@@ -309,20 +309,43 @@ public:
     void write_to_buffer(char* dataBuffer, size_t const bufferSize) const { detail::check(hbsm_serialize(h_, dataBuffer, bufferSize)); }   // H:244
     void assign_from_buffer(const char* dataBuffer, size_t const bufferSize) { detail::check(hbsm_deserialize(h_, dataBuffer, bufferSize)); }   // H:245
 
+    // a-priori estimators from the cached norms (count_skips H:4945, get_errors_of_approx_multiplication H:5193,
+    // get_spamm_errors H:5236): host recursion over the per-level norm tables inside the engine
+    static std::vector<unsigned long int> count_skips(HierarchicalBlockSparseMatrix<Treal> const& A, const bool tA,
+                                                      HierarchicalBlockSparseMatrix<Treal> const& B, const bool tB,
+                                                      std::vector<Treal> const& taus, const bool& apply_truncation, const bool& apply_spamm) {
+        std::vector<double> t(taus.begin(), taus.end());
+        std::vector<unsigned long int> out(taus.size(), 0);
+        detail::check(hbsm_count_skips(A.h_, tA ? 1 : 0, B.h_, tB ? 1 : 0, t.size(), t.data(), apply_truncation ? 1 : 0, apply_spamm ? 1 : 0, out.data()));
+        return out;
+    }
+    static std::vector<Treal> get_errors_of_approx_multiplication(HierarchicalBlockSparseMatrix<Treal> const& A, const bool tA,
+                                                                  HierarchicalBlockSparseMatrix<Treal> const& B, const bool tB,
+                                                                  std::vector<Treal> const& taus, const bool& apply_truncation, const bool& apply_spamm) {
+        std::vector<unsigned long int> skips = count_skips(A, tA, B, tB, taus, apply_truncation, apply_spamm);
+        std::vector<Treal> errors(skips.size(), (Treal)0);
+        const Treal c1 = A.get_max_abs_value(), c2 = B.get_max_abs_value(), cm = c1 > c2 ? c1 : c2;
+        for (size_t i = 0; i < errors.size(); ++i) {
+            const Treal base = std::sqrt(taus[i] * taus[i] * skips[i]);
+            if (apply_truncation && !apply_spamm) errors[i] = cm * base;
+            else if (!apply_truncation && apply_spamm) errors[i] = base;
+            else if (apply_truncation && apply_spamm) errors[i] = (cm > (Treal)1 ? cm : (Treal)1) * base;
+        }
+        return errors;
+    }
+    static std::vector<Treal> get_spamm_errors(HierarchicalBlockSparseMatrix<Treal> const& A, const bool tA,
+                                               HierarchicalBlockSparseMatrix<Treal> const& B, const bool tB, std::vector<Treal> const& taus) {
+        std::vector<double> t(taus.begin(), taus.end()), out(taus.size(), 0.0);
+        size_t n = 0;
+        detail::check(hbsm_spamm_errors(A.h_, tA ? 1 : 0, B.h_, tB ? 1 : 0, t.size(), t.data(), out.data(), &n));
+        return std::vector<Treal>(out.begin(), out.begin() + n);
+    }
+
     // ---- members outside the multiply / SpAMM / add path (SURVEY 2 "OUT OF SCOPE", 8f "next"): declared, throwing ----
 #define HBSM_B200_NOT_PROVIDED(name) \
     throw std::runtime_error("Error in HierarchicalBlockSparseMatrix<Treal>::" name ": not provided by hbsm_b200 (outside the multiply/SpAMM/add path).")
     static void inv_chol(HierarchicalBlockSparseMatrix<Treal> const&, HierarchicalBlockSparseMatrix<Treal>&) { HBSM_B200_NOT_PROVIDED("inv_chol"); }   // H:268
     static void adjust_sizes(HierarchicalBlockSparseMatrix<Treal>&, const int, const int) { HBSM_B200_NOT_PROVIDED("adjust_sizes"); }   // H:286
-    static std::vector<unsigned long int> count_skips(HierarchicalBlockSparseMatrix<Treal> const&, const bool,
-                                                      HierarchicalBlockSparseMatrix<Treal> const&, const bool,
-                                                      std::vector<Treal> const&, const bool&, const bool&) { HBSM_B200_NOT_PROVIDED("count_skips"); }   // H:405
-    static std::vector<Treal> get_errors_of_approx_multiplication(HierarchicalBlockSparseMatrix<Treal> const&, const bool,
-                                                                  HierarchicalBlockSparseMatrix<Treal> const&, const bool,
-                                                                  std::vector<Treal> const&, const bool&, const bool&) { HBSM_B200_NOT_PROVIDED("get_errors_of_approx_multiplication"); }   // H:412
-    static std::vector<Treal> get_spamm_errors(HierarchicalBlockSparseMatrix<Treal> const&, const bool,
-                                               HierarchicalBlockSparseMatrix<Treal> const&, const bool,
-                                               std::vector<Treal> const&) { HBSM_B200_NOT_PROVIDED("get_spamm_errors"); }   // H:415
 #undef HBSM_B200_NOT_PROVIDED
 
     // ---- the reference's own "dummy function, for compatibility" stubs (H:271, H:317-427): same throwing behaviour ----

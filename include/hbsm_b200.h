@@ -124,6 +124,12 @@ int hbsm_copy(hbsm_handle C, hbsm_handle A);
 int hbsm_frob_block_trunc(hbsm_handle A, hbsm_handle C, double trunc_value, int* removed);
 int hbsm_leaf_norms(hbsm_handle h, size_t cap, void* out, size_t* n);
 
+/* ---- a-priori estimators from the CACHED norms (count_skips H:4945, get_spamm_errors H:5236); taus in double ---- */
+int hbsm_count_skips(hbsm_handle A, int tA, hbsm_handle B, int tB, size_t n, const double* taus, int apply_truncation, int apply_spamm,
+                     unsigned long* out);
+/* *n_out = n, or 0 when the pair has no executable product (the reference returns an empty vector) */
+int hbsm_spamm_errors(hbsm_handle A, int tA, hbsm_handle B, int tB, size_t n, const double* taus, double* out, size_t* n_out);
+
 /* ---- wire format (get_size H:1124, write_to_buffer H:1159, assign_from_buffer H:1348): byte-compatible ---- */
 int hbsm_serialized_size(hbsm_handle h, size_t* out);
 int hbsm_serialize(hbsm_handle h, char* buffer, size_t capacity);

@@ -305,6 +305,20 @@ class RefMatrix(_Base):
         return bi, bj, nrm, t
 
     @classmethod
+    def count_skips(cls, A, tA, B, tB, taus, apply_truncation, apply_spamm):
+        t = np.ascontiguousarray(taus, A.dtype); out = np.zeros(len(t), np.uint64)
+        A._ck(A._f("count_skips")(A.h, C.c_int(tA), B.h, C.c_int(tB), _L(len(t)), _ptr(t), C.c_int(apply_truncation),
+                                  C.c_int(apply_spamm), _ptr(out)), "count_skips")
+        return out
+
+    @classmethod
+    def spamm_errors(cls, A, tA, B, tB, taus):
+        t = np.ascontiguousarray(taus, A.dtype); out = np.zeros(len(t), A.dtype)
+        n = A._f("spamm_errors", _L)(A.h, C.c_int(tA), B.h, C.c_int(tB), _L(len(t)), _ptr(t), _ptr(out))
+        if n < 0: raise RuntimeError(cls.last_error())
+        return out[:n]
+
+    @classmethod
     def task_set(cls, A, tA, B, tB, spamm=False, tau=0.0):
         f = A._f("task_set", _L)
         args = (A.h, C.c_int(tA), B.h, C.c_int(tB), C.c_int(spamm), _CT[A.dtype](tau))

@@ -227,6 +227,17 @@ template <class T> struct Api {
         GUARD(Api<T>::M(h).write_to_buffer(buf, (size_t)cap)) }                                              \
     extern "C" int ref_assign_from_buffer_##SUF(void* h, const char* buf, long n) {                           \
         GUARD(Api<T>::M(h).assign_from_buffer(buf, (size_t)n)) }                                             \
+    extern "C" int ref_count_skips_##SUF(void* a, int tA, void* b, int tB, long n, const T* taus, int tr, int sp,   \
+                                         unsigned long* out) {                                                \
+        GUARD(std::vector<T> t(taus, taus + n);                                                              \
+              std::vector<unsigned long> r = Mat<T>::count_skips(Api<T>::M(a), tA, Api<T>::M(b), tB, t, tr, sp); \
+              for (long i = 0; i < n; ++i) out[i] = r[i]) }                                                  \
+    extern "C" long ref_spamm_errors_##SUF(void* a, int tA, void* b, int tB, long n, const T* taus, T* out) { \
+        try { std::vector<T> t(taus, taus + n);                                                              \
+              std::vector<T> r = Mat<T>::get_spamm_errors(Api<T>::M(a), tA, Api<T>::M(b), tB, t);            \
+              for (size_t i = 0; i < r.size(); ++i) out[i] = r[i];                                           \
+              return (long)r.size(); }                                                                       \
+        catch (const std::exception& e) { g_err = e.what(); return -1; } }                                   \
     extern "C" long ref_size_bytes_##SUF(void* h) { return (long)Api<T>::M(h).get_size(); }
 
 DEFINE_API(d, double)

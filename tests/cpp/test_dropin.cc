@@ -160,6 +160,23 @@ void run() {
         { M P; M::spamm(As, false, Bs, true, P, (T)0.2, true, &nm, &nr); REQUIRE(nm == 6 && nr == 4); }
         { M P; M::spamm(As, true, Bs, false, P, (T)0.2, true, &nm, &nr); REQUIRE(nm == 7 && nr == 4); }
         { M P; M::spamm(As, true, Bs, true, P, (T)0.2, true, &nm, &nr); REQUIRE(nm == 7 && nr == 4); }
+        {   // a-priori skip counts and error bounds, TO:687-723 (reference prints S = 0 1 2 2 2 3 4)
+            std::vector<T> taus = {(T)0.0125, (T)0.025, (T)0.05, (T)0.1, (T)0.2, (T)0.4, (T)0.8};
+            std::vector<unsigned long int> skips = M::count_skips(As, false, Bs, false, taus, false, true);
+            const unsigned long want[7] = {0, 1, 2, 2, 2, 3, 4};
+            for (int i = 0; i < 7; ++i) REQUIRE(skips[i] == want[i]);
+            std::vector<T> bound = M::get_errors_of_approx_multiplication(As, false, Bs, false, taus, false, true);
+            std::vector<T> est = M::get_spamm_errors(As, false, Bs, false, taus);
+            REQUIRE(bound.size() == 7 && est.size() == 7);
+            for (int i = 0; i < 7; ++i) {
+                M approx, exact, minus, err;
+                M::spamm(As, false, Bs, false, approx, taus[i], true);
+                M::spamm(As, false, Bs, false, exact, (T)0.0, true);
+                minus.rescale(exact, (T)-1.0);
+                M::add(approx, minus, err);
+                if (bound[i] > 0) REQUIRE(std::sqrt((double)err.get_frob_squared()) < (double)bound[i]);   // TO:722
+            }
+        }
         REQUIRE(M::worth_to_spamm(As, false, Bs, false, (T)0.2));
         REQUIRE(!M::worth_to_spamm(As, false, Bs, false, (T)1e6));
         // error vs tau = 0 via rescale + add + get_frob_squared (TO:714-723)

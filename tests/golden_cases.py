@@ -22,6 +22,8 @@ CASES = [
     dict(id="structure_f32", kind="structure", dtype=np.float32, n=100, b=8, lam=0.2),
     dict(id="symmetric_f64", kind="symmetric", dtype=np.float64, n=72, b=8, lam=0.15),
     dict(id="assembly_f64", kind="assembly", dtype=np.float64, m=29, n=37, b=4),
+    dict(id="estimators_f64", kind="estimators", dtype=np.float64, needs_serialize=True),
+    dict(id="estimators_f32", kind="estimators", dtype=np.float32, needs_serialize=True),
     dict(id="wire_format_f64", kind="wire", dtype=np.float64, needs_serialize=True),
     dict(id="wire_format_f32", kind="wire", dtype=np.float32, needs_serialize=True),
 ]
@@ -118,6 +120,24 @@ def run_case(K, case):
         out["t_symm_mul_BA"] = np.asarray(K.to_dense(K.symm_multiply(B, False, U, True)))
         out["t_symm_rk_n"] = np.asarray(K.to_dense(K.symm_rk(B, False)))
         out["t_symm_rk_t"] = np.asarray(K.to_dense(K.symm_rk(B, True)))
+    elif kind == "estimators":
+        # count_skips H:4945 / get_spamm_errors H:5236 on the reference's own example (TO:634-702: skips 0 1 2 2 2 3 4) and on
+        # a decay pair with three levels, all four transpositions, the three skip rules
+        dt = case["dtype"]
+        from known_answers import SP_A, SP_B
+        As = K.dense(2, SP_A); Bs = K.dense(2, SP_B)
+        taus = np.array([0.0125, 0.025, 0.05, 0.1, 0.2, 0.4, 0.8], dt)
+        out["x_to_skips_spamm"] = np.asarray(K.count_skips(As, 0, Bs, 0, taus, False, True), np.int64)
+        out["t_to_spamm_errors"] = np.asarray(K.spamm_errors(As, 0, Bs, 0, taus), np.float64)
+        n, b = 96, 8
+        W = G.decay_width(0.25)
+        A = K.coo(b, n, n, *G.decay_coo(n, 0.25, min(W, n - 1), 1, dtype=dt))
+        B = K.coo(b, n, n, *G.decay_coo(n, 0.25, min(W, n - 1), 2, dtype=dt))
+        taus2 = np.array([1e-6, 1e-4, 1e-3, 1e-2, 0.1, 1.0, 10.0], dt)
+        for tA, tB in ((0, 0), (0, 1), (1, 0), (1, 1)):
+            for name, tr, sp in (("spamm", False, True), ("trunc", True, False), ("hybrid", True, True), ("none", False, False)):
+                out["x_skips_%s_%d%d" % (name, tA, tB)] = np.asarray(K.count_skips(A, tA, B, tB, taus2, tr, sp), np.int64)
+            out["t_spamm_errors_%d%d" % (tA, tB)] = np.asarray(K.spamm_errors(A, tA, B, tB, taus2), np.float64)
     elif kind == "wire":
         # the reference's serialisation (H:1124-1487), byte for byte: TC:131-133 size 528 (fp64), a product result with
         # its multiply counter and stale norms, a refreshed matrix, a single-leaf matrix, sized-but-childless, empty

@@ -97,6 +97,9 @@ class OracleBackend:
     def rescale(self, A, alpha): return self.cls.rescale(A, alpha)
     def copy(self, A): return self.cls.copy(A)
     def trunc(self, A, t): return self.cls.trunc(A, t)
+    def can_estimate(self): return hasattr(self.cls, "count_skips")
+    def count_skips(self, A, tA, B, tB, taus, tr, sp): return self.cls.count_skips(A, tA, B, tB, taus, int(tr), int(sp))
+    def spamm_errors(self, A, tA, B, tB, taus): return self.cls.spamm_errors(A, tA, B, tB, taus)
     def can_serialize(self): return hasattr(self.cls, "write_to_buffer")
     def serialize(self, A): return A.write_to_buffer()
     def deserialize(self, b, data): A = self.cls(b, self.dtype); A.assign_from_buffer(data); return A
@@ -159,6 +162,9 @@ class GpuBackend:
     def rescale(self, A, alpha): Cm = HBSM(self.dtype); Cm.rescale(A, alpha); return Cm
     def copy(self, A): Cm = HBSM(self.dtype); Cm.copy(A); return Cm
     def trunc(self, A, t): Cm = HBSM(self.dtype); r = A.frob_block_trunc(Cm, t); return Cm, r
+    def can_estimate(self): return True
+    def count_skips(self, A, tA, B, tB, taus, tr, sp): return HBSM.count_skips(A, tA, B, tB, taus, tr, sp)
+    def spamm_errors(self, A, tA, B, tB, taus): return HBSM.get_spamm_errors(A, tA, B, tB, taus)
     def can_serialize(self): return True
     def serialize(self, A): return A.write_to_buffer()
     def deserialize(self, b, data): A = HBSM(self.dtype); A.assign_from_buffer(data); return A
