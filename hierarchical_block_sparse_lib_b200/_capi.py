@@ -75,6 +75,8 @@ SIGNATURES = {
     "hbsm_copy": (_I, [_H, _H]),
     "hbsm_frob_block_trunc": (_I, [_H, _H, C.c_double, C.POINTER(_I)]),
     "hbsm_leaf_norms": (_I, [_H, _sz, _P, C.POINTER(_sz)]),
+    "hbsm_extract_quadrant": (_I, [_H, _I, _H, C.POINTER(_I)]),
+    "hbsm_assemble_quadrants": (_I, [_H, _I, _I, _H, _H, _H, _H]),
     "hbsm_count_skips": (_I, [_H, _I, _H, _I, _sz, _P, _I, _I, _P]),
     "hbsm_spamm_errors": (_I, [_H, _I, _H, _I, _sz, _P, _P, C.POINTER(_sz)]),
     "hbsm_serialized_size": (_I, [_H, C.POINTER(_sz)]),

@@ -269,6 +269,18 @@ int hbsm_count_skips(hbsm_handle A, int tA, hbsm_handle B, int tB, size_t n, con
 int hbsm_spamm_errors(hbsm_handle A, int tA, hbsm_handle B, int tB, size_t n, const double* taus, double* out, size_t* n_out) {
     return guarded([&] { *n_out = spamm_errors(M(A), tA != 0, M(B), tB != 0, n, taus, out); });
 }
+int hbsm_extract_quadrant(hbsm_handle A, int q, hbsm_handle C, int* exists) {
+    return guarded([&] {
+        const bool e = op_extract_quadrant(M(A), q, M(C));
+        if (exists) *exists = e ? 1 : 0;
+    });
+}
+int hbsm_assemble_quadrants(hbsm_handle C, int n_rows, int n_cols, hbsm_handle q0, hbsm_handle q1, hbsm_handle q2, hbsm_handle q3) {
+    return guarded([&] {
+        const Matrix* quads[4] = {q0 ? &q0->m : nullptr, q1 ? &q1->m : nullptr, q2 ? &q2->m : nullptr, q3 ? &q3->m : nullptr};
+        op_assemble_quadrants(M(C), n_rows, n_cols, quads);
+    });
+}
 int hbsm_symm_multiply(hbsm_handle A, int sA, hbsm_handle B, int sB, hbsm_handle C) {
     return guarded([&] {
         if (!sA && !sB)   // H:3264

@@ -341,10 +341,20 @@ public:
         return std::vector<Treal>(out.begin(), out.begin() + n);
     }
 
+    // inv_chol H:3110: inverse Cholesky factor Z (upper triangular, Z^T A Z = I) by the reference's block recursion
+    //   Z00 = invchol(A00);  X = -Z00 (Z00^T A01);  Z11 = invchol(A10 X + A11);  Z01 = X Z11
+    // The recursion runs on the host over quadrant matrices; every product / sum in it is the engine's multiply / add /
+    // rescale on the GPU, only the b x b leaf factor (the scalar loop of H:3118-3140) is computed on the host.
+    static void inv_chol(HierarchicalBlockSparseMatrix<Treal> const& A, HierarchicalBlockSparseMatrix<Treal>& Z) {
+        if (!Z.empty()) throw std::runtime_error("Error in HierarchicalBlockSparseMatrix::inv_chol(): non-empty matrix to write result!");
+        if (A.get_n_rows() != A.get_n_cols()) throw std::runtime_error("Error in HierarchicalBlockSparseMatrix::inv_chol(): call for non-square matrix!");
+        Z.set_params(A.get_params());
+        inv_chol_rec(A, Z, A.get_n_rows(), A.get_n_rows());
+    }
+
     // ---- members outside the multiply / SpAMM / add path (SURVEY 2 "OUT OF SCOPE", 8f "next"): declared, throwing ----
 #define HBSM_B200_NOT_PROVIDED(name) \
     throw std::runtime_error("Error in HierarchicalBlockSparseMatrix<Treal>::" name ": not provided by hbsm_b200 (outside the multiply/SpAMM/add path).")
-    static void inv_chol(HierarchicalBlockSparseMatrix<Treal> const&, HierarchicalBlockSparseMatrix<Treal>&) { HBSM_B200_NOT_PROVIDED("inv_chol"); }   // H:268
     static void adjust_sizes(HierarchicalBlockSparseMatrix<Treal>&, const int, const int) { HBSM_B200_NOT_PROVIDED("adjust_sizes"); }   // H:286
 #undef HBSM_B200_NOT_PROVIDED
 
@@ -381,6 +391,82 @@ public:
 
 private:
     hbsm_handle h_;
+
+    typedef HierarchicalBlockSparseMatrix<Treal> Self;
+    bool quadrant(int q, Self& out) const {
+        int e = 0;
+        out.set_params(get_params());
+        detail::check(hbsm_extract_quadrant(h_, q, out.h_, &e));
+        return e != 0;
+    }
+    // A: node of virtual size v (dims = v unless it is the root); `valid` = rows/cols of it inside the real matrix;
+    // Z receives dims (zdim, zdim)
+    static void inv_chol_rec(Self const& A, Self& Z, int zdim, int valid) {
+        const int b = A.get_params().blocksize;
+        if (A.expected_depth() == 0) {   // leaf factor, H:3118-3140
+            Z.resize(zdim, zdim);
+            const int n = valid < b ? valid : b;
+            if (n <= 0) return;
+            std::vector<int> r((size_t)n * n), c((size_t)n * n);
+            for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) { r[(size_t)j * n + i] = i; c[(size_t)j * n + i] = j; }
+            std::vector<Treal> a;
+            A.get_values(r, c, a);                      // a[j*n + i] = A(i,j)
+            std::vector<Treal> z((size_t)n * n, (Treal)0);   // z[col*n + row]
+            for (int i = 0; i < n; ++i) z[(size_t)i * n + i] = (Treal)1;
+            z[0] = std::sqrt(1 / a[0]);
+            for (int i = 1; i < n; ++i) {
+                Treal R;
+                for (int j = 0; j < i; ++j) {
+                    R = 0;
+                    for (int k = 0; k < n; ++k) R += a[(size_t)k * n + j] * z[(size_t)i * n + k];
+                    R *= z[(size_t)j * n + j];
+                    for (int k = 0; k < n; ++k) z[(size_t)i * n + k] -= z[(size_t)j * n + k] * R;
+                }
+                R = 0;
+                for (int k = 0; k < n; ++k) R += a[(size_t)k * n + i] * z[(size_t)i * n + k];
+                R = std::sqrt(1 / R);
+                for (int k = 0; k < n; ++k) z[(size_t)i * n + k] *= R;
+            }
+            Z.assign_from_vectors(r, c, z);
+            return;
+        }
+        long long v = b;
+        for (int l = A.expected_depth(); l > 0; --l) v *= 2;
+        const int half = (int)(v / 2);
+        Self A00, A01, A10, A11;
+        const bool h00 = A.quadrant(0, A00), h10 = A.quadrant(1, A10), h01 = A.quadrant(2, A01), h11 = A.quadrant(3, A11);
+        if (!h00) throw std::runtime_error("Error in HierarchicalBlockSparseMatrix::inv_chol(): smth went wrong since Z_00 is NULL!");
+        Self Z00, Z01, Z11, X;
+        Z00.set_params(A.get_params()); Z01.set_params(A.get_params()); Z11.set_params(A.get_params());
+        inv_chol_rec(A00, Z00, half, valid < half ? valid : half);
+        bool hX = false, hQ = false, hZ11 = false, hZ01 = false;
+        Self Q;
+        if (h01) {
+            Self R, T;
+            multiply(Z00, true, A01, false, R);     // R = Z00^T A01
+            multiply(Z00, false, R, false, T);      // T = Z00 R
+            X.rescale(T, (Treal)-1);                // X = -T
+            hX = true;
+        }
+        if (h10 && hX) {
+            Self Y;
+            multiply(A10, false, X, false, Y);      // Y = A10 X
+            if (h11) add(Y, A11, Q); else Q.copy(Y);
+            hQ = true;
+        } else if (h11) {
+            Q.copy(A11);
+            hQ = true;
+        }
+        if (hQ && valid > half) {
+            inv_chol_rec(Q, Z11, half, valid - half);
+            hZ11 = !Z11.empty() && Z11.get_n_blocks() > 0;
+        }
+        if (hX && hZ11) {
+            multiply(X, false, Z11, false, Z01);    // Z01 = X Z11
+            hZ01 = true;
+        }
+        detail::check(hbsm_assemble_quadrants(Z.h_, zdim, zdim, Z00.h_, NULL, hZ01 ? Z01.h_ : NULL, hZ11 ? Z11.h_ : NULL));
+    }
 
     static uint64_t next_random(uint64_t& s) {   // splitmix64
         s += 0x9E3779B97F4A7C15ull;

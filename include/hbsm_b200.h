@@ -124,6 +124,11 @@ int hbsm_copy(hbsm_handle C, hbsm_handle A);
 int hbsm_frob_block_trunc(hbsm_handle A, hbsm_handle C, double trunc_value, int* removed);
 int hbsm_leaf_norms(hbsm_handle h, size_t cap, void* out, size_t* n);
 
+/* ---- quadrants (the recursion of inv_chol H:3110 runs on the host over these): child q of the root (0=TL 1=BL 2=TR 3=BR,
+ * H:52-56) as its own matrix of the child's virtual size, and the inverse (NULL / empty handle = absent child) ---- */
+int hbsm_extract_quadrant(hbsm_handle A, int q, hbsm_handle C, int* exists);   /* *exists = 0: the child is absent */
+int hbsm_assemble_quadrants(hbsm_handle C, int n_rows, int n_cols, hbsm_handle q0, hbsm_handle q1, hbsm_handle q2, hbsm_handle q3);
+
 /* ---- a-priori estimators from the CACHED norms (count_skips H:4945, get_spamm_errors H:5236); taus in double ---- */
 int hbsm_count_skips(hbsm_handle A, int tA, hbsm_handle B, int tB, size_t n, const double* taus, int apply_truncation, int apply_spamm,
                      unsigned long* out);

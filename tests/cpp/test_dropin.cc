@@ -3,6 +3,7 @@
 // include/hbsm/HierarchicalBlockSparseMatrix.h, i.e. through the C ABI onto the B200.
 // Usage is deliberately that of a reference caller: same includes (via the umbrella header), same type name,
 // same method calls, exact `==` comparison of dense expansions.  Exit code 0 = all passed.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <initializer_list>
@@ -263,6 +264,50 @@ void run() {
         D.get_values(qr, qc, out);
         for (int i = 0; i < 33; ++i) REQUIRE(out[i] == (i == 5 ? (T)2.2 + (T)0.5 : (T)0.5));
         REQUIRE(out[33] == (T)-2.2 && out[34] == (T)0 && D.get_nnz() == 34);
+    }
+    // ---- inv_chol, TO:188-223 (5x5) and TO:527-562 (4x4), both at b = 2, to 1e-10 (fp64) ----
+    {
+        const double tol = sizeof(T) == 8 ? 1e-10 : 2e-6;
+        M A5, Z5;
+        fill(A5, 2, 5, 5, {{5, 0, 1, 0, 0}, {0, 6, 2, 0, 0}, {1, 2, 5, 3, 0}, {0, 0, 3, 8, 0}, {0, 0, 0, 0, 7}});
+        M::inv_chol(A5, Z5);
+        const double z5[5][5] = {{0.447213595499958, 0, -0.098373875367593, 0.060157954894827, 0},
+                                 {0, 0.408248290463863, -0.163956458945988, 0.100263258158045, 0},
+                                 {0, 0, 0.491869376837965, -0.300789774474136, 0},
+                                 {0, 0, 0, 0.414421467053253, 0},
+                                 {0, 0, 0, 0, 0.377964473009227}};
+        std::vector<double> d5 = dense(Z5);
+        REQUIRE(Z5.get_n_rows() == 5 && Z5.get_n_cols() == 5);
+        for (int i = 0; i < 5; ++i) for (int j = 0; j < 5; ++j) REQUIRE(std::fabs(d5[i * 5 + j] - z5[i][j]) <= tol);
+        M A4, Z4;
+        fill(A4, 2, 4, 4, {{5.2, 0.1, 0.4, 0.7}, {0.1, 5.8, 0.25, 0.55}, {0.4, 0.25, 6.7, 0.6}, {0.7, 0.55, 0.6, 5.5}});
+        M::inv_chol(A4, Z4);
+        const double z4[4][4] = {{0.438529009653515, -0.007986466419713, -0.029497652767486, -0.055022297341530},
+                                 {0, 0.415296253825059, -0.016194789754698, -0.038713453134371},
+                                 {0, 0, 0.387518183415998, -0.034114893784155},
+                                 {0, 0, 0, 0.433761784290076}};
+        std::vector<double> d4 = dense(Z4);
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) REQUIRE(std::fabs(d4[i * 4 + j] - z4[i][j]) <= tol);
+        // a larger SPD band through three levels with a ragged edge (37 = 4*8 + 5): Z^T A Z = I
+        const int n = 37;
+        typename M::Params p; p.blocksize = 8;
+        M A, Z; A.set_params(p); A.resize(n, n);
+        std::vector<int> r, c; std::vector<T> v;
+        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) {
+            const int d = i > j ? i - j : j - i;
+            if (d <= 6) { r.push_back(i); c.push_back(j); v.push_back((T)(d == 0 ? 4.0 + 0.01 * i : 0.5 / (1 + d) + 0.001 * ((i * j) % 7))); }
+        }
+        A.assign_from_vectors(r, c, v);
+        M::inv_chol(A, Z);
+        M AZ, ZtAZ;
+        M::multiply(A, false, Z, false, AZ);
+        M::multiply(Z, true, AZ, false, ZtAZ);
+        std::vector<double> id = dense(ZtAZ);
+        double worst = 0;
+        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) worst = std::max(worst, std::fabs(id[i * n + j] - (i == j ? 1.0 : 0.0)));
+        REQUIRE(worst <= (sizeof(T) == 8 ? 1e-12 : 5e-5));
+        std::vector<double> zd = dense(Z);
+        for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) REQUIRE(zd[i * n + j] == 0.0);   // upper triangular
     }
     // ---- value semantics of the drop-in: deep copy ----
     {
