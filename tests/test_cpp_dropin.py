@@ -31,3 +31,19 @@ def test_reference_known_answers_through_cpp_dropin():
     r = subprocess.run([BIN], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "checks passed" in r.stdout
+
+
+REF_TESTS = [("ref_test_matrix_creation", []), ("ref_test_matrix_operations", []),
+             ("ref_test_matrix_alloc_problem", ["32", "4", "20", "20", "1"])]   # arguments of the reference's `make check`
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,argv", REF_TESTS, ids=[t[0] for t in REF_TESTS])
+def test_reference_own_test_programs_pass_against_the_dropin(name, argv):
+    """The reference's test_source/*.cc, compiled UNMODIFIED against include/hbsm/ (tests/cpp/Makefile `reftests`, built
+    where /root/reference exists), run on the B200: failure = uncaught exception / assert, as in the reference."""
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", name)
+    if not os.path.exists(exe):
+        pytest.skip("reference test binaries were not built (no /root/reference at build time)")
+    r = subprocess.run([exe] + argv, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:] + r.stderr[-2000:])
