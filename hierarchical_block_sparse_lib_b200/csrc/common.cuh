@@ -138,5 +138,7 @@ struct EventTimer {
 void exclusive_scan_u32(const uint32_t* d_in, uint64_t* d_out, size_t n);
 // stable LSD radix sort of (key,value) pairs on the low `key_bits` bits; result left in d_keys/d_vals
 void radix_sort_pairs(uint64_t* d_keys, uint32_t* d_vals, size_t n, int key_bits);
+// same, on bits [lo_bit, key_bits) only (stable: ties keep their input order)
+void radix_sort_pairs_bits(uint64_t* d_keys, uint32_t* d_vals, size_t n, int lo_bit, int key_bits);
 
 }  // namespace hbsm_b200

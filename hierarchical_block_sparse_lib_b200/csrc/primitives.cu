@@ -99,11 +99,40 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __r
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = block_offsets[gridDim.x];
 }
 
+// whole scan in ONE block (one launch instead of three): for the short arrays that dominate the launch count of the
+// task-list builder and of the radix sort's digit histograms
+__global__ void __launch_bounds__(1024) k_scan_small(const uint32_t* __restrict__ in, size_t n, uint64_t* __restrict__ out) {
+    __shared__ uint64_t sm[1024 / 32 + 1];
+    __shared__ uint64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    constexpr int ITEMS = 4;
+    for (size_t base = 0; base < n; base += 1024 * ITEMS) {
+        const size_t i0 = base + (size_t)threadIdx.x * ITEMS;
+        uint32_t v[ITEMS];
+        uint64_t s = 0;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) { v[i] = (i0 + i < n) ? in[i0 + i] : 0; s += v[i]; }
+        uint64_t total;
+        uint64_t ex = block_excl_scan<1024>(s, &total, sm) + carry_s;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) { if (i0 + i < n) out[i0 + i] = ex; ex += v[i]; }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry_s;
+}
+
 }  // namespace
 
 void exclusive_scan_u32(const uint32_t* d_in, uint64_t* d_out, size_t n) {
     if (n == 0) {
         HB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(uint64_t), engine().stream));
+        return;
+    }
+    if (n <= 32 * 1024) {
+        HB_LAUNCH(k_scan_small, 1, 1024, 0, d_in, n, d_out);
         return;
     }
     size_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
@@ -186,10 +215,15 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
 }  // namespace
 
 void radix_sort_pairs(uint64_t* d_keys, uint32_t* d_vals, size_t n, int key_bits) {
+    radix_sort_pairs_bits(d_keys, d_vals, n, 0, key_bits);
+}
+
+void radix_sort_pairs_bits(uint64_t* d_keys, uint32_t* d_vals, size_t n, int lo_bit, int key_bits) {
     if (n <= 1) return;
     if (key_bits < 1) key_bits = 1;
     if (key_bits > 64) key_bits = 64;
-    int passes = (key_bits + 7) / 8;
+    if (lo_bit < 0 || lo_bit >= key_bits) lo_bit = 0;
+    int passes = (key_bits - lo_bit + 7) / 8;
     size_t nblk = (n + RS_TILE - 1) / RS_TILE;
     DevBuf<uint64_t> keys_tmp(n);
     DevBuf<uint32_t> vals_tmp(n);
@@ -198,7 +232,7 @@ void radix_sort_pairs(uint64_t* d_keys, uint32_t* d_vals, size_t n, int key_bits
     uint64_t* kin = d_keys; uint64_t* kout = keys_tmp.p;
     uint32_t* vin = d_vals; uint32_t* vout = vals_tmp.p;
     for (int p = 0; p < passes; ++p) {
-        int shift = 8 * p;
+        int shift = lo_bit + 8 * p;
         HB_LAUNCH(k_rs_hist, (unsigned)nblk, RS_THREADS, 0, kin, n, shift, hist.p);
         exclusive_scan_u32(hist.p, offs.p, (size_t)RS_RADIX * nblk);
         HB_LAUNCH(k_rs_scatter, (unsigned)nblk, RS_THREADS, 0, kin, vin, n, shift, offs.p, kout, vout);

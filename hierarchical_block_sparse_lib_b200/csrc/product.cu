@@ -616,7 +616,9 @@ void build_tasks(const Matrix& A, bool tA, const Matrix& B, bool tB, const Produ
                   (unsigned long long*)nullptr);
     }
     HB_LAUNCH(k_iota, blocks_for(P, 256), 256, 0, perm.p, (size_t)P);
-    radix_sort_pairs(keys.p, perm.p, P, 3 * kbits);
+    // Stable sort on the C-tile bits only: products are emitted per op(A) tile in (ci, k) order (the row index is sorted
+    // by k inside a row), so inside one C tile they already appear with k ascending and a stable sort keeps that order.
+    radix_sort_pairs_bits(keys.p, perm.p, P, kbits, 3 * kbits);
     DevBuf<uint32_t> head(P);
     HB_LAUNCH(k_task_heads, blocks_for(P, 256), 256, 0, keys.p, (size_t)P, kbits, head.p);
     DevBuf<uint64_t> pos(P + 1);
