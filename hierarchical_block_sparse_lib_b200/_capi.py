@@ -66,6 +66,8 @@ SIGNATURES = {
     "hbsm_product_begin": (_I, [_H, _I, _H, _I, _H, _I, C.c_double, _I, _I]),
     "hbsm_product_finish": (_I, [_H, _P, C.POINTER(_sz), C.POINTER(_sz)]),
     "hbsm_product_to_host": (_I, [_H, _I, _H, _I, _H, _I, C.c_double, _I, _P, _sz, C.POINTER(_sz), C.POINTER(_sz)]),
+    "hbsm_product_from_host": (_I, [_H, _sz, _P, _P, _P, _I, _H, _sz, _P, _P, _P, _I, _H, _I, C.c_double, _I, _P, _sz, _P, _P,
+                                    C.POINTER(_sz), C.POINTER(_sz)]),
     "hbsm_worth_to_multiply": (_I, [_H, _I, _H, _I, C.POINTER(_I)]),
     "hbsm_worth_to_spamm": (_I, [_H, _I, _H, _I, C.c_double, C.POINTER(_I)]),
     "hbsm_add": (_I, [_H, _H, _H]),

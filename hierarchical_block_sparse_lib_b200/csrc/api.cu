@@ -207,6 +207,24 @@ int hbsm_product_to_host(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_hand
         }
     });
 }
+int hbsm_product_from_host(hbsm_handle A, size_t n_a, const int* a_bi, const int* a_bj, const void* a_tiles, int tA,
+                           hbsm_handle B, size_t n_b, const int* b_bi, const int* b_bj, const void* b_tiles, int tB,
+                           hbsm_handle C, int spamm, double tau, int n_slabs, void* host_c_tiles, size_t cap_tiles,
+                           int* c_bi, int* c_bj, size_t* n_block_multiplies, size_t* n_resizes) {
+    return guarded([&] {
+        ProductOpts o;
+        o.spamm = spamm != 0;
+        o.tau = tau;
+        HostTiles ha{n_a, a_bi, a_bj, a_tiles}, hb{n_b, b_bi, b_bj, b_tiles};
+        try {
+            op_product_from_host(M(A), ha, tA != 0, M(B), hb, tB != 0, M(C), o, n_slabs, host_c_tiles, cap_tiles, c_bi, c_bj,
+                                 n_block_multiplies, n_resizes);
+        } catch (...) {
+            op_product_abort();
+            throw;
+        }
+    });
+}
 int hbsm_worth_to_multiply(hbsm_handle A, int tA, hbsm_handle B, int tB, int* out) {
     return guarded([&] { *out = worth_product(M(A), tA != 0, M(B), tB != 0, false, 0.0) ? 1 : 0; });
 }

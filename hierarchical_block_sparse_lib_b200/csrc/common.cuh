@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <utility>
 #include "../../include/hbsm_b200.h"
 
 namespace hbsm_b200 {
@@ -41,6 +42,9 @@ struct Engine {
     int gemm_variant = 0;      // 0 auto (TMA-tiled DMMA), 1 generic scalar kernel, 2 bulk-copy DMMA kernel
     int last_gemm_kernel = 0;  // which leaf kernel the last product ran: 0 generic, 1 TMA-tiled DMMA, 2 bulk-copy DMMA
     hbsm_stage_times last{};
+    // pinned, device-mapped host words: kernels post the few scalars the host needs between launches (sizes of the next
+    // allocations) straight into host memory, so those read-backs never queue on a PCIe copy engine behind bulk transfers
+    uint64_t* mailbox = nullptr;
 };
 Engine& engine();
 void ensure_engine();
@@ -134,6 +138,8 @@ struct EventTimer {
 };
 
 // ---- primitives.cu ----
+// post up to two device scalars (either may be null) into the engine's host mailbox and wait: returns {*a, *b}
+std::pair<uint64_t, uint64_t> read_scalars(const uint64_t* d_a, const uint64_t* d_b);
 // exclusive prefix sum of n uint32 counts into uint64 offsets; out[n] = total (out has n+1 entries)
 void exclusive_scan_u32(const uint32_t* d_in, uint64_t* d_out, size_t n);
 // stable LSD radix sort of (key,value) pairs on the low `key_bits` bits; result left in d_keys/d_vals

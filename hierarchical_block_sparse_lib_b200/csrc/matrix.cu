@@ -41,6 +41,7 @@ void ensure_engine() {
     HB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
     uint64_t thr = UINT64_MAX;
     HB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    HB_CUDA(cudaHostAlloc((void**)&e.mailbox, 64 * sizeof(uint64_t), cudaHostAllocMapped));
     e.ready = true;
 }
 
@@ -312,23 +313,67 @@ __global__ void __launch_bounds__(128) k_leaf_norms(const T* __restrict__ tiles,
     if (lane < nleaf) out[leaf0 + lane] = acc;
 }
 
-// one level of H:3918-3923 / H:656-662: parent = sum of existing children in order 0..3, starting from 0
-__global__ void k_level_heads(const uint64_t* __restrict__ keys, size_t n, uint32_t* __restrict__ head) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    head[i] = (i == 0 || (keys[i - 1] >> 2) != (keys[i] >> 2)) ? 1u : 0u;
-}
+// The whole bottom-up refresh of H:3918-3923 / H:656-662 in ONE block: every node = sum of its existing children in child
+// order 0..3, starting from 0, in Treal.  Siblings are adjacent in Morton order, so one level is a head-flag compaction
+// (ballot + block scan, 1024 entries per round) whose heads add up their <= 4 followers; the levels ping-pong between two
+// scratch tables.  Only the root is kept (inner-node norms are never consulted: the prune rule is flat); it is
+// posted to the engine's host mailbox as a double, so the refresh costs no PCIe copy and no host pass.
 template <typename T>
-__global__ void k_level_reduce(const uint64_t* __restrict__ keys, const T* __restrict__ vals, size_t n,
-                               const uint32_t* __restrict__ head, const uint64_t* __restrict__ pos,
-                               uint64_t* __restrict__ okeys, T* __restrict__ ovals) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !head[i]) return;
-    uint64_t pk = keys[i] >> 2;
-    T s = 0;
-    for (size_t j = i; j < n && (keys[j] >> 2) == pk; ++j) s = DT<T>::add(s, vals[j]);
-    okeys[pos[i]] = pk;
-    ovals[pos[i]] = s;
+__global__ void __launch_bounds__(1024) k_fold_root(const uint64_t* __restrict__ keys0, const T* __restrict__ vals0, size_t n0,
+                                                    int depth, uint64_t* ka, T* va, uint64_t* kb, T* vb,
+                                                    volatile uint64_t* mailbox_slot) {
+    __shared__ uint32_t warp_cnt[33];
+    __shared__ size_t carry_s;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t* kin = keys0;
+    const T* vin = vals0;
+    size_t n = n0;
+    uint64_t* kout = ka;
+    T* vout = va;
+    for (int l = 0; l < depth; ++l) {
+        if (tid == 0) carry_s = 0;
+        __syncthreads();
+        for (size_t base = 0; base < n; base += 1024) {
+            const size_t i = base + tid;
+            const bool head = i < n && (i == 0 || (kin[i - 1] >> 2) != (kin[i] >> 2));
+            const unsigned bal = __ballot_sync(0xffffffffu, head);
+            if (lane == 0) warp_cnt[warp] = __popc(bal);
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t v = warp_cnt[lane];
+                uint32_t incl = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if ((int)lane >= d) incl += o;
+                }
+                warp_cnt[lane] = incl - v;
+                if (lane == 31) warp_cnt[32] = incl;
+            }
+            __syncthreads();
+            if (head) {
+                const size_t pos = carry_s + warp_cnt[warp] + __popc(bal & ((1u << lane) - 1u));
+                const uint64_t pk = kin[i] >> 2;
+                T sum = 0;
+                for (size_t j = i; j < n && (kin[j] >> 2) == pk; ++j) sum = DT<T>::add(sum, vin[j]);
+                kout[pos] = pk;
+                vout[pos] = sum;
+            }
+            __syncthreads();
+            if (tid == 0) carry_s += warp_cnt[32];
+            __syncthreads();
+        }
+        n = carry_s;
+        kin = kout;
+        vin = vout;
+        kout = (kout == ka) ? kb : ka;
+        vout = (vout == va) ? vb : va;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        *mailbox_slot = (uint64_t)__double_as_longlong((double)vin[0]);
+        __threadfence_system();
+    }
 }
 
 // ---- line index ----
@@ -898,50 +943,41 @@ size_t get_all_values(const Matrix& A, size_t cap, int* rows, int* cols, void* v
 // ---------------------------------------------------------------------------------------------------
 // norms
 // ---------------------------------------------------------------------------------------------------
-void compute_leaf_norms(const Matrix& A, void* d_out) {
-    if (A.L == 0) return;
+void compute_leaf_norms(const Matrix& A, void* d_out) { compute_leaf_norms_range(A, 0, A.L, d_out); }
+
+// leaves [t0, t0 + cnt) only; d_out is the base of the norm array (entry t0 + i is written)
+void compute_leaf_norms_range(const Matrix& A, size_t t0, size_t cnt, void* d_out) {
+    if (cnt == 0) return;
     ensure_engine();
-    const unsigned grid = (unsigned)((A.L + 127) / 128);
+    const unsigned grid = (unsigned)((cnt + 127) / 128);
+    const char* src = A.tiles.p + t0 * A.tile_bytes();
     if (A.dtype == HBSM_F64) {
         auto kfn = k_leaf_norms<double, 32>;
-        HB_LAUNCH(kfn, grid, 128, 0, (const double*)A.tiles.p, A.L, A.tile_elems(), (double*)d_out);
+        HB_LAUNCH(kfn, grid, 128, 0, (const double*)src, cnt, A.tile_elems(), (double*)d_out + t0);
     } else {
         auto kfn = k_leaf_norms<float, 64>;
-        HB_LAUNCH(kfn, grid, 128, 0, (const float*)A.tiles.p, A.L, A.tile_elems(), (float*)d_out);
+        HB_LAUNCH(kfn, grid, 128, 0, (const float*)src, cnt, A.tile_elems(), (float*)d_out + t0);
     }
 }
 
-// Root value of the bottom-up refresh (H:3918-3923 / H:656-662): every node = sum of its existing children in child order
-// 0..3, in Treal.  Only the root is kept (inner-node norms are never consulted: the prune rule is flat), so the
-// L leaf norms (8 B each) are brought to the host and folded there along the Morton order -- one small D2H instead of
-// ~4 launches and a host sync per tree level.
-template <typename T>
-static T fold_norms(std::vector<uint64_t>& keys, T* nsq, size_t n, int depth) {
-    // bottom-up, in place: siblings are adjacent in Morton order, so one linear pass per level (1.33 n adds in total)
-    for (int l = 0; l < depth; ++l) {
-        size_t w = 0;
-        for (size_t i = 0; i < n;) {
-            const uint64_t pk = keys[i] >> 2;
-            T s = 0;
-            for (; i < n && (keys[i] >> 2) == pk; ++i) s += nsq[i];
-            keys[w] = pk;
-            nsq[w++] = s;
-        }
-        n = w;
-    }
-    return nsq[0];
-}
-
+// Root value of the bottom-up refresh (H:3918-3923 / H:656-662): k_fold_root, one launch, result through the mailbox.
 double hierarchical_norm(const Matrix& A, const void* d_leaf_norms) {
     if (A.L == 0) return 0.0;
     ensure_engine();
-    std::vector<uint64_t> keys(A.L);
-    std::vector<char> nsq(A.L * A.esize());
-    HB_CUDA(cudaMemcpyAsync(keys.data(), A.keys.p, A.L * sizeof(uint64_t), cudaMemcpyDeviceToHost, engine().stream));
-    HB_CUDA(cudaMemcpyAsync(nsq.data(), d_leaf_norms, A.L * A.esize(), cudaMemcpyDeviceToHost, engine().stream));
+    Engine& e = engine();
+    const size_t half = (A.L + 1) / 2 + 1;   // a level has at most as many nodes as the one below; two scratch tables
+    DevBuf<uint64_t> ka(A.L), kb(half);
+    DevBuf<char> va(A.L * A.esize()), vb(half * A.esize());
+    dispatch(A.dtype, [&](auto z) {
+        using T = decltype(z);
+        HB_LAUNCH(k_fold_root<T>, 1, 1024, 0, A.keys.p, (const T*)d_leaf_norms, A.L, A.vdepth(), ka.p, (T*)va.p, kb.p, (T*)vb.p,
+                  e.mailbox + 2);
+    });
     sync_stream();
-    if (A.dtype == HBSM_F64) return fold_norms<double>(keys, reinterpret_cast<double*>(nsq.data()), A.L, A.vdepth());
-    return (double)fold_norms<float>(keys, reinterpret_cast<float*>(nsq.data()), A.L, A.vdepth());
+    double root;
+    const uint64_t bits = e.mailbox[2];
+    memcpy(&root, &bits, sizeof root);
+    return root;
 }
 
 void update_norms(Matrix& A) {   // H:3905

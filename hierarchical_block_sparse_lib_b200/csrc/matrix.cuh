@@ -75,6 +75,7 @@ void get_values(const Matrix& A, size_t n, const int* rows, const int* cols, voi
 size_t get_all_values(const Matrix& A, size_t cap, int* rows, int* cols, void* vals);
 size_t count_nnz(const Matrix& A);
 void compute_leaf_norms(const Matrix& A, void* d_out);   // bit-exact sequential sum per leaf (H:646-652)
+void compute_leaf_norms_range(const Matrix& A, size_t t0, size_t cnt, void* d_out_base);
 double hierarchical_norm(const Matrix& A, const void* d_leaf_norms);   // root value of H:3918-3923 / H:656-662
 void update_norms(Matrix& A);
 double frob_squared(const Matrix& A);
@@ -127,6 +128,15 @@ void op_product_begin(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix
 void op_product_to_host(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, const ProductOpts& o, void* host_tiles,
                         size_t cap_tiles, int n_chunks, size_t* n_mults, size_t* n_blocks);
 void op_product_finish(Matrix& C, cudaEvent_t wait_for, size_t* n_mults, size_t* n_blocks);
+// The whole host-to-host call in one pipeline: A and B (sized, without tiles) are assembled from HOST tiles, their norms
+// refreshed, C = op(A)*op(B) computed and its tiles delivered to HOST memory, with the PCIe uploads, the leaf GEMMs and the
+// downloads overlapped block-row slab by block-row slab.  Same end state as assign_tiles(A); assign_tiles(B);
+// update_norms(A); update_norms(B); product(A,B,C).  host_c_tiles/c_bi/c_bj receive C's tiles and block coordinates in
+// slab-major order (Morton order inside a slab).
+struct HostTiles { size_t n; const int* bi; const int* bj; const void* tiles; };
+void op_product_from_host(Matrix& A, const HostTiles& ha, bool tA, Matrix& B, const HostTiles& hb, bool tB, Matrix& C,
+                          const ProductOpts& o, int n_slabs, void* host_c_tiles, size_t cap_tiles, int* c_bi, int* c_bj,
+                          size_t* n_mults, size_t* n_blocks);
 void op_product_abort();
 bool worth_product(const Matrix& A, bool tA, const Matrix& B, bool tB, bool spamm, double tau);
 

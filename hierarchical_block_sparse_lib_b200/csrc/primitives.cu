@@ -245,4 +245,19 @@ void radix_sort_pairs_bits(uint64_t* d_keys, uint32_t* d_vals, size_t n, int lo_
     }
 }
 
+namespace {
+__global__ void k_post_scalars(const uint64_t* __restrict__ a, const uint64_t* __restrict__ b, volatile uint64_t* mailbox) {
+    mailbox[0] = a ? *a : 0;
+    mailbox[1] = b ? *b : 0;
+    __threadfence_system();
+}
+}  // namespace
+
+std::pair<uint64_t, uint64_t> read_scalars(const uint64_t* d_a, const uint64_t* d_b) {
+    Engine& e = engine();
+    HB_LAUNCH(k_post_scalars, 1, 1, 0, d_a, d_b, e.mailbox);
+    HB_CUDA(cudaStreamSynchronize(e.stream));
+    return {e.mailbox[0], e.mailbox[1]};
+}
+
 }  // namespace hbsm_b200

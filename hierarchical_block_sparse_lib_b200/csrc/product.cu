@@ -12,6 +12,7 @@
 // test of the reference collapses to this flat leaf-pair rule because node norms are sums of non-negative child norms.
 #include "matrix.cuh"
 #include "gemm_common.cuh"
+#include <chrono>
 
 namespace hbsm_b200 {
 
@@ -28,7 +29,8 @@ struct JoinArgs {
     const void* a_norms; const void* b_norms;
     int spamm; int upper_only;
     double tau2_d; float tau2_f;
-    size_t a_entries;
+    size_t a_entries;      // number of op(A) entries joined by this launch ...
+    size_t a_entry_lo;     // ... starting at this entry of the line index (a block-row range of C; 0 = all of op(A))
 };
 
 template <typename T> __device__ __forceinline__ bool spamm_keep(T na, T nb, const JoinArgs& g);
@@ -46,8 +48,9 @@ __global__ void __launch_bounds__(256) k_join(JoinArgs g, const uint32_t* __rest
                                                int kbits, uint64_t* __restrict__ keys, uint32_t* __restrict__ pa,
                                                uint32_t* __restrict__ pb, unsigned long long* __restrict__ n_cand) {
     const unsigned lane = threadIdx.x & 31;
-    const size_t e = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (e >= g.a_entries) return;
+    const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // counts / offsets are indexed by w
+    if (w >= g.a_entries) return;
+    const size_t e = g.a_entry_lo + w;
     const uint32_t ci = a_line_of_entry[e];
     const uint32_t k = g.a_other[e];
     const uint32_t ta = g.a_tile[e];
@@ -55,7 +58,7 @@ __global__ void __launch_bounds__(256) k_join(JoinArgs g, const uint32_t* __rest
     if (k < g.b_lines) { beg = g.b_ptr[k]; end = g.b_ptr[k + 1]; }
     T na = g.spamm ? reinterpret_cast<const T*>(g.a_norms)[ta] : (T)0;
     uint32_t total = 0;
-    uint64_t base = FILL ? offsets[e] : 0;
+    uint64_t base = FILL ? offsets[w] : 0;
     for (uint32_t f0 = beg; f0 < end; f0 += 32) {
         uint32_t f = f0 + lane;
         bool keep = false;
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(256) k_join(JoinArgs g, const uint32_t* __rest
         total += __popc(bal);
     }
     if (!FILL && lane == 0) {
-        counts[e] = total;
+        counts[w] = total;
         if (n_cand && end > beg) atomicAdd(n_cand, (unsigned long long)(end - beg));
     }
 }
@@ -565,13 +568,17 @@ struct TaskList {
 };
 
 // builds the executed-product list; returns with the stream synchronised
+// entry_lo/entry_hi: range of op(A)'s line-index entries to join (= a block-row range of C), default all
 void build_tasks(const Matrix& A, bool tA, const Matrix& B, bool tB, const ProductOpts& o, int kbits, TaskList& tl,
-                 bool count_only) {
+                 bool count_only, size_t entry_lo = 0, size_t entry_hi = (size_t)-1) {
     const LineIndex& la = line_index(A, tA);   // op(A): lines are C rows
     const LineIndex& lb = line_index(B, tB, true);   // op(B): lines are k; includes the halo tail if one is committed
     tl.n_products = tl.n_ctiles = 0;
     tl.n_candidates = 0;
     if (A.L == 0 || B.n_ext() == 0) return;
+    entry_hi = std::min(entry_hi, A.L);
+    if (entry_lo >= entry_hi) return;
+    const size_t n_e = entry_hi - entry_lo;
     JoinArgs g{};
     g.a_ptr = la.ptr.p; g.a_other = la.other.p; g.a_tile = la.tile.p; g.a_lines = la.n_lines;
     g.b_ptr = lb.ptr.p; g.b_other = lb.other.p; g.b_tile = lb.tile.p; g.b_lines = lb.n_lines;
@@ -580,12 +587,13 @@ void build_tasks(const Matrix& A, bool tA, const Matrix& B, bool tB, const Produ
     g.upper_only = o.upper_only ? 1 : 0;
     g.tau2_d = o.tau * o.tau;                       // fl(tau*tau) in Treal, H:2008
     { float tf = (float)o.tau; g.tau2_f = tf * tf; }
-    g.a_entries = A.L;
-    DevBuf<uint32_t> line_of(A.L), counts(A.L);
+    g.a_entries = n_e;
+    g.a_entry_lo = entry_lo;
+    DevBuf<uint32_t> line_of(A.L), counts(n_e);
     HB_LAUNCH(k_entry_lines, blocks_for(la.n_lines, 256), 256, 0, la.ptr.p, la.n_lines, line_of.p);
     DevBuf<unsigned long long> ncand(1);
     ncand.zero();
-    const unsigned jgrid = blocks_for(A.L * 32, 256);
+    const unsigned jgrid = blocks_for(n_e * 32, 256);
     if (A.dtype == HBSM_F64) {
         auto kfn = k_join<double, false>;
         HB_LAUNCH(kfn, jgrid, 256, 0, g, line_of.p, counts.p, (const uint64_t*)nullptr, kbits, (uint64_t*)nullptr,
@@ -595,12 +603,11 @@ void build_tasks(const Matrix& A, bool tA, const Matrix& B, bool tB, const Produ
         HB_LAUNCH(kfn, jgrid, 256, 0, g, line_of.p, counts.p, (const uint64_t*)nullptr, kbits, (uint64_t*)nullptr,
                   (uint32_t*)nullptr, (uint32_t*)nullptr, ncand.p);
     }
-    DevBuf<uint64_t> offs(A.L + 1);
-    exclusive_scan_u32(counts.p, offs.p, A.L);
-    uint64_t P = 0;
-    HB_CUDA(cudaMemcpyAsync(&P, offs.p + A.L, sizeof(uint64_t), cudaMemcpyDeviceToHost, engine().stream));
-    HB_CUDA(cudaMemcpyAsync(&tl.n_candidates, ncand.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, engine().stream));
-    sync_stream();
+    DevBuf<uint64_t> offs(n_e + 1);
+    exclusive_scan_u32(counts.p, offs.p, n_e);
+    const auto pc = read_scalars(offs.p + n_e, (const uint64_t*)ncand.p);
+    const uint64_t P = pc.first;
+    tl.n_candidates = pc.second;
     tl.n_products = (size_t)P;
     if (P == 0 || count_only) return;
     if (P >= 0xffffffffull) throw Error(HBSM_E_ARG, "hbsm_b200: more than 2^32-1 leaf products in one call");
@@ -623,9 +630,7 @@ void build_tasks(const Matrix& A, bool tA, const Matrix& B, bool tB, const Produ
     HB_LAUNCH(k_task_heads, blocks_for(P, 256), 256, 0, keys.p, (size_t)P, kbits, head.p);
     DevBuf<uint64_t> pos(P + 1);
     exclusive_scan_u32(head.p, pos.p, P);
-    uint64_t nct = 0;
-    HB_CUDA(cudaMemcpyAsync(&nct, pos.p + P, sizeof(uint64_t), cudaMemcpyDeviceToHost, engine().stream));
-    sync_stream();
+    const uint64_t nct = read_scalars(pos.p + P, nullptr).first;
     tl.n_ctiles = (size_t)nct;
     tl.ckeys.alloc(nct);
     tl.begin.alloc(nct + 1);
@@ -695,9 +700,7 @@ __global__ void k_list_from_flags(const uint32_t* __restrict__ flags, const uint
 size_t list_of(const DevBuf<uint32_t>& flags, size_t n, DevBuf<uint32_t>& out) {
     DevBuf<uint64_t> pos(n + 1);
     exclusive_scan_u32(flags.p, pos.p, n);
-    uint64_t total = 0;
-    HB_CUDA(cudaMemcpyAsync(&total, pos.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, engine().stream));
-    sync_stream();
+    const uint64_t total = read_scalars(pos.p + n, nullptr).first;
     out.alloc(std::max<size_t>((size_t)total, 1));
     if (total) HB_LAUNCH(k_list_from_flags, blocks_for(n, 256), 256, 0, flags.p, pos.p, n, out.p);
     return (size_t)total;
@@ -909,6 +912,348 @@ void op_product_to_host(const Matrix& A, bool tA, const Matrix& B, bool tB, Matr
     }
     op_product_finish(C, nullptr, n_mults, n_blocks);
     if (!streamed && host_tiles && C.L && cap_tiles < C.L) throw Error(HBSM_E_ARG, "hbsm_b200: host buffer too small for the tiles of C");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-to-host product: uploads, norms, task lists, leaf GEMMs and downloads pipelined over block-row slabs of C
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct HostPlan {   // one operand: its tiles sorted by Morton key, cut into upload runs per slab
+    struct Run { size_t dst, src, cnt; };   // sorted positions [dst, dst+cnt) <- host tiles [src, src+cnt)
+    std::vector<uint64_t> keys;             // ascending
+    std::vector<uint32_t> src;              // host tile of sorted position i
+    std::vector<std::vector<Run>> runs;     // [slab]
+    size_t n_runs = 0;
+};
+
+// slab coordinate of a tile: block row (by_col = false) or block column (by_col = true), >> shift
+void plan_operand(const Matrix& X, const HostTiles& h, bool by_col, int shift, int S, HostPlan& pl) {
+    const uint32_t g = X.grid_side();
+    const size_t n = h.n;
+    pl.keys.resize(n);
+    pl.src.resize(n);
+    bool sorted = true;
+    for (size_t i = 0; i < n; ++i) {
+        const int bi = h.bi[i], bj = h.bj[i];
+        if (bi < 0 || bj < 0 || (uint32_t)bi >= g || (uint32_t)bj >= g || (long long)bi * X.b >= std::max(X.M, 1) ||
+            (long long)bj * X.b >= std::max(X.N, 1))
+            throw_ref("Error in HierarchicalBlockSparseMatrix<Treal>::assign_from_vectors: index outside matrix boundaries.");
+        pl.keys[i] = morton_encode((uint32_t)bi, (uint32_t)bj);
+        pl.src[i] = (uint32_t)i;
+        if (i && pl.keys[i] <= pl.keys[i - 1]) sorted = false;
+    }
+    if (!sorted) {
+        std::sort(pl.src.begin(), pl.src.end(), [&](uint32_t a, uint32_t b) { return pl.keys[a] < pl.keys[b]; });
+        std::vector<uint64_t> k2(n);
+        for (size_t i = 0; i < n; ++i) k2[i] = pl.keys[pl.src[i]];
+        pl.keys.swap(k2);
+        for (size_t i = 1; i < n; ++i)
+            if (pl.keys[i] == pl.keys[i - 1]) throw Error(HBSM_E_ARG, "hbsm_b200: assign_tiles: tile coordinates are not unique");
+    }
+    pl.runs.assign((size_t)S, {});
+    int cur = -1;
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t coord = by_col ? morton_col(pl.keys[i]) : morton_row(pl.keys[i]);
+        const int sl = std::min<int>((int)(coord >> shift), S - 1);
+        if (sl == cur && pl.src[i] == pl.src[i - 1] + 1) {
+            pl.runs[sl].back().cnt++;
+        } else {
+            pl.runs[sl].push_back({i, pl.src[i], 1});
+            pl.n_runs++;
+            cur = sl;
+        }
+    }
+}
+
+// dst tile j = tile idx[j] of the concatenation of the per-slab tile buffers (16-byte vectors)
+__global__ void __launch_bounds__(256) k_gather_slab_tiles(const uint32_t* __restrict__ idx, const uint64_t* __restrict__ slab_off,
+                                                           const uint4* const* __restrict__ slab_ptr, int n_slabs,
+                                                           size_t vec_per_tile, uint4* __restrict__ dst) {
+    const size_t j = blockIdx.x;
+    const uint32_t src = idx[j];
+    int lo = 0, hi = n_slabs - 1;   // last slab with slab_off[s] <= src
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (slab_off[mid] <= src) lo = mid; else hi = mid - 1;
+    }
+    const uint4* from = slab_ptr[lo] + (size_t)(src - slab_off[lo]) * vec_per_tile;
+    uint4* to = dst + j * vec_per_tile;
+    for (size_t v = (size_t)blockIdx.y * blockDim.x + threadIdx.x; v < vec_per_tile; v += (size_t)gridDim.y * blockDim.x) to[v] = from[v];
+}
+
+struct SideStreams {
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+};
+SideStreams& side_streams() {
+    static SideStreams s;
+    if (!s.h2d) {
+        HB_CUDA(cudaStreamCreateWithFlags(&s.h2d, cudaStreamNonBlocking));
+        HB_CUDA(cudaStreamCreateWithFlags(&s.d2h, cudaStreamNonBlocking));
+    }
+    return s;
+}
+
+}  // namespace
+
+void op_product_from_host(Matrix& A, const HostTiles& ha, bool tA, Matrix& B, const HostTiles& hb, bool tB, Matrix& C,
+                          const ProductOpts& o, int n_slabs, void* host_c_tiles, size_t cap_tiles, int* c_bi, int* c_bj,
+                          size_t* n_mults, size_t* n_blocks) {
+    ensure_engine();
+    Engine& e = engine();
+    const auto wall0 = std::chrono::steady_clock::now();
+    std::vector<std::pair<const char*, double>> marks;
+    auto mark = [&](const char* what) {
+        marks.emplace_back(what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
+    };
+    if (&A == &B) throw Error(HBSM_E_ARG, "hbsm_b200: product_from_host needs two distinct operand handles");
+    int AM = 0, BN = 0;
+    check_operands(A, tA, B, tB, C, o.spamm, AM, BN);
+    if ((ha.n && (!ha.bi || !ha.bj || !ha.tiles)) || (hb.n && (!hb.bi || !hb.bj || !hb.tiles)))
+        throw Error(HBSM_E_ARG, "hbsm_b200: product_from_host: null tile arrays");
+    const uint64_t launches0 = e.launches;
+    const size_t tb = A.tile_bytes();
+    // degenerate (single-leaf operand) or unordered input: bulk upload + device gather, then the ordinary product whose
+    // C tiles stream to the host
+    auto classic = [&]() {
+        assign_tiles_host(A, ha.n, ha.bi, ha.bj, ha.tiles);
+        assign_tiles_host(B, hb.n, hb.bi, hb.bj, hb.tiles);
+        update_norms(A);
+        update_norms(B);
+        size_t nb = 0;
+        op_product_to_host(A, tA, B, tB, C, o, host_c_tiles, cap_tiles, 8, n_mults, &nb);
+        if (n_blocks) *n_blocks = nb;
+        if (nb && c_bi && c_bj) {
+            std::vector<uint64_t> hk = C.keys.to_host();
+            for (size_t i = 0; i < nb && i < hk.size(); ++i) { c_bi[i] = (int)morton_row(hk[i]); c_bj[i] = (int)morton_col(hk[i]); }
+        }
+    };
+    if (A.vdepth() == 0 || B.vdepth() == 0) { classic(); return; }
+    if (A.L != 0 || B.L != 0)
+        throw_ref("Error in HierarchicalBlockSparseMatrix<Treal>::assign_from_vectors: non-null child0 matrix occured.");
+
+    // slab geometry: 2^shift block rows of C per slab, aligned to Morton squares so that a slab is a few contiguous runs
+    const uint32_t g = std::max(A.grid_side(), B.grid_side());
+    int gbits = 0;
+    while ((1u << gbits) < g) ++gbits;
+    int S = n_slabs;
+    if (S <= 0) S = (ha.n + hb.n) * tb >= ((size_t)64 << 20) ? 16 : 1;
+    int sbits = 0;
+    while ((2 << sbits) <= S && sbits < gbits) ++sbits;
+    S = 1 << sbits;
+    const int shift = gbits - sbits;
+
+    HostPlan pa, pb;
+    plan_operand(A, ha, tA, shift, S, pa);    // op(A): slab by ci (block column of A if tA)
+    plan_operand(B, hb, tB, shift, S, pb);    // op(B): slab by k  (block column of B if tB)
+    if (pa.n_runs + pb.n_runs > 4096) { classic(); return; }
+    mark("planned");
+
+    // line-entry ranges of op(A) per slab, and the upload order: chunk c = op(A)'s slab c plus every slab of op(B) that
+    // slab c's products read and that is not on its way yet, so that C's slab c is computable as soon as chunk c has landed;
+    // op(B) slabs nobody asked for travel in a last chunk S
+    const uint32_t ga = A.grid_side();
+    std::vector<size_t> hptr((size_t)ga + 2, 0);
+    std::vector<int> kmax((size_t)S, -1);
+    for (size_t i = 0; i < ha.n; ++i) {
+        const uint32_t r = morton_row(pa.keys[i]), c = morton_col(pa.keys[i]);
+        const uint32_t ci = tA ? c : r, k = tA ? r : c;
+        hptr[ci + 1]++;
+        const int sc = std::min<int>((int)(ci >> shift), S - 1), sk = std::min<int>((int)(k >> shift), S - 1);
+        kmax[sc] = std::max(kmax[sc], sk);
+    }
+    for (uint32_t l = 0; l < ga; ++l) hptr[l + 1] += hptr[l];
+    std::vector<std::vector<int>> chunk_b((size_t)S + 1);
+    {
+        int b_up = -1;
+        for (int c = 0; c < S; ++c)
+            for (; b_up < kmax[c];) chunk_b[c].push_back(++b_up);
+        for (; b_up < S - 1;) chunk_b[S].push_back(++b_up);
+    }
+
+    // device tables: keys now, tiles as they arrive
+    {
+        DevBuf<uint64_t> ka(std::max<size_t>(ha.n, 1)), kb(std::max<size_t>(hb.n, 1));
+        ka.upload(pa.keys.data(), ha.n);
+        kb.upload(pb.keys.data(), hb.n);
+        DevBuf<char> ta(std::max<size_t>(ha.n, 1) * tb), tbuf(std::max<size_t>(hb.n, 1) * tb);
+        A.set_table(std::move(ka), std::move(ta), ha.n);
+        B.set_table(std::move(kb), std::move(tbuf), hb.n);
+    }
+    mark("tables allocated");
+    SideStreams& ss = side_streams();
+    const bool trace = getenv("HBSM_TRACE_PIPE") != nullptr;   // per-slab timeline on stderr (development aid)
+    std::vector<cudaEvent_t> up((size_t)S + 1, nullptr), done((size_t)S, nullptr), shipped((size_t)S, nullptr);
+    for (int c = 0; c <= S; ++c) HB_CUDA(cudaEventCreateWithFlags(&up[c], trace ? cudaEventDefault : cudaEventDisableTiming));
+    for (int s2 = 0; s2 < S; ++s2) {
+        HB_CUDA(cudaEventCreateWithFlags(&done[s2], trace ? cudaEventDefault : cudaEventDisableTiming));
+        if (trace) HB_CUDA(cudaEventCreate(&shipped[s2]));
+    }
+    struct SlabOut { TaskList tl; DevBuf<char> ct; size_t off = 0; };
+    std::vector<SlabOut> outs((size_t)S);
+    std::vector<EventTimer> tg((size_t)S);
+    std::vector<char> timed((size_t)S, 0);
+    EventTimer t_total;
+    size_t n_ct = 0, P_total = 0;
+    unsigned long long cand = 0;
+    bool host_ok = host_c_tiles != nullptr;
+    std::vector<uint64_t> hk;   // C's keys in slab-major order (the order of host_c_tiles)
+    auto destroy_events = [&]() {
+        for (cudaEvent_t ev : up) if (ev) cudaEventDestroy(ev);
+        for (cudaEvent_t ev : done) if (ev) cudaEventDestroy(ev);
+        for (cudaEvent_t ev : shipped) if (ev) cudaEventDestroy(ev);
+    };
+    try {
+        t_total.start();
+        // the tile pools were allocated in engine-stream order: the upload stream may touch them after this event
+        HB_CUDA(cudaEventRecord(done[0], e.stream));
+        HB_CUDA(cudaStreamWaitEvent(ss.h2d, done[0], 0));
+        for (int c = 0; c <= S; ++c) {   // every upload is queued now; PCIe stays busy from here to the last tile
+            if (c < S)
+                for (const HostPlan::Run& r : pa.runs[c])
+                    HB_CUDA(cudaMemcpyAsync(A.tiles.p + r.dst * tb, (const char*)ha.tiles + r.src * tb, r.cnt * tb, cudaMemcpyHostToDevice, ss.h2d));
+            for (int j : chunk_b[c])
+                for (const HostPlan::Run& r : pb.runs[j])
+                    HB_CUDA(cudaMemcpyAsync(B.tiles.p + r.dst * tb, (const char*)hb.tiles + r.src * tb, r.cnt * tb, cudaMemcpyHostToDevice, ss.h2d));
+            HB_CUDA(cudaEventRecord(up[c], ss.h2d));
+        }
+        mark("uploads queued");
+        C.dtype = A.dtype;
+        C.b = A.b;
+        C.resize(AM, BN);
+        const int kbits = coord_bits(A, B, AM, BN, A.b);
+        if (3 * kbits > 64) throw Error(HBSM_E_ARG, "hbsm_b200: block grid too deep for 64-bit task keys (depth > 21)");
+        ProductOpts oo = o;
+        oo.updated = true;   // norms are refreshed chunk by chunk below
+        int normed = -1;
+        auto norms_up_to = [&](int c_hi) {
+            for (int c = normed + 1; c <= c_hi; ++c) {
+                HB_CUDA(cudaStreamWaitEvent(e.stream, up[c], 0));
+                if (c < S)
+                    for (const HostPlan::Run& r : pa.runs[c]) compute_leaf_norms_range(A, r.dst, r.cnt, A.norms.p);
+                for (int j : chunk_b[c])
+                    for (const HostPlan::Run& r : pb.runs[j]) compute_leaf_norms_range(B, r.dst, r.cnt, B.norms.p);
+            }
+            normed = std::max(normed, c_hi);
+        };
+        for (int s2 = 0; s2 < S; ++s2) {
+            const uint32_t l_lo = std::min<uint32_t>((uint32_t)s2 << shift, ga);
+            const uint32_t l_hi = (s2 == S - 1) ? ga : std::min<uint32_t>((uint32_t)(s2 + 1) << shift, ga);
+            const size_t e_lo = hptr[l_lo], e_hi = hptr[l_hi];
+            if (e_lo == e_hi) continue;
+            norms_up_to(s2);
+            SlabOut& so = outs[s2];
+            build_tasks(A, tA, B, tB, oo, kbits, so.tl, false, e_lo, e_hi);
+            cand += so.tl.n_candidates;
+            if (so.tl.n_products == 0) continue;
+            const size_t nct = so.tl.n_ctiles;
+            so.off = n_ct;
+            so.ct.alloc(nct * tb);
+            tg[s2].start();
+            launch_leaf_gemm(A, tA, B, tB, so.tl, nullptr, nct, so.ct.p);
+            tg[s2].stop();
+            timed[s2] = 1;
+            if (host_ok && n_ct + nct <= cap_tiles) {
+                HB_CUDA(cudaEventRecord(done[s2], e.stream));
+                HB_CUDA(cudaStreamWaitEvent(ss.d2h, done[s2], 0));
+                HB_CUDA(cudaMemcpyAsync((char*)host_c_tiles + n_ct * tb, so.ct.p, nct * tb, cudaMemcpyDeviceToHost, ss.d2h));
+                if (trace) HB_CUDA(cudaEventRecord(shipped[s2], ss.d2h));
+            } else {
+                host_ok = false;
+            }
+            n_ct += nct;
+            P_total += so.tl.n_products;
+        }
+        norms_up_to(S);
+        mark("slabs launched");
+        // roots of the two norm refreshes (H:3918-3923); this is also where the host joins the engine stream
+        A.root_norm_cached = A.L ? hierarchical_norm(A, A.norms.p) : 0.0;
+        B.root_norm_cached = B.L ? hierarchical_norm(B, B.norms.p) : 0.0;
+        mark("root norms");
+
+        // C's block table: the slabs' tiles merged into one Morton-ordered pool.  Queued behind the last leaf GEMM and NOT
+        // waited for: the host results are complete when the download stream drains, the device table when the engine
+        // stream does (every later call on C is stream-ordered behind it).
+        if (n_ct > 0) {
+            int first = -1, n_nonempty = 0;
+            for (int s2 = 0; s2 < S; ++s2) if (outs[s2].tl.n_products) { if (first < 0) first = s2; ++n_nonempty; }
+            if (c_bi && c_bj) {
+                hk.resize(n_ct);
+                for (int s2 = 0; s2 < S; ++s2)
+                    if (outs[s2].tl.n_products) outs[s2].tl.ckeys.download(hk.data() + outs[s2].off, outs[s2].tl.n_ctiles);
+                sync_stream();
+            }
+            if (n_nonempty == 1) {
+                SlabOut& so = outs[first];
+                C.set_table(std::move(so.tl.ckeys), std::move(so.ct), n_ct);
+                C.task_begin = std::move(so.tl.begin);
+                C.task_k = std::move(so.tl.task_k);
+                C.n_tasks = so.tl.n_products;
+            } else {
+                DevBuf<uint64_t> skeys(n_ct);
+                DevBuf<uint32_t> idx(n_ct);
+                std::vector<uint64_t> h_off((size_t)S);
+                std::vector<const uint4*> h_ptr((size_t)S);
+                for (int s2 = S - 1, nxt = -1; s2 >= 0; --s2) {   // slabs without tiles must not win the search below
+                    if (outs[s2].tl.n_products) {
+                        nxt = s2;
+                        h_off[s2] = outs[s2].off;
+                        HB_CUDA(cudaMemcpyAsync(skeys.p + outs[s2].off, outs[s2].tl.ckeys.p, outs[s2].tl.n_ctiles * sizeof(uint64_t),
+                                                cudaMemcpyDeviceToDevice, e.stream));
+                    } else {
+                        h_off[s2] = nxt >= 0 ? outs[nxt].off : n_ct;
+                    }
+                    h_ptr[s2] = (const uint4*)outs[s2].ct.p;
+                }
+                HB_LAUNCH(k_iota, blocks_for(n_ct, 256), 256, 0, idx.p, n_ct);
+                radix_sort_pairs(skeys.p, idx.p, n_ct, 2 * std::max(C.vdepth(), 1));
+                DevBuf<uint64_t> d_off((size_t)S);
+                DevBuf<const uint4*> d_ptr((size_t)S);
+                d_off.upload(h_off.data(), (size_t)S);   // small pageable sources: staged by the driver before the call returns
+                d_ptr.upload(h_ptr.data(), (size_t)S);
+                DevBuf<char> t(n_ct * tb);
+                dim3 grid((unsigned)n_ct, (unsigned)std::max<size_t>(1, std::min<size_t>(8, tb / 16 / 1024)));
+                HB_LAUNCH(k_gather_slab_tiles, grid, 256, 0, idx.p, d_off.p, d_ptr.p, S, tb / 16, (uint4*)t.p);
+                C.set_table(std::move(skeys), std::move(t), n_ct);
+                C.drop_tasks();
+            }
+        }
+        t_total.stop();
+        mark("C merge queued");
+        HB_CUDA(cudaStreamSynchronize(ss.d2h));
+        mark("downloads complete");
+        if (c_bi && c_bj && host_ok)
+            for (size_t i = 0; i < hk.size(); ++i) { c_bi[i] = (int)morton_row(hk[i]); c_bj[i] = (int)morton_col(hk[i]); }
+        if (trace) {
+            sync_stream();
+            auto at = [&](cudaEvent_t ev) { float t = -1.f; if (ev && cudaEventQuery(ev) == cudaSuccess) cudaEventElapsedTime(&t, t_total.a, ev); return t; };
+            fprintf(stderr, "[hbsm pipe] S=%d runs A=%zu B=%zu device timeline %.2f ms\n", S, pa.n_runs, pb.n_runs, t_total.ms());
+            for (auto& mk : marks) fprintf(stderr, "[hbsm pipe] host wall %8.2f ms  %s\n", mk.second, mk.first);
+            for (int s2 = 0; s2 < S; ++s2)
+                fprintf(stderr, "[hbsm pipe] slab %2d: uploaded %.2f  gemm start %.2f end %.2f  shipped %.2f  (%zu products, %zu C tiles)\n",
+                        s2, at(up[s2]), timed[s2] ? at(tg[s2].a) : -1.f, timed[s2] ? at(tg[s2].b) : -1.f,
+                        host_ok && timed[s2] ? at(shipped[s2]) : -1.f, outs[s2].tl.n_products, outs[s2].tl.n_ctiles);
+        }
+    } catch (...) {
+        cudaStreamSynchronize(ss.h2d); cudaStreamSynchronize(e.stream); cudaStreamSynchronize(ss.d2h);
+        destroy_events();
+        throw;
+    }
+    destroy_events();
+    C.n_mults = P_total;
+    if (n_mults) *n_mults = P_total;
+    if (n_blocks) *n_blocks = C.L;
+    hbsm_stage_times st{};
+    for (int s2 = 0; s2 < S; ++s2) if (timed[s2]) st.gemm_ms += tg[s2].ms();
+    mark("return");
+    st.total_ms = marks.back().second;   // host wall clock of the call: the device table of C may still be merging
+    st.n_candidates = cand;
+    st.n_products = P_total;
+    st.n_ctiles = n_ct;
+    st.gpu_launches = e.launches - launches0;
+    st.gemm_kernel = (uint64_t)e.last_gemm_kernel;
+    e.last = st;
+    if (host_c_tiles && !host_ok) throw Error(HBSM_E_ARG, "hbsm_b200: host buffer too small for the tiles of C");
 }
 
 void op_product(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, const ProductOpts& o, size_t* n_mults,

@@ -150,6 +150,25 @@ class HierarchicalBlockSparseMatrix:
         return nm.value, nr.value
 
     @staticmethod
+    def product_from_host(A, a_bi, a_bj, a_tiles, tA, B, b_bi, b_bj, b_tiles, tB, Cm, spamm=False, tau=0.0, out_tiles=None,
+                          n_slabs=0):
+        """Host-to-host multiply / SpAMM as one pipeline (hbsm_product_from_host): A and B are sized, tile-less matrices
+        that end up assembled with fresh norms, Cm receives the product; `out_tiles` (numpy, [cap, b*b], ideally a view of
+        pinned memory) receives C's tiles.  Returns (n_mults, n_blocks, c_bi, c_bj) with the coordinates of out_tiles' rows."""
+        a_bi = np.ascontiguousarray(a_bi, np.int32); a_bj = np.ascontiguousarray(a_bj, np.int32)
+        b_bi = np.ascontiguousarray(b_bi, np.int32); b_bj = np.ascontiguousarray(b_bj, np.int32)
+        at = np.ascontiguousarray(a_tiles, A.dtype); bt = np.ascontiguousarray(b_tiles, B.dtype)
+        cap = 0 if out_tiles is None else out_tiles.shape[0]
+        cbi = np.zeros(max(cap, 1), np.int32); cbj = np.zeros(max(cap, 1), np.int32)
+        nm = C.c_size_t(0); nr = C.c_size_t(0)
+        check(lib().hbsm_product_from_host(A._h, len(a_bi), _ptr(a_bi), _ptr(a_bj), _ptr(at), int(bool(tA)),
+                                           B._h, len(b_bi), _ptr(b_bi), _ptr(b_bj), _ptr(bt), int(bool(tB)),
+                                           Cm._h, int(bool(spamm)), float(tau), int(n_slabs),
+                                           None if out_tiles is None else _ptr(out_tiles), cap,
+                                           _ptr(cbi) if cap else None, _ptr(cbj) if cap else None, C.byref(nm), C.byref(nr)))
+        return nm.value, nr.value, cbi[:nr.value], cbj[:nr.value]
+
+    @staticmethod
     def worth_to_multiply(A, tA, B, tB):
         v = C.c_int(0)
         check(lib().hbsm_worth_to_multiply(A._h, int(bool(tA)), B._h, int(bool(tB)), C.byref(v)))

@@ -108,6 +108,19 @@ int hbsm_product_finish(hbsm_handle C, void* cuda_event_or_null, size_t* n_block
  * of C tiles nothing is copied and HBSM_E_ARG is returned after C is complete (read *n_resizes and call again / export). */
 int hbsm_product_to_host(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, int spamm, double tau, int updated,
                          void* host_tiles, size_t cap_tiles, size_t* n_block_multiplies, size_t* n_resizes);
+/* The whole host-to-host call as ONE pipeline (what a caller whose matrices live in host memory, like the reference's,
+ * does per multiply): A and B are sized handles without tiles; their tiles come from HOST arrays (tile t of A at block
+ * coordinates (a_bi[t], a_bj[t]), dense column-major, pinned memory recommended, Morton-ordered input streams best), are
+ * uploaded block-row slab by block-row slab, their norms refreshed as they land, and every slab of C = op(A)*op(B) is
+ * computed and shipped to host_c_tiles as soon as the tiles it reads have arrived: PCIe upload, leaf GEMMs and PCIe
+ * download overlap.  End state = hbsm_assign_tiles(A), hbsm_assign_tiles(B), hbsm_update_norms(A), hbsm_update_norms(B),
+ * hbsm_multiply / hbsm_spamm(A,B,C).  host_c_tiles (room for cap_tiles tiles), c_bi, c_bj (cap_tiles ints each, may be
+ * null) receive C's tiles and their block coordinates in slab-major order (Morton order inside a slab).  n_slabs = 0
+ * lets the engine choose.  HBSM_E_ARG after C is complete if cap_tiles was too small (read *n_resizes, export C). */
+int hbsm_product_from_host(hbsm_handle A, size_t n_a, const int* a_bi, const int* a_bj, const void* a_tiles, int tA,
+                           hbsm_handle B, size_t n_b, const int* b_bi, const int* b_bj, const void* b_tiles, int tB,
+                           hbsm_handle C, int spamm, double tau, int n_slabs, void* host_c_tiles, size_t cap_tiles,
+                           int* c_bi, int* c_bj, size_t* n_block_multiplies, size_t* n_resizes);
 int hbsm_worth_to_multiply(hbsm_handle A, int tA, hbsm_handle B, int tB, int* out);             /* H:1873 */
 int hbsm_worth_to_spamm(hbsm_handle A, int tA, hbsm_handle B, int tB, double tau, int* out);    /* H:2006 */
 

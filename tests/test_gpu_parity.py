@@ -297,3 +297,63 @@ def test_product_to_host_streams_the_same_tiles():
         C2 = HBSM(np.float64)
         _capi.check(_capi.lib().hbsm_product_to_host(A._h, 0, B._h, 1, C2._h, 1, tau, 1, C.c_void_p(host.data_ptr()), 3,
                                                       C.byref(nm), C.byref(nr)))
+
+
+@pytest.mark.parametrize("dtype,b,n,lam", [(np.float64, 64, 8192, 0.02), (np.float32, 32, 2048, 0.05), (np.float64, 32, 1000, 0.05)])
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("n_slabs,shuffled", [(8, False), (4, True), (1, False), (0, False)])
+def test_product_from_host_pipeline(dtype, b, n, lam, tA, tB, n_slabs, shuffled):
+    """hbsm_product_from_host (slab-pipelined upload / norms / task list / GEMM / download) leaves A, B, C exactly as
+    assign_tiles + update_norms + spamm do, and delivers C's tiles with their coordinates to the host buffer."""
+    tau = 1e-6
+    W = G.decay_width(lam)
+    A = HBSM(dtype, b); A.generate_decay(n, lam, W, 1); A.update_internal_info()
+    B = HBSM(dtype, b); B.generate_decay(n, lam, W, 2); B.update_internal_info()
+    Cref = HBSM(dtype); nm0, nr0 = HBSM.spamm(A, tA, B, tB, Cref, tau, True)
+    ci0, cj0, _, want = Cref.export_leaves(norms=False)
+    abi, abj, an, at = A.export_leaves()
+    bbi, bbj, bn, bt = B.export_leaves()
+    if shuffled:   # unordered host tiles: more (shorter) upload runs, or the bulk fallback
+        rng = np.random.default_rng(5)
+        pa = rng.permutation(len(abi)); pb = rng.permutation(len(bbi))
+        abi, abj, at = abi[pa], abj[pa], at[pa]
+        bbi, bbj, bt = bbi[pb], bbj[pb], bt[pb]
+    A2 = HBSM(dtype, b); A2.resize(n, n)
+    B2 = HBSM(dtype, b); B2.resize(n, n)
+    C2 = HBSM(dtype)
+    out = np.zeros((nr0 + 3, b * b), dtype)
+    nm, nr, cbi, cbj = HBSM.product_from_host(A2, abi, abj, at, tA, B2, bbi, bbj, bt, tB, C2, True, tau, out, n_slabs)
+    assert (nm, nr) == (nm0, nr0)
+    # operands: same table, same (bit-exact) leaf norms and root norm as the two-call path
+    for X, Y in ((A, A2), (B, B2)):
+        xi, xj, xn, xt = X.export_leaves(); yi, yj, yn, yt = Y.export_leaves()
+        assert np.array_equal(xi, yi) and np.array_equal(xj, yj) and np.array_equal(xn, yn) and np.array_equal(xt, yt)
+        assert X.get_frob_norm_squared_internal() == Y.get_frob_norm_squared_internal()
+    # C on the device: identical table and bitwise identical tiles (same products in the same k order per C tile)
+    ci2, cj2, _, got = C2.export_leaves(norms=False)
+    assert np.array_equal(ci0, ci2) and np.array_equal(cj0, cj2) and np.array_equal(want, got)
+    # C on the host: the same tiles, slab-major, labelled by (c_bi, c_bj)
+    order = np.lexsort((cbj, cbi))
+    ref_order = np.lexsort((cj0, ci0))
+    assert np.array_equal(cbi[order], ci0[ref_order]) and np.array_equal(cbj[order], cj0[ref_order])
+    assert np.array_equal(out[:nr][order], want[ref_order])
+    assert C2.get_n_block_multiplications() == nm0
+
+
+def test_product_from_host_errors():
+    b, n = 32, 256
+    A = HBSM(np.float64, b); A.generate_decay(n, 0.1, 100, 1)
+    bi, bj, _, t = A.export_leaves(norms=False)
+    A2 = HBSM(np.float64, b); A2.resize(n, n); B2 = HBSM(np.float64, b); B2.resize(n, n); C2 = HBSM(np.float64)
+    out = np.zeros((2, b * b))
+    with pytest.raises(hb.HbsmError):      # host buffer too small: reported after C is complete
+        HBSM.product_from_host(A2, bi, bj, t, 0, B2, bi, bj, t, 0, C2, False, 0.0, out, 2)
+    assert C2.get_n_blocks() > 2 and A2.get_n_blocks() == len(bi)
+    A3 = HBSM(np.float64, b); A3.resize(n, n); B3 = HBSM(np.float64, b); B3.resize(n, n)
+    with pytest.raises(hb.HbsmError):      # C must be empty (H:5681)
+        HBSM.product_from_host(A3, bi, bj, t, 0, B3, bi, bj, t, 0, C2, False, 0.0, None, 2)
+    bad = bi.copy(); bad[0] = n // b + 5
+    with pytest.raises(hb.HbsmError):      # coordinates outside the matrix
+        HBSM.product_from_host(A3, bad, bj, t, 0, B3, bi, bj, t, 0, HBSM(np.float64), False, 0.0, None, 2)
+    with pytest.raises(hb.HbsmError):      # operands already populated
+        HBSM.product_from_host(A2, bi, bj, t, 0, B2, bi, bj, t, 0, HBSM(np.float64), False, 0.0, None, 2)
