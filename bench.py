@@ -298,6 +298,12 @@ def measure_e2e(hb, H, A, B, w, steps, torch):
 
 
 def main():
+    # stdout carries exactly ONE line (the JSON): everything else that writes to fd 1 (e.g. NCCL's version banner) is sent
+    # to stderr; print() below writes through the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

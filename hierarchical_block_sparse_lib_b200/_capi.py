@@ -98,6 +98,7 @@ SIGNATURES = {
     "hbsm_halo_select": (_I, [_H, _I, _P, _I, _I, _I, _I, _I, C.c_double, _P, C.POINTER(_sz)]),
     "hbsm_halo_mask": (_I, [_I, _P, _P, _P, _sz, _sz, _sz, _I, C.c_double, _P]),
     "hbsm_compact_flags": (_I, [_P, _sz, _sz, C.POINTER(_sz), _sz, _P, C.POINTER(_sz)]),
+    "hbsm_halo_plan": (_I, [_H, _I, _H, _P, _P, _P, _sz, _I, _I, _P, _I, C.c_double, _P, _P, C.POINTER(_sz), C.POINTER(_P)]),
     "hbsm_halo_reserve": (_I, [_H, _sz, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "hbsm_halo_commit": (_I, [_H, _sz]),
     "hbsm_generate_decay": (_I, [_H, _I, _P, _I, C.c_uint64, _I, _I, _I]),

@@ -438,6 +438,14 @@ int hbsm_compact_flags(const uint8_t* d_flags, size_t n, size_t n_edges, const s
         compact_flags(d_flags, n, n_edges, edges, modulo, d_idx, counts);
     });
 }
+int hbsm_halo_plan(hbsm_handle A, int tA, hbsm_handle B, const uint64_t* d_keys_all, const int64_t* d_k_all,
+                   const void* d_norms_all, size_t n_all, int world, int rank, const size_t* offsets, int spamm, double tau,
+                   uint8_t* d_need, size_t* recv_counts, size_t* n_in, void** d_tail_tiles) {
+    return guarded([&] {
+        halo_plan(M(A), tA != 0, M(B), d_keys_all, d_k_all, d_norms_all, n_all, world, rank, offsets, spamm != 0, tau, d_need,
+                  recv_counts, n_in, d_tail_tiles);
+    });
+}
 int hbsm_halo_reserve(hbsm_handle h, size_t capacity, uint64_t** d_keys, void** d_norms, void** d_tiles) {
     return guarded([&] { reserve_halo(M(h), capacity, d_keys, d_norms, d_tiles); });
 }

@@ -702,6 +702,37 @@ __global__ void k_compact_idx(const uint32_t* __restrict__ flags, const uint64_t
     out[pos[e]] = (int64_t)(modulo ? e % modulo : e);
 }
 
+// halo_plan: mask with a widened copy for the scan, edge read-back through the mailbox, tail fill from the published table
+template <typename T>
+__global__ void k_halo_mask_wide(const T* __restrict__ thr, const int64_t* __restrict__ k_all, const T* __restrict__ norms_all,
+                                 size_t n_all, size_t own_lo, size_t own_hi, int spamm, T tau2, uint8_t* __restrict__ need,
+                                 uint32_t* __restrict__ wide) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_all) return;
+    bool keep = false;
+    if (i < own_lo || i >= own_hi) {
+        const T t = thr[k_all[i]];
+        keep = t >= (T)0;
+        if (keep && spamm) keep = DT<T>::mul(t, norms_all[i]) > tau2;
+    }
+    need[i] = keep ? 1 : 0;
+    wide[i] = keep ? 1u : 0u;
+}
+struct EdgeList { uint64_t at[64]; int n; };
+__global__ void k_post_edges(const uint64_t* __restrict__ pos, EdgeList edges, volatile uint64_t* mailbox) {
+    if ((int)threadIdx.x < edges.n) mailbox[threadIdx.x] = pos[edges.at[threadIdx.x]];
+    __threadfence_system();
+}
+template <typename T>
+__global__ void k_halo_tail_fill(const uint32_t* __restrict__ flags, const uint64_t* __restrict__ pos, size_t n,
+                                 const uint64_t* __restrict__ keys_all, const T* __restrict__ norms_all,
+                                 uint64_t* __restrict__ tail_keys, T* __restrict__ tail_norms) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n || !flags[e]) return;
+    tail_keys[pos[e]] = keys_all[e];
+    tail_norms[pos[e]] = norms_all[e];
+}
+
 // frob_block_trunc (H:4904-4943): a subtree is dropped iff its (recomputed) norm^2 < trunc^2.  A node's norm^2 is a sum of
 // non-negative child norm^2 with monotone rounding, so a leaf survives iff its OWN norm^2 >= trunc^2 -- the flat rule.
 __global__ void k_trunc_flags(const void* __restrict__ norms, size_t n, int is_f64, double t2d, float t2f, uint32_t* __restrict__ keep) {
@@ -1057,6 +1088,55 @@ void compact_flags(const uint8_t* d_flags, size_t n, size_t n_edges, const size_
         HB_CUDA(cudaMemcpyAsync(&at[q], pos.p + std::min(edges[q], n), sizeof(uint64_t), cudaMemcpyDeviceToHost, engine().stream));
     sync_stream();
     for (size_t q = 0; q + 1 < n_edges; ++q) counts[q] = (size_t)(at[q + 1] - at[q]);
+}
+
+// The rank-local half of the published-table protocol in one call: request thresholds of op(A), request mask over the
+// published table of op(B), receive counts per peer, and the halo tail of B filled with the keys and norms of the tiles that
+// will arrive (the tiles themselves follow over NCCL).  8 launches, one host sync, no PCIe copy.
+void halo_plan(const Matrix& A, bool tA, Matrix& B, const uint64_t* d_keys_all, const int64_t* d_k_all, const void* d_norms_all,
+               size_t n_all, int world, int rank, const size_t* offsets, bool spamm, double tau, uint8_t* d_need, size_t* recv_counts,
+               size_t* n_in_out, void** d_tail_tiles) {
+    ensure_engine();
+    Engine& e = engine();
+    if (world < 1 || world > 63 || rank < 0 || rank >= world) throw Error(HBSM_E_ARG, "hbsm_b200: halo_plan: bad world / rank");
+    if (A.dtype != B.dtype) throw Error(HBSM_E_ARG, "hbsm_b200: halo_plan: operands differ in dtype");
+    for (int q = 0; q < world; ++q) recv_counts[q] = 0;
+    *n_in_out = 0;
+    if (d_tail_tiles) *d_tail_tiles = nullptr;
+    if (n_all == 0) { commit_halo(B, 0); return; }
+    DevBuf<char> thr((size_t)A.grid_side() * A.esize());
+    halo_request(A, tA, thr.p);
+    DevBuf<uint32_t> wide(n_all);
+    DevBuf<uint64_t> pos(n_all + 1);
+    dispatch(A.dtype, [&](auto z) {
+        using T = decltype(z);
+        const T tt = (T)tau;
+        HB_LAUNCH(k_halo_mask_wide<T>, blocks_for(n_all, 256), 256, 0, (const T*)thr.p, d_k_all, (const T*)d_norms_all, n_all,
+                  offsets[rank], offsets[rank + 1], spamm ? 1 : 0, (T)(tt * tt), d_need, wide.p);
+    });
+    exclusive_scan_u32(wide.p, pos.p, n_all);
+    EdgeList el;
+    el.n = world + 1;
+    for (int q = 0; q <= world; ++q) el.at[q] = std::min(offsets[q], n_all);
+    HB_LAUNCH(k_post_edges, 1, 64, 0, pos.p, el, e.mailbox + 8);
+    sync_stream();
+    size_t n_in = 0;
+    for (int q = 0; q < world; ++q) {
+        recv_counts[q] = (size_t)(e.mailbox[8 + q + 1] - e.mailbox[8 + q]);
+        n_in += recv_counts[q];
+    }
+    *n_in_out = n_in;
+    if (n_in == 0) { commit_halo(B, 0); return; }
+    uint64_t* tk = nullptr;
+    void* tn = nullptr;
+    void* tt = nullptr;
+    reserve_halo(B, std::max(B.halo_cap, n_in > B.halo_cap ? std::max<size_t>(n_in + n_in / 4, 64) : n_in), &tk, &tn, &tt);
+    dispatch(A.dtype, [&](auto z) {
+        using T = decltype(z);
+        HB_LAUNCH(k_halo_tail_fill<T>, blocks_for(n_all, 256), 256, 0, wide.p, pos.p, n_all, d_keys_all, (const T*)d_norms_all, tk, (T*)tn);
+    });
+    commit_halo(B, n_in);
+    if (d_tail_tiles) *d_tail_tiles = tt;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -87,6 +87,9 @@ void halo_mask(int dtype, const void* d_thr, const int64_t* d_k_all, const void*
                size_t own_hi, bool spamm, double tau, uint8_t* d_need);
 void compact_flags(const uint8_t* d_flags, size_t n, size_t n_edges, const size_t* edges, size_t modulo, int64_t* d_idx,
                    size_t* counts);
+void halo_plan(const Matrix& A, bool tA, Matrix& B, const uint64_t* d_keys_all, const int64_t* d_k_all, const void* d_norms_all,
+               size_t n_all, int world, int rank, const size_t* offsets, bool spamm, double tau, uint8_t* d_need, size_t* recv_counts,
+               size_t* n_in, void** d_tail_tiles);
 void halo_select(const Matrix& B, bool tB, const void* d_thr_in, int world, int rank, uint32_t lo, uint32_t rows, bool spamm,
                  double tau, int64_t* d_send_idx, size_t* h_counts);
 void op_add(const Matrix& A, const Matrix& B, Matrix& C);

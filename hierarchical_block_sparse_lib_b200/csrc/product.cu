@@ -683,27 +683,20 @@ namespace {
 
 // per C tile: does any of its products read a halo tile of B (tile index >= n_own)?
 __global__ void k_classify_ctiles(const uint2* __restrict__ ab, const uint64_t* __restrict__ begin, size_t nct, uint32_t n_own,
-                                  uint32_t* __restrict__ own_only, uint32_t* __restrict__ needs_halo) {
+                                  uint32_t* __restrict__ own_only) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nct) return;
     bool halo = false;
     for (uint64_t p = begin[t]; p < begin[t + 1] && !halo; ++p) halo = ab[p].y >= n_own;
     own_only[t] = halo ? 0u : 1u;
-    needs_halo[t] = halo ? 1u : 0u;
 }
-__global__ void k_list_from_flags(const uint32_t* __restrict__ flags, const uint64_t* __restrict__ pos, size_t n,
-                                  uint32_t* __restrict__ out) {
+// both lists from ONE scan of the own-only flags: own tiles go to first[pos], the others to later[t - pos]
+__global__ void k_split_lists(const uint32_t* __restrict__ own_only, const uint64_t* __restrict__ pos, size_t n,
+                              uint32_t* __restrict__ first, uint32_t* __restrict__ later) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && flags[i]) out[pos[i]] = (uint32_t)i;
-}
-
-size_t list_of(const DevBuf<uint32_t>& flags, size_t n, DevBuf<uint32_t>& out) {
-    DevBuf<uint64_t> pos(n + 1);
-    exclusive_scan_u32(flags.p, pos.p, n);
-    const uint64_t total = read_scalars(pos.p + n, nullptr).first;
-    out.alloc(std::max<size_t>((size_t)total, 1));
-    if (total) HB_LAUNCH(k_list_from_flags, blocks_for(n, 256), 256, 0, flags.p, pos.p, n, out.p);
-    return (size_t)total;
+    if (i >= n) return;
+    if (own_only[i]) first[pos[i]] = (uint32_t)i;
+    else later[i - pos[i]] = (uint32_t)i;
 }
 
 // one leaf-GEMM launch over `n` C tiles: all of them (tile_list == nullptr) or the listed subset
@@ -810,11 +803,16 @@ void op_product_begin(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix
     size_t n_first = P.tl.n_ctiles;
     const bool split = defer_halo_tiles && B.n_halo > 0 && P.tl.n_products > 0;
     if (split) {   // C tiles that only read B's own tiles can start now; the others wait for the halo tiles
-        DevBuf<uint32_t> own(P.tl.n_ctiles), halo(P.tl.n_ctiles);
-        HB_LAUNCH(k_classify_ctiles, blocks_for(P.tl.n_ctiles, 256), 256, 0, P.tl.ab.p, P.tl.begin.p, P.tl.n_ctiles, (uint32_t)B.L,
-                  own.p, halo.p);
-        n_first = list_of(own, P.tl.n_ctiles, first);
-        P.n_later = list_of(halo, P.tl.n_ctiles, P.later);
+        const size_t nct = P.tl.n_ctiles;
+        DevBuf<uint32_t> own(nct);
+        DevBuf<uint64_t> pos(nct + 1);
+        HB_LAUNCH(k_classify_ctiles, blocks_for(nct, 256), 256, 0, P.tl.ab.p, P.tl.begin.p, nct, (uint32_t)B.L, own.p);
+        exclusive_scan_u32(own.p, pos.p, nct);
+        first.alloc(nct);       // sized for the worst case: no read-back before the kernels are queued
+        P.later.alloc(nct);
+        HB_LAUNCH(k_split_lists, blocks_for(nct, 256), 256, 0, own.p, pos.p, nct, first.p, P.later.p);
+        n_first = (size_t)read_scalars(pos.p + nct, nullptr).first;
+        P.n_later = nct - n_first;
     }
     P.t_task.stop();
 

@@ -407,54 +407,44 @@ def _sharded_product_overlapped(A_loc, tA, B_loc, tB, spamm, tau, group, timers,
     tr = _Trace(timers.setdefault("trace", {}) if timers is not None else None)
     t0 = time.perf_counter()
     k_all = table.k_of(bool(tB))
-    lo_r, hi_r = table.offsets[rank], table.offsets[rank + 1]
     L_r = table.counts[rank]; n_all = table.offsets[-1]
-    dt_code = _capi.HBSM_F64 if table.norms_all.dtype == torch.float64 else _capi.HBSM_F32
-    with torch.cuda.stream(ext):
-        bk, bn, bt = device_views(B_loc)
-        if bk.numel() != L_r:
-            raise RuntimeError("sharded_product: the published table of B is stale (B changed after publish())")
-        dev = bn.device
-        thr = torch.empty((grid_side,), dtype=bn.dtype, device=dev)
-        _capi.check(Lc.hbsm_halo_request(A_loc._h, int(bool(tA)), C.c_void_p(thr.data_ptr())))
-        need_u8 = torch.empty((max(n_all, 1),), dtype=torch.uint8, device=dev)
-        _capi.check(Lc.hbsm_halo_mask(dt_code, C.c_void_p(thr.data_ptr()), C.c_void_p(k_all.data_ptr()), C.c_void_p(table.norms_all.data_ptr()),
-                                      n_all, lo_r, hi_r, int(bool(spamm)), float(tau), C.c_void_p(need_u8.data_ptr())))
-        need_u8 = need_u8[:n_all]
-        ev_mask = torch.cuda.Event(); ev_mask.record(ext)
-    with torch.cuda.stream(comm):          # round 1 goes out while the engine stream keeps planning
-        comm.wait_event(ev_mask)
-        asked = torch.empty((world * L_r,), dtype=torch.uint8, device=dev)
-        dist.all_to_all_single(asked, need_u8, [L_r] * world, table.counts, group=group)
-    with torch.cuda.stream(ext):
-        recv_idx = torch.empty((max(n_all, 1),), dtype=torch.int64, device=dev)
-        e2 = (C.c_size_t * (world + 1))(*table.offsets); c2 = (C.c_size_t * world)()
-        _capi.check(Lc.hbsm_compact_flags(C.c_void_p(need_u8.data_ptr()), n_all, world + 1, e2, 0, C.c_void_p(recv_idx.data_ptr()), c2))
-        recv_counts = [int(c) for c in c2]
-        n_in = sum(recv_counts)
-        recv_idx = recv_idx[:n_in]
-        tiles_in = bt[:0]
+    b = B_loc.get_params().blocksize
+    ts = "<f8" if B_loc.dtype == np.float64 else "<f4"
+    dev = table.norms_all.device
+    if B_loc.get_n_blocks() != L_r:
+        raise RuntimeError("sharded_product: the published table of B is stale (B changed after publish())")
+    scratch = getattr(table, "_scratch", None)     # request mask out / in: buffers, not results -- reused across products
+    if scratch is None:
+        with torch.cuda.stream(ext):
+            scratch = (torch.empty((max(n_all, 1),), dtype=torch.uint8, device=dev),
+                       torch.empty((max(world * L_r, 1),), dtype=torch.uint8, device=dev),
+                       (C.c_size_t * (world + 1))(*table.offsets))
+        table._scratch = scratch
+    need_u8, asked, offs_c = scratch
+    rc = (C.c_size_t * world)(); n_in_c = C.c_size_t(0); tail = C.c_void_p()
+    # one engine call: thresholds, mask, receive counts, halo keys + norms from the table, commit (8 launches, 1 sync)
+    _capi.check(Lc.hbsm_halo_plan(A_loc._h, int(bool(tA)), B_loc._h, C.c_void_p(table.keys_all.data_ptr()), C.c_void_p(k_all.data_ptr()),
+                                  C.c_void_p(table.norms_all.data_ptr()), n_all, world, rank, offs_c, int(bool(spamm)), float(tau),
+                                  C.c_void_p(need_u8.data_ptr()), rc, C.byref(n_in_c), C.byref(tail)))
+    recv_counts = [int(c) for c in rc]
+    n_in = n_in_c.value
+    with torch.cuda.stream(comm):          # round 1 goes out while the engine stream builds the task list
+        # (hbsm_halo_plan returned with the engine stream idle, so the mask is complete: no event needed)
+        dist.all_to_all_single(asked[:world * L_r], need_u8[:n_all], [L_r] * world, table.counts, group=group)
         if n_in:
-            cap = getattr(B_loc, "_halo_cap", 0)
-            if n_in > cap:
-                cap = max(n_in + n_in // 4, 64)
-                B_loc._halo_cap = cap
-            kt, nt, tt = _tail_views(B_loc, cap)
-            bk, bn, bt = device_views(B_loc)          # a growth moved the arrays
-            torch.index_select(table.keys_all, 0, recv_idx, out=kt[:n_in])
-            torch.index_select(table.norms_all, 0, recv_idx, out=nt[:n_in])
-            tiles_in = tt[:n_in]
-        ext.synchronize()
+            tiles_in = torch.as_tensor(_DevArray(tail.value, (n_in, b * b), ts), device=dev)
+        else:
+            tiles_in = torch.empty((0, b * b), dtype=table.norms_all.dtype, device=dev)
     tr.mark("plan")
-    _capi.check(Lc.hbsm_halo_commit(B_loc._h, n_in))       # keys + norms valid; tiles arrive below
     Cm = H(A_loc.dtype)
     ok = False
     try:
         _capi.check(Lc.hbsm_product_begin(A_loc._h, int(bool(tA)), B_loc._h, int(bool(tB)), Cm._h, int(bool(spamm)), float(tau), 1, 1))
         t1 = time.perf_counter()
         with torch.cuda.stream(comm):
-            nz = torch.nonzero(asked.view(world, L_r), as_tuple=False)       # syncs the comm stream only
-            send_counts = [int(c) for c in torch.bincount(nz[:, 0], minlength=world).tolist()]
+            _, _, bt = device_views(B_loc)
+            nz = torch.nonzero(asked[:world * L_r].view(world, L_r), as_tuple=False)       # syncs the comm stream only
+            send_counts = np.bincount(nz[:, 0].cpu().numpy(), minlength=world).tolist()
             tiles_out = bt.index_select(0, nz[:, 1].contiguous())
             dist.all_to_all_single(tiles_in, tiles_out, recv_counts, send_counts, group=group)
             ev_tiles = torch.cuda.Event(); ev_tiles.record(comm)

@@ -194,6 +194,22 @@ public:
         if (no_of_resizes) *no_of_resizes = nr;
     }
     hbsm_handle handle() const { return h_; }
+    // Host-to-host multiply / SpAMM in one pipelined call (hbsm_product_from_host): A and B are sized matrices without
+    // tiles; their dense column-major tiles come from host arrays (tile t at block (a_bi[t], a_bj[t])), C's tiles go to
+    // c_tiles (room for cap_tiles tiles; c_bi/c_bj receive their block coordinates).  PCIe upload, norm refresh, leaf
+    // GEMMs and download overlap slab by slab; afterwards A, B (norms fresh) and C live on the device as usual.
+    static void product_from_host_tiles(HierarchicalBlockSparseMatrix<Treal>& A, size_t n_a, const int* a_bi, const int* a_bj,
+                                        const Treal* a_tiles, bool tA, HierarchicalBlockSparseMatrix<Treal>& B, size_t n_b,
+                                        const int* b_bi, const int* b_bj, const Treal* b_tiles, bool tB,
+                                        HierarchicalBlockSparseMatrix<Treal>& C, bool use_spamm, const Treal tau, Treal* c_tiles,
+                                        size_t cap_tiles, int* c_bi, int* c_bj, size_t* no_of_block_multiplies = NULL,
+                                        size_t* no_of_resizes = NULL) {
+        size_t nm = 0, nr = 0;
+        detail::check(hbsm_product_from_host(A.h_, n_a, a_bi, a_bj, a_tiles, tA ? 1 : 0, B.h_, n_b, b_bi, b_bj, b_tiles, tB ? 1 : 0,
+                                             C.h_, use_spamm ? 1 : 0, (double)tau, 0, c_tiles, cap_tiles, c_bi, c_bj, &nm, &nr));
+        if (no_of_block_multiplies) *no_of_block_multiplies = nm;
+        if (no_of_resizes) *no_of_resizes = nr;
+    }
 
     // ---- host-side utilities around the hot path (SURVEY 8f "next"), built on the calls above ----
     // add_scaled_identity H:1532: *this = other + alpha * I.  (The reference also writes alpha onto the diagonal of the

@@ -198,6 +198,13 @@ int hbsm_halo_mask(int dtype, const void* d_thr, const int64_t* d_k_all, const v
                    size_t own_hi, int spamm, double tau, uint8_t* d_need);
 int hbsm_compact_flags(const uint8_t* d_flags, size_t n, size_t n_edges, const size_t* edges, size_t modulo, int64_t* d_idx,
                        size_t* counts);
+/* The rank-local half of the published-table protocol in ONE call (8 launches, one host sync): request thresholds of
+ * op(A); d_need[t] as hbsm_halo_mask (the mask to send to the owners; offsets[q]..offsets[q+1] = rank q's tiles in the
+ * table, world + 1 entries); recv_counts[q] = tiles to expect from peer q; B's halo tail is reserved, filled with the keys
+ * and norms of those n_in tiles (table order = peer-major) and committed; *d_tail_tiles = where NCCL must deliver them. */
+int hbsm_halo_plan(hbsm_handle A, int tA, hbsm_handle B, const uint64_t* d_keys_all, const int64_t* d_k_all,
+                   const void* d_norms_all, size_t n_all, int world, int rank, const size_t* offsets, int spamm, double tau,
+                   uint8_t* d_need, size_t* recv_counts, size_t* n_in, void** d_tail_tiles);
 int hbsm_halo_reserve(hbsm_handle h, size_t capacity, uint64_t** d_keys, void** d_norms, void** d_tiles);
 int hbsm_halo_commit(hbsm_handle h, size_t n_halo);
 /* banded decay generator a_ij = (0.5+0.5u(seed,i,j)) * table[|i-j|], |i-j| <= W (table has W+1 entries, e.g.

@@ -309,6 +309,34 @@ void run() {
         std::vector<double> zd = dense(Z);
         for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) REQUIRE(zd[i * n + j] == 0.0);   // upper triangular
     }
+    // ---- host-to-host product in one pipelined call (engine extra): same result as assign + multiply ----
+    {
+        const int n = 24, b = 4, g = n / b;
+        typename M::Params p; p.blocksize = b;
+        std::vector<int> bi, bj;
+        std::vector<T> tiles;
+        for (int i = 0; i < g; ++i) for (int j = 0; j < g; ++j) {
+            if (std::abs(i - j) > 1) continue;
+            bi.push_back(i); bj.push_back(j);
+            for (int e = 0; e < b * b; ++e) tiles.push_back((T)(1 + ((i * 7 + j * 3 + e) % 5)));   // small integers: exact in any order
+        }
+        M A2, B2, C2;
+        A2.set_params(p); A2.resize(n, n); B2.set_params(p); B2.resize(n, n);
+        std::vector<T> ct((size_t)g * g * b * b);
+        std::vector<int> cbi(g * g), cbj(g * g);
+        size_t nm = 0, nr = 0;
+        M::product_from_host_tiles(A2, bi.size(), bi.data(), bj.data(), tiles.data(), false, B2, bi.size(), bi.data(), bj.data(),
+                                   tiles.data(), true, C2, false, (T)0, ct.data(), (size_t)g * g, cbi.data(), cbj.data(), &nm, &nr);
+        M C3;
+        size_t nm3 = 0, nr3 = 0;
+        M::multiply(A2, false, B2, true, C3, &nm3, &nr3);
+        REQUIRE(nm == nm3 && nr == nr3 && nr == C2.get_n_blocks());
+        std::vector<double> d2 = dense(C2), d3 = dense(C3);
+        REQUIRE(d2 == d3);
+        for (size_t t = 0; t < nr; ++t)   // host copy: column-major tiles labelled by block coordinates
+            for (int c = 0; c < b; ++c) for (int r = 0; r < b; ++r)
+                REQUIRE((double)ct[t * b * b + c * b + r] == d3[(size_t)(cbi[t] * b + r) * n + cbj[t] * b + c]);
+    }
     // ---- value semantics of the drop-in: deep copy ----
     {
         M C1(A);
