@@ -112,10 +112,10 @@ struct F32Cfg {
 };
 
 struct F32Header {
-    uint64_t full_raw[8], full_cvt[8], empty[8], tmem_full[2], tmem_empty[2];
+    uint64_t full_raw[8], full_cvt[8], empty[8], tmem_full[8], tmem_empty[8];   // the 3-MMA kernel uses 2 accumulator sets
     GemmMeta meta[8];
-    int acc_tile[2];
-    int acc_flags[2];     // 1 = first product of its C tile, 2 = last product, 4 = no more work
+    int acc_tile[8];
+    int acc_flags[8];     // 1 = first product of its C tile, 2 = last product, 4 = no more work
     uint32_t tmem_base;
 };
 
@@ -380,7 +380,11 @@ struct Q4Cfg {
     static constexpr int STG_BYTES = 2 * EPI_H * 32 * 32 * 4;   // lo-row partial tiles handed to the hi-row warps
     static constexpr int HEADER_BYTES = 1024;
     static constexpr int SMEM_BYTES = 1024 + HEADER_BYTES + NST * STAGE_BYTES + STG_BYTES;
-    static constexpr int TMEM_COLS = 2 * NN;                 // two accumulator sets (128 or 256 columns)
+    // Accumulator ring: every leaf product gets its own TMEM accumulator set (NN columns); all 512 columns are used (8 sets
+    // at 32-leaves, 4 at 64) so that the issue -> commit -> drain -> release round trip of one product (several hundred
+    // clocks, longer than a 32-leaf product's MMAs) overlaps with the MMAs of the next ones.
+    static constexpr int NSETS = 512 / NN;
+    static constexpr int TMEM_COLS = NSETS * NN;
     static constexpr int THREADS = 512;
     static constexpr int CVT_WARPS = 4;
     static constexpr int KSTEPS = KC / 8;
@@ -406,7 +410,7 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             mbar_init(smem_u32(&hd->full_cvt[s]), Cfg::CVT_WARPS);
             mbar_init(smem_u32(&hd->empty[s]), 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < Cfg::NSETS; ++a) {
             mbar_init(smem_u32(&hd->tmem_full[a]), 1);
             mbar_init(smem_u32(&hd->tmem_empty[a]), Cfg::EPI_WARPS);
         }
@@ -419,44 +423,60 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const uint32_t tmem_base = hd->tmem_base;
 
     if (warp == 0) {
-        // ===== TMA producer: raw operand slabs land in the "hi" positions of the stacked layout =====
+        // ===== TMA producer: raw operand slabs land in the "hi" positions of the stacked layout.  The warp walks the task
+        // list together (next C tile claimed one tile ahead, 32 (A tile, B tile) pairs per coalesced load): a 32-leaf
+        // product lasts a few hundred clocks, less than one dependent index fetch; lane 0 issues the copies =====
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
-            uint32_t it = 0;
-            for (;;) {
-                unsigned tile = atomicAdd(next_tile, 1u);
-                if (tile >= n_ctiles) break;
-                if (tile_list) tile = tile_list[tile];
-                const uint64_t p0 = begin[tile], p1 = begin[tile + 1];
-                uint2 t = ab[p0];
-                for (uint64_t p = p0; p < p1; ++p, ++it) {
-                    const uint2 tn = (p + 1 < p1) ? ab[p + 1] : t;
-                    const uint32_t s = it % NST, ph = (it / NST) & 1u;
-                    mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
-                    const uint32_t fb = smem_u32(&hd->full_raw[s]);
-                    hd->meta[s].ctile = (int)tile;
-                    hd->meta[s].flags = (p == p0 ? 1 : 0) | (p + 1 == p1 ? 2 : 0);
-                    mbar_arrive_expect_tx(fb, 2 * Cfg::OPER_BYTES);
-                    const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
-                    const uint32_t sb = sa + 2 * Cfg::OPER_BYTES;
-                    if (TA) {   // K-major: [BS mn][32 k] slabs, hi slab j at 2j * SLAB_K
+        }
+        uint32_t it = 0;
+        unsigned claimed = 0;
+        if (lane == 0) claimed = atomicAdd(next_tile, 1u);
+        for (;;) {
+            unsigned tile = __shfl_sync(0xffffffffu, claimed, 0);
+            if (tile >= n_ctiles) break;
+            if (lane == 0) claimed = atomicAdd(next_tile, 1u);   // consumed at the top of the next round
+            if (tile_list) tile = tile_list[tile];
+            const uint64_t bnd = begin[tile + (lane & 1u)];
+            const uint64_t p0 = __shfl_sync(0xffffffffu, bnd, 0), p1 = __shfl_sync(0xffffffffu, bnd, 1);
+            for (uint64_t pb = p0; pb < p1; pb += 32) {
+                const uint2 mine = (pb + lane < p1) ? ab[pb + lane] : make_uint2(0u, 0u);
+                const int cnt = (int)((p1 - pb) < 32 ? (p1 - pb) : 32);
+                for (int j = 0; j < cnt; ++j, ++it) {
+                    uint2 t;
+                    t.x = __shfl_sync(0xffffffffu, mine.x, j);
+                    t.y = __shfl_sync(0xffffffffu, mine.y, j);
+                    if (lane == 0) {
+                        const uint64_t p = pb + j;
+                        const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                        mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
+                        const uint32_t fb = smem_u32(&hd->full_raw[s]);
+                        hd->meta[s].ctile = (int)tile;
+                        hd->meta[s].flags = (p == p0 ? 1 : 0) | (p + 1 == p1 ? 2 : 0);
+                        mbar_arrive_expect_tx(fb, 2 * Cfg::OPER_BYTES);
+                        const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
+                        const uint32_t sb = sa + 2 * Cfg::OPER_BYTES;
+                        if (TA) {   // K-major: [BS mn][32 k] slabs, hi slab j at 2j * SLAB_K
 #pragma unroll
-                        for (int j = 0; j < KC / 32; ++j) tma_box_g2s(sa + 2 * j * Cfg::SLAB_K, &mapA, 32 * j, (int)t.x * BS, fb);
-                    } else {    // MN-major: [KC k][32 mn] slabs, hi slabs first
+                            for (int jj = 0; jj < KC / 32; ++jj) tma_box_g2s(sa + 2 * jj * Cfg::SLAB_K, &mapA, 32 * jj, (int)t.x * BS, fb);
+                        } else {    // MN-major: [KC k][32 mn] slabs, hi slabs first
 #pragma unroll
-                        for (int j = 0; j < BS / 32; ++j) tma_box_g2s(sa + j * Cfg::SLAB_MN, &mapA, 32 * j, (int)t.x * BS, fb);
+                            for (int jj = 0; jj < BS / 32; ++jj) tma_box_g2s(sa + jj * Cfg::SLAB_MN, &mapA, 32 * jj, (int)t.x * BS, fb);
+                        }
+                        if (TB) {
+#pragma unroll
+                            for (int jj = 0; jj < BS / 32; ++jj) tma_box_g2s(sb + jj * Cfg::SLAB_MN, &mapB, 32 * jj, (int)t.y * BS, fb);
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < KC / 32; ++jj) tma_box_g2s(sb + 2 * jj * Cfg::SLAB_K, &mapB, 32 * jj, (int)t.y * BS, fb);
+                        }
                     }
-                    if (TB) {
-#pragma unroll
-                        for (int j = 0; j < BS / 32; ++j) tma_box_g2s(sb + j * Cfg::SLAB_MN, &mapB, 32 * j, (int)t.y * BS, fb);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < KC / 32; ++j) tma_box_g2s(sb + 2 * j * Cfg::SLAB_K, &mapB, 32 * j, (int)t.y * BS, fb);
-                    }
-                    t = tn;
+                    __syncwarp();
                 }
             }
+        }
+        if (lane == 0) {
             const uint32_t s = it % NST, ph = (it / NST) & 1u;
             mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
             hd->meta[s].ctile = -1;
@@ -471,12 +491,14 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             constexpr uint32_t A_LBO = TA ? 16 : Cfg::SLAB_MN, B_LBO = TB ? Cfg::SLAB_MN : 16;
             constexpr uint32_t A_SBO = TA ? 1024 : 512, B_SBO = TB ? 512 : 1024;
             constexpr uint32_t A_LT = TA ? 2 : 1, B_LT = TB ? 1 : 2;
+            // (Interleaving the K-steps of consecutive products over their accumulator sets was tried and is SLOWER:
+            // 100 -> 72 TF/s at 64-leaves, 23.6 -> 20.8 at 32 -- the issuer then waits for whole batches of stages.)
             for (uint32_t it = 0;; ++it) {
                 const uint32_t s = it % NST, ph = (it / NST) & 1u;
                 mbar_wait(smem_u32(&hd->full_cvt[s]), ph);
                 const GemmMeta m = hd->meta[s];
-                const uint32_t as = it & 1u;
-                mbar_wait(smem_u32(&hd->tmem_empty[as]), ((it >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator set
+                const uint32_t as = it % Cfg::NSETS;
+                mbar_wait(smem_u32(&hd->tmem_empty[as]), ((it / Cfg::NSETS) & 1u) ^ 1u);   // epilogue drained this accumulator set
                 if (m.flags & 4) {
                     hd->acc_flags[as] = 4;
                     __threadfence_block();
@@ -545,8 +567,8 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         float* my_stg = stg + (size_t)(((q & 1) * Cfg::EPI_H + h) * 32 * 32);
         float acc[32];
         for (uint32_t pc = 0;; ++pc) {
-            const uint32_t as = pc & 1u;
-            mbar_wait(smem_u32(&hd->tmem_full[as]), (pc >> 1) & 1u);
+            const uint32_t as = pc % Cfg::NSETS;
+            mbar_wait(smem_u32(&hd->tmem_full[as]), (pc / Cfg::NSETS) & 1u);
             const int flags = hd->acc_flags[as];
             if (flags & 4) break;
             const int ctile = hd->acc_tile[as];

@@ -413,44 +413,61 @@ k_gemm_f64_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
 
     if (warp == Cfg::CONSUMER_WARPS) {
-        // ===== producer: one elected lane walks the task list and issues two TMA tile copies per chunk =====
+        // ===== producer: the warp walks the task list together -- the next work unit is claimed one unit ahead and 32
+        // (A tile, B tile) pairs arrive per coalesced load, so no index fetch latency sits between two TMA issues (at
+        // 32-leaves a product lasts ~500 clk, less than one dependent L2 round trip) -- and lane 0 issues the copies =====
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
-            uint32_t it = 0;
-            for (;;) {
-                const unsigned unit = atomicAdd(next_tile, 1u);       // work unit = (C tile, sub-tile)
-                if (unit >= n_ctiles * (unsigned)(S * S)) break;
-                const unsigned sub = unit % (S * S);
-                const unsigned tile = tile_list ? tile_list[unit / (S * S)] : unit / (S * S);
-                const int cunit = (int)(tile * (S * S) + sub);
-                const int si = (int)(sub % S) * BS, sj = (int)(sub / S) * BS;
-                const uint64_t p0 = begin[tile], p1 = begin[tile + 1];
-                uint2 t = ab[p0];
-                for (uint64_t p = p0; p < p1; ++p) {
-                    const uint2 tn = (p + 1 < p1) ? ab[p + 1] : t;   // prefetch the next pair
+        }
+        uint32_t it = 0;
+        const unsigned n_units = n_ctiles * (unsigned)(S * S);
+        unsigned claimed = 0;
+        if (lane == 0) claimed = atomicAdd(next_tile, 1u);       // work unit = (C tile, sub-tile)
+        for (;;) {
+            const unsigned unit = __shfl_sync(0xffffffffu, claimed, 0);
+            if (unit >= n_units) break;
+            if (lane == 0) claimed = atomicAdd(next_tile, 1u);   // consumed at the top of the next round
+            const unsigned sub = unit % (S * S);
+            const unsigned tile = tile_list ? tile_list[unit / (S * S)] : unit / (S * S);
+            const int cunit = (int)(tile * (S * S) + sub);
+            const int si = (int)(sub % S) * BS, sj = (int)(sub / S) * BS;
+            const uint64_t bnd = begin[tile + (lane & 1u)];
+            const uint64_t p0 = __shfl_sync(0xffffffffu, bnd, 0), p1 = __shfl_sync(0xffffffffu, bnd, 1);
+            for (uint64_t pb = p0; pb < p1; pb += 32) {
+                const uint2 mine = (pb + lane < p1) ? ab[pb + lane] : make_uint2(0u, 0u);
+                const int cnt = (int)((p1 - pb) < 32 ? (p1 - pb) : 32);
+                for (int j = 0; j < cnt; ++j) {
+                    uint2 t;
+                    t.x = __shfl_sync(0xffffffffu, mine.x, j);
+                    t.y = __shfl_sync(0xffffffffu, mine.y, j);
+                    if (lane == 0) {
+                        const uint64_t p = pb + j;
 #pragma unroll 1
-                    for (int kc = 0; kc < S * Cfg::NCHUNK; ++kc, ++it) {
-                        const uint32_t s = it % NST, ph = (it / NST) & 1u;
-                        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-                        const uint32_t fb = smem_u32(&full_bar[s]);
-                        int fl = 0;
-                        if (p == p0 && kc == 0) fl |= 1;
-                        if (p + 1 == p1 && kc == S * Cfg::NCHUNK - 1) fl |= 2;
-                        meta[s].ctile = cunit;
-                        meta[s].flags = fl;
-                        mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
-                        const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
-                        const uint32_t sb = sa + Cfg::CHUNK_ELEMS * 8;
-                        const int k0 = kc * KC;   // position along the leaf's full contraction dimension
-                        if (TA) tma_tile_g2s(sa, &mapA, 0, si, k0 / 4, (int)t.x, fb);   // k along leaf rows
-                        else    tma_tile_g2s(sa, &mapA, 0, k0, si / 4, (int)t.x, fb);   // k along leaf columns
-                        if (TB) tma_tile_g2s(sb, &mapB, 0, k0, sj / 4, (int)t.y, fb);
-                        else    tma_tile_g2s(sb, &mapB, 0, sj, k0 / 4, (int)t.y, fb);
+                        for (int kc = 0; kc < S * Cfg::NCHUNK; ++kc, ++it) {
+                            const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                            mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                            const uint32_t fb = smem_u32(&full_bar[s]);
+                            int fl = 0;
+                            if (p == p0 && kc == 0) fl |= 1;
+                            if (p + 1 == p1 && kc == S * Cfg::NCHUNK - 1) fl |= 2;
+                            meta[s].ctile = cunit;
+                            meta[s].flags = fl;
+                            mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
+                            const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
+                            const uint32_t sb = sa + Cfg::CHUNK_ELEMS * 8;
+                            const int k0 = kc * KC;   // position along the leaf's full contraction dimension
+                            if (TA) tma_tile_g2s(sa, &mapA, 0, si, k0 / 4, (int)t.x, fb);   // k along leaf rows
+                            else    tma_tile_g2s(sa, &mapA, 0, k0, si / 4, (int)t.x, fb);   // k along leaf columns
+                            if (TB) tma_tile_g2s(sb, &mapB, 0, k0, sj / 4, (int)t.y, fb);
+                            else    tma_tile_g2s(sb, &mapB, 0, sj, k0 / 4, (int)t.y, fb);
+                        }
                     }
-                    t = tn;
+                    __syncwarp();
                 }
             }
+        }
+        if (lane == 0) {
             const uint32_t s = it % NST, ph = (it / NST) & 1u;
             mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
             meta[s].ctile = -1;

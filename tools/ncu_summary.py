@@ -22,6 +22,9 @@ KEEP = [
     "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "TPC.TriageCompute.sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "TPC.TriageCompute.sm__cycles_active.avg",
+    "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
     "sm__inst_executed_pipe_tensor.sum", "sm__inst_executed_pipe_uniform.sum",
     "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
