@@ -54,6 +54,7 @@ SIGNATURES = {
     "hbsm_assign_tiles": (_I, [_H, _sz, _P, _P, _P]),
     "hbsm_get_values": (_I, [_H, _sz, _P, _P, _P]),
     "hbsm_get_all_values": (_I, [_H, _sz, _P, _P, _P, C.POINTER(_sz)]),
+    "hbsm_export_tile": (_I, [_H, _I, _I, _P, C.POINTER(_I)]),
     "hbsm_nnz": (_I, [_H, C.POINTER(_sz)]),
     "hbsm_n_blocks": (_I, [_H, C.POINTER(_sz)]),
     "hbsm_get_n_block_multiplications": (_I, [_H, C.POINTER(_sz)]),

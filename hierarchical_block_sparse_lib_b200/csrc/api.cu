@@ -137,6 +137,12 @@ int hbsm_get_values(hbsm_handle h, size_t n, const int* rows, const int* cols, v
 int hbsm_get_all_values(hbsm_handle h, size_t cap, int* rows, int* cols, void* vals, size_t* n) {
     return guarded([&] { *n = get_all_values(M(h), cap, rows, cols, vals); });
 }
+int hbsm_export_tile(hbsm_handle h, int bi, int bj, void* host_tile, int* found) {
+    return guarded([&] {
+        if (bi < 0 || bj < 0) throw Error(HBSM_E_ARG, "hbsm_b200: export_tile: negative block coordinate");
+        *found = export_tile(M(h), (uint32_t)bi, (uint32_t)bj, host_tile) ? 1 : 0;
+    });
+}
 int hbsm_nnz(hbsm_handle h, size_t* out) {
     return guarded([&] { *out = count_nnz(M(h)); });
 }

@@ -932,6 +932,26 @@ void get_values(const Matrix& A, size_t n, const int* rows, const int* cols, voi
     sync_stream();
 }
 
+// one tile by block coordinates (parity hook: sample C tiles at sizes where exporting everything is too much)
+namespace {
+__global__ void k_find_one(const uint64_t* __restrict__ keys, size_t n, uint64_t key, volatile uint64_t* mailbox) {
+    mailbox[0] = (uint64_t)find_key(keys, n, key);
+    __threadfence_system();
+}
+}  // namespace
+bool export_tile(const Matrix& A, uint32_t bi, uint32_t bj, void* host_buf) {
+    if (A.empty() || A.L == 0) return false;
+    ensure_engine();
+    Engine& e = engine();
+    HB_LAUNCH(k_find_one, 1, 1, 0, A.keys.p, A.L, A.vdepth() == 0 ? 0ull : morton_encode(bi, bj), e.mailbox + 4);
+    sync_stream();
+    const long long at = (long long)e.mailbox[4];
+    if (at < 0) return false;
+    HB_CUDA(cudaMemcpyAsync(host_buf, A.tiles.p + (size_t)at * A.tile_bytes(), A.tile_bytes(), cudaMemcpyDeviceToHost, e.stream));
+    sync_stream();
+    return true;
+}
+
 static void tile_nnz_counts(const Matrix& A, DevBuf<uint32_t>& cnt) {
     cnt.alloc(A.L);
     dispatch(A.dtype, [&](auto z) {

@@ -74,6 +74,7 @@ void assign_tiles_device(Matrix& A, size_t n_tiles, const uint64_t* d_keys, cons
 void get_values(const Matrix& A, size_t n, const int* rows, const int* cols, void* out);
 size_t get_all_values(const Matrix& A, size_t cap, int* rows, int* cols, void* vals);
 size_t count_nnz(const Matrix& A);
+bool export_tile(const Matrix& A, uint32_t bi, uint32_t bj, void* host_buf);   // false = no such tile
 void compute_leaf_norms(const Matrix& A, void* d_out);   // bit-exact sequential sum per leaf (H:646-652)
 void compute_leaf_norms_range(const Matrix& A, size_t t0, size_t cnt, void* d_out_base);
 double hierarchical_norm(const Matrix& A, const void* d_leaf_norms);   // root value of H:3918-3923 / H:656-662

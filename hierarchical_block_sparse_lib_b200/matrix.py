@@ -257,6 +257,14 @@ class HierarchicalBlockSparseMatrix:
             check(lib().hbsm_export_leaves(self._h, n, _ptr(bi), _ptr(bj), _ptr(nrm), _ptr(t), C.byref(m)))
         return bi, bj, nrm, t
 
+    def get_tile(self, bi, bj):
+        """Dense b x b block at block coordinates (bi, bj) as a (row, col) array; None if the tile does not exist."""
+        b = self.get_params().blocksize
+        buf = np.zeros(b * b, self.dtype)
+        found = C.c_int(0)
+        check(lib().hbsm_export_tile(self._h, int(bi), int(bj), _ptr(buf), C.byref(found)))
+        return buf.reshape(b, b).T.copy() if found.value else None
+
     def to_dense(self):
         m, n = self.get_n_rows(), self.get_n_cols()
         b = self.get_params().blocksize

@@ -79,6 +79,8 @@ int hbsm_assign_coo(hbsm_handle h, size_t n, const int* rows, const int* cols, c
 int hbsm_assign_tiles(hbsm_handle h, size_t n_tiles, const int* bi, const int* bj, const void* tiles);
 int hbsm_get_values(hbsm_handle h, size_t n, const int* rows, const int* cols, void* out);      /* H:1012 */
 int hbsm_get_all_values(hbsm_handle h, size_t cap, int* rows, int* cols, void* vals, size_t* n); /* H:1034; cap=0 -> count */
+/* parity hook: the dense column-major tile at block coordinates (bi, bj) -> host_tile (b*b elements); *found = 0 if absent */
+int hbsm_export_tile(hbsm_handle h, int bi, int bj, void* host_tile, int* found);
 int hbsm_nnz(hbsm_handle h, size_t* out);                 /* H:985 */
 int hbsm_n_blocks(hbsm_handle h, size_t* out);            /* H:7311 */
 int hbsm_get_n_block_multiplications(hbsm_handle h, size_t* out);   /* H:218 */
