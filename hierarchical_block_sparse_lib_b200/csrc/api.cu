@@ -190,7 +190,9 @@ int hbsm_product_begin(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle
         o.spamm = spamm != 0;
         o.tau = tau;
         o.updated = updated != 0;
-        op_product_begin(M(A), tA != 0, M(B), tB != 0, M(C), o, defer_halo_tiles != 0);
+        // defer_halo_tiles: 1 = launch the own-only C tiles now; 2 = plan only, hbsm_product_finish launches them too (so that a
+        // transfer queued in between gets its SMs before the persistent leaf GEMM occupies all of them)
+        op_product_begin(M(A), tA != 0, M(B), tB != 0, M(C), o, defer_halo_tiles != 0, defer_halo_tiles != 2, defer_halo_tiles == 2);
     });
 }
 int hbsm_product_finish(hbsm_handle C, void* cuda_event_or_null, size_t* n_block_multiplies, size_t* n_resizes) {

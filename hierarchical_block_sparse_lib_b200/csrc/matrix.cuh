@@ -128,7 +128,7 @@ void op_product(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, c
 // B's own tiles (when defer_halo_tiles and B has a committed halo whose TILES are still in flight); finish waits for
 // `wait_for` (may be null), computes the remaining C tiles and completes C.  One product in flight at a time.
 void op_product_begin(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, const ProductOpts& o, bool defer_halo_tiles,
-                      bool launch = true);
+                      bool launch = true, bool launch_in_finish = false);
 void op_product_to_host(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, const ProductOpts& o, void* host_tiles,
                         size_t cap_tiles, int n_chunks, size_t* n_mults, size_t* n_blocks);
 void op_product_finish(Matrix& C, cudaEvent_t wait_for, size_t* n_mults, size_t* n_blocks);

@@ -775,6 +775,9 @@ struct PendingProduct {
     DevBuf<char> ct;
     DevBuf<uint32_t> later;      // C tiles whose products read halo tiles: computed by finish
     size_t n_later = 0;
+    DevBuf<uint32_t> first;      // the other C tiles, when their launch was left to finish as well (launch_in_finish)
+    size_t n_first = 0;
+    bool first_pending = false, first_is_list = false;
     uint64_t launches0 = 0;
     EventTimer t_total, t_norm, t_index, t_task, t_gemm, t_gemm2;
 };
@@ -786,7 +789,7 @@ PendingProduct& pending() {
 }  // namespace
 
 void op_product_begin(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, const ProductOpts& o, bool defer_halo_tiles,
-                      bool launch) {
+                      bool launch, bool launch_in_finish) {
     ensure_engine();   // before pending(): its event timers must be created on the engine's device
     PendingProduct& P = pending();
     if (P.active) throw Error(HBSM_E_ARG, "hbsm_b200: a product is already in flight (finish it first)");
@@ -816,8 +819,10 @@ void op_product_begin(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix
     P.tl = TaskList();
     build_tasks(A, tA, B, tB, o, kbits, P.tl, false);
     P.n_later = 0;
-    DevBuf<uint32_t> first;
+    DevBuf<uint32_t>& first = P.first;
+    first.release();
     size_t n_first = P.tl.n_ctiles;
+    P.first_pending = false;
     const bool split = defer_halo_tiles && B.n_halo > 0 && P.tl.n_products > 0;
     if (split) {   // C tiles that only read B's own tiles can start now; the others wait for the halo tiles
         const size_t nct = P.tl.n_ctiles;
@@ -837,6 +842,7 @@ void op_product_begin(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix
     if (P.tl.n_products > 0) {
         P.ct.alloc(P.tl.n_ctiles * C.tile_bytes());
         if (launch) launch_leaf_gemm(A, tA, B, tB, P.tl, split ? first.p : nullptr, n_first, P.ct.p);
+        else if (launch_in_finish) { P.first_pending = true; P.first_is_list = split; P.n_first = n_first; }
     }
     P.t_gemm.stop();
     P.A = &A; P.B = &B; P.C = &C; P.tA = tA; P.tB = tB;
@@ -848,6 +854,12 @@ void op_product_finish(Matrix& C, cudaEvent_t wait_for, size_t* n_mults, size_t*
     if (!P.active || P.C != &C) throw Error(HBSM_E_ARG, "hbsm_b200: product_finish without a matching product_begin");
     Engine& e = engine();
     P.active = false;
+    if (P.first_pending) {   // begin left every launch to us: own-only tiles now, the halo readers once `wait_for` has fired
+        P.t_gemm.start();
+        launch_leaf_gemm(*P.A, P.tA, *P.B, P.tB, P.tl, P.first_is_list ? P.first.p : nullptr, P.n_first, P.ct.p);
+        P.t_gemm.stop();
+        P.first_pending = false;
+    }
     if (wait_for) HB_CUDA(cudaStreamWaitEvent(e.stream, wait_for, 0));   // e.g. the NCCL transfer of the halo tiles
     P.t_gemm2.start();
     if (P.n_later > 0) launch_leaf_gemm(*P.A, P.tA, *P.B, P.tB, P.tl, P.later.p, P.n_later, P.ct.p);
@@ -862,6 +874,7 @@ void op_product_finish(Matrix& C, cudaEvent_t wait_for, size_t* n_mults, size_t*
     P.t_total.stop();
     sync_stream();
     P.later.release();
+    P.first.release();
     C.n_mults = P.tl.n_products;   // H:2194 / H:3984
     if (n_mults) *n_mults = P.tl.n_products;
     if (n_blocks) *n_blocks = C.L;   // get_n_blocks(), H:7311
@@ -885,7 +898,7 @@ void op_product_abort() {
     if (!P.active) return;
     P.active = false;
     cudaStreamSynchronize(engine().stream);
-    P.tl = TaskList(); P.ct.release(); P.later.release();
+    P.tl = TaskList(); P.ct.release(); P.later.release(); P.first.release(); P.first_pending = false;
 }
 
 // product whose C tiles stream to HOST memory while later tiles are still being computed: the leaf GEMM is launched in
@@ -897,7 +910,7 @@ void op_product_to_host(const Matrix& A, bool tA, const Matrix& B, bool tB, Matr
     Engine& e = engine();
     static cudaStream_t copy_stream = nullptr;
     if (!copy_stream) HB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-    op_product_begin(A, tA, B, tB, C, o, /*defer_halo_tiles=*/false, /*launch=*/false);
+    op_product_begin(A, tA, B, tB, C, o, /*defer_halo_tiles=*/false, /*launch=*/false, /*launch_in_finish=*/false);
     PendingProduct& P = pending();
     const size_t nct = P.tl.n_ctiles;
     bool streamed = false;
@@ -1273,7 +1286,7 @@ void op_product_from_host(Matrix& A, const HostTiles& ha, bool tA, Matrix& B, co
 
 void op_product(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix& C, const ProductOpts& o, size_t* n_mults,
                 size_t* n_blocks) {
-    op_product_begin(A, tA, B, tB, C, o, false, true);
+    op_product_begin(A, tA, B, tB, C, o, false, true, false);
     op_product_finish(C, nullptr, n_mults, n_blocks);
 }
 

@@ -25,7 +25,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-TRACE = bool(int(os.environ.get("HBSM_SHARD_TRACE", "0")))
+TRACE = int(os.environ.get("HBSM_SHARD_TRACE", "0"))    # 1 = synchronising phase timer, 2 = host timestamps only (no syncs)
 
 
 class _Trace:
@@ -38,7 +38,7 @@ class _Trace:
     def mark(self, name):
         if self.sink is None:
             return
-        if torch.cuda.is_available():
+        if TRACE == 1 and torch.cuda.is_available():
             torch.cuda.synchronize()
         now = time.perf_counter()
         self.sink[name] = self.sink.get(name, 0.0) + (now - self.t)
@@ -390,8 +390,9 @@ def publish(B_loc, group=None):
 def _sharded_product_overlapped(A_loc, tA, B_loc, tB, spamm, tau, group, timers, table):
     """Published-table protocol with the tile transfer hidden behind the leaf GEMMs that need no remote tile:
 
-      engine stream : request, mask, recv list | halo keys+norms from the table | task list | GEMM(own-only C tiles) ...... GEMM(rest)
-      comm stream   :            a2a(request masks) ............ send list, pack, a2a(tiles -> halo tail) --event--^
+      engine stream : hbsm_halo_plan (mask, recv counts, halo keys+norms) | line index, task list, split | GEMM(own-only C tiles) | GEMM(rest)
+      comm stream   :                 a2a(request masks) ................... send list, pack, a2a(tiles -> halo tail) -----event----^
+    (the tile transfer is queued before the first GEMM launch and runs beside it)
 
     The task list needs only keys and norms of the halo tiles, and those are known locally from the published table."""
     from . import _capi
@@ -428,34 +429,67 @@ def _sharded_product_overlapped(A_loc, tA, B_loc, tB, spamm, tau, group, timers,
                                   C.c_void_p(need_u8.data_ptr()), rc, C.byref(n_in_c), C.byref(tail)))
     recv_counts = [int(c) for c in rc]
     n_in = n_in_c.value
-    with torch.cuda.stream(comm):          # round 1 goes out while the engine stream builds the task list
-        # (hbsm_halo_plan returned with the engine stream idle, so the mask is complete: no event needed)
-        dist.all_to_all_single(asked[:world * L_r], need_u8[:n_all], [L_r] * world, table.counts, group=group)
-        if n_in:
-            tiles_in = torch.as_tensor(_DevArray(tail.value, (n_in, b * b), ts), device=dev)
-        else:
-            tiles_in = torch.empty((0, b * b), dtype=table.norms_all.dtype, device=dev)
-    tr.mark("plan")
+    tr.mark("halo_plan")
+    # The exchange (both all-to-alls, the send list, the pack) runs on a helper THREAD with its own stream while this thread
+    # builds the task list through the C ABI (ctypes drops the GIL): the two host-side chains, each with its own syncs,
+    # overlap instead of adding up.  All collectives of a product are issued by that one thread, in the same order on
+    # every rank.  HBSM_SHARD_COMM_THREAD=0 runs the same steps inline.
+    if n_in:
+        tiles_in = torch.as_tensor(_DevArray(tail.value, (n_in, b * b), ts), device=dev)
+    else:
+        tiles_in = torch.empty((0, b * b), dtype=table.norms_all.dtype, device=dev)
+    _, _, bt = device_views(B_loc)
+    dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+
+    def exchange():
+        torch.cuda.set_device(dev_index)            # the current device is per thread
+        with torch.cuda.stream(comm):
+            # (hbsm_halo_plan returned with the engine stream idle, so the mask is complete: no event needed)
+            dist.all_to_all_single(asked[:world * L_r], need_u8[:n_all], [L_r] * world, table.counts, group=group)
+            nz = torch.nonzero(asked[:world * L_r].view(world, L_r), as_tuple=False)       # syncs the comm stream only
+            counts = np.bincount(nz[:, 0].cpu().numpy(), minlength=world).tolist()
+            tiles_out = bt.index_select(0, nz[:, 1].contiguous())
+            dist.all_to_all_single(tiles_in, tiles_out, recv_counts, counts, group=group)
+            ev = torch.cuda.Event(); ev.record(comm)
+        return counts, ev, tiles_out
+
+    use_thread = os.environ.get("HBSM_SHARD_COMM_THREAD", "1") == "1"
+    fut = None
+    if use_thread:
+        pool = getattr(sharded_product, "_comm_pool", None)
+        if pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="hbsm-comm")
+            sharded_product._comm_pool = pool
+        fut = pool.submit(exchange)
+    tr.mark("exchange_submit")
     Cm = H(A_loc.dtype)
     ok = False
+    send_counts = []
     try:
-        _capi.check(Lc.hbsm_product_begin(A_loc._h, int(bool(tA)), B_loc._h, int(bool(tB)), Cm._h, int(bool(spamm)), float(tau), 1, 1))
+        # plan only (mode 2): the all-to-all of the tiles is queued BEFORE the first leaf GEMM, whose persistent CTAs would
+        # otherwise hold every SM until they drain (HBSM_SHARD_GEMM_FIRST=1 restores the old order for comparison)
+        mode = 1 if os.environ.get("HBSM_SHARD_GEMM_FIRST", "0") == "1" else 2
+        _capi.check(Lc.hbsm_product_begin(A_loc._h, int(bool(tA)), B_loc._h, int(bool(tB)), Cm._h, int(bool(spamm)), float(tau), 1, mode))
         t1 = time.perf_counter()
-        with torch.cuda.stream(comm):
-            _, _, bt = device_views(B_loc)
-            nz = torch.nonzero(asked[:world * L_r].view(world, L_r), as_tuple=False)       # syncs the comm stream only
-            send_counts = np.bincount(nz[:, 0].cpu().numpy(), minlength=world).tolist()
-            tiles_out = bt.index_select(0, nz[:, 1].contiguous())
-            dist.all_to_all_single(tiles_in, tiles_out, recv_counts, send_counts, group=group)
-            ev_tiles = torch.cuda.Event(); ev_tiles.record(comm)
+        tr.mark("product_begin")
+        send_counts, ev_tiles, _keep = fut.result() if fut is not None else exchange()
+        fut = None
+        tr.mark("exchange_joined")
         nm = C.c_size_t(0); nb = C.c_size_t(0)
         _capi.check(Lc.hbsm_product_finish(Cm._h, C.c_void_p(ev_tiles.cuda_event), C.byref(nm), C.byref(nb)))
+        tr.mark("product_finish")
         ok = True
     finally:
         if not ok:
+            if fut is not None:
+                try:
+                    fut.result()
+                except Exception:
+                    pass
             torch.cuda.synchronize()
         _capi.check(Lc.hbsm_halo_commit(B_loc._h, 0))
-    tr.mark("engine_product")
+    tr.mark("halo_drop")
     if timers is not None:
         timers["plan_s"] = t1 - t0
         timers["sent_tiles"] = sum(send_counts)
@@ -565,6 +599,12 @@ def bench_main(args, w, workload_config, fp64_peak, ClockSampler):
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     launches = hb.kernel_launch_count() - l0
     trace = {k: round(1e3 * v / args.steps, 4) for k, v in timers.get("trace", {}).items()} or None   # ms per step
+    if trace is not None:     # every rank's phases (+ its engine stage times) on rank 0's line
+        mine = dict(trace, rank=rank, gemm_ms=float(np.mean(gemm_ms)), tasklist_ms=float(np.mean(task_ms)), index_ms=float(st["index_ms"]),
+                    engine_total_ms=float(st["total_ms"]))
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+        trace = allr
     clocks = sampler.stop() if rank == 0 else None
     ms_local = ev0.elapsed_time(ev1) / args.steps
     stats = torch.tensor([ms_local, float(np.mean(gemm_ms))], dtype=torch.float64, device="cuda")
