@@ -838,9 +838,9 @@ void op_product_begin(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix
     }
     P.t_task.stop();
 
+    if (P.tl.n_products > 0) P.ct.alloc(P.tl.n_ctiles * C.tile_bytes());   // before the timer: a growing pool stalls the host here
     P.t_gemm.start();
     if (P.tl.n_products > 0) {
-        P.ct.alloc(P.tl.n_ctiles * C.tile_bytes());
         if (launch) launch_leaf_gemm(A, tA, B, tB, P.tl, split ? first.p : nullptr, n_first, P.ct.p);
         else if (launch_in_finish) { P.first_pending = true; P.first_is_list = split; P.n_first = n_first; }
     }
