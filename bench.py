@@ -23,7 +23,7 @@ import numpy as np  # noqa: E402
 from hierarchical_block_sparse_lib_b200 import _capi  # noqa: E402
 
 WORKLOAD = dict(n=65536, b=64, lam=0.01, tau=1e-6, eps=1e-12, seeds=(1, 2))
-CPU_SAMPLE_N = 8192           # leading principal block of the same matrices, same law
+CPU_SAMPLE_N = int(os.environ.get("HBSM_CPU_SAMPLE_N", "8192"))   # leading principal block of the same matrices, same law
 FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "r01_peak_fp64.json")
 
 

@@ -322,6 +322,7 @@ template <typename T>
 __global__ void __launch_bounds__(1024) k_fold_root(const uint64_t* __restrict__ keys0, const T* __restrict__ vals0, size_t n0,
                                                     int depth, uint64_t* ka, T* va, uint64_t* kb, T* vb,
                                                     volatile uint64_t* mailbox_slot) {
+    constexpr int ITEMS = 4;                 // consecutive entries per thread and round: 4096 per round, 3 barriers
     __shared__ uint32_t warp_cnt[33];
     __shared__ size_t carry_s;
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -333,36 +334,55 @@ __global__ void __launch_bounds__(1024) k_fold_root(const uint64_t* __restrict__
     for (int l = 0; l < depth; ++l) {
         if (tid == 0) carry_s = 0;
         __syncthreads();
-        for (size_t base = 0; base < n; base += 1024) {
-            const size_t i = base + tid;
-            const bool head = i < n && (i == 0 || (kin[i - 1] >> 2) != (kin[i] >> 2));
-            const unsigned bal = __ballot_sync(0xffffffffu, head);
-            if (lane == 0) warp_cnt[warp] = __popc(bal);
+        for (size_t base = 0; base < n; base += 1024 * ITEMS) {
+            const size_t i0 = base + (size_t)tid * ITEMS;
+            uint64_t pk[ITEMS];
+            bool head[ITEMS];
+            uint64_t prev = (i0 > 0 && i0 - 1 < n) ? (kin[i0 - 1] >> 2) : ~0ull;
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) {
+                const size_t i = i0 + j;
+                pk[j] = i < n ? (kin[i] >> 2) : ~0ull;
+                head[j] = i < n && (i == 0 || pk[j] != prev);
+                prev = pk[j];
+                cnt += head[j] ? 1u : 0u;
+            }
+            uint32_t incl = cnt;              // block-wide exclusive scan of the per-thread head counts
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int)lane >= d) incl += o;
+            }
+            if (lane == 31) warp_cnt[warp] = incl;
             __syncthreads();
             if (warp == 0) {
                 const uint32_t v = warp_cnt[lane];
-                uint32_t incl = v;
+                uint32_t wi = v;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                    if ((int)lane >= d) incl += o;
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+                    if ((int)lane >= d) wi += o;
                 }
-                warp_cnt[lane] = incl - v;
-                if (lane == 31) warp_cnt[32] = incl;
+                warp_cnt[lane] = wi - v;
+                if (lane == 31) warp_cnt[32] = wi;
             }
             __syncthreads();
-            if (head) {
-                const size_t pos = carry_s + warp_cnt[warp] + __popc(bal & ((1u << lane) - 1u));
-                const uint64_t pk = kin[i] >> 2;
-                T sum = 0;
-                for (size_t j = i; j < n && (kin[j] >> 2) == pk; ++j) sum = DT<T>::add(sum, vin[j]);
-                kout[pos] = pk;
-                vout[pos] = sum;
+            size_t pos = carry_s + warp_cnt[warp] + (incl - cnt);
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) {
+                if (head[j]) {
+                    T sum = 0;
+                    for (size_t q = i0 + j; q < n && (kin[q] >> 2) == pk[j]; ++q) sum = DT<T>::add(sum, vin[q]);
+                    kout[pos] = pk[j];
+                    vout[pos] = sum;
+                    ++pos;
+                }
             }
             __syncthreads();
             if (tid == 0) carry_s += warp_cnt[32];
-            __syncthreads();
         }
+        __syncthreads();
         n = carry_s;
         kin = kout;
         vin = vout;
