@@ -87,7 +87,12 @@ def run_reference_cpu(steps, warmup, n_sample=CPU_SAMPLE_N):
     """The reference's own OpenMP implementation (oracle/_ref = unmodified header compiled in place) on the host
     cores, on the leading n_sample x n_sample block of the workload's matrices.  Returns (tflops, ms, info)."""
     cores = host_threads()
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    if "HBSM_REF_THREADS" in os.environ:
+        os.environ["OMP_NUM_THREADS"] = os.environ["HBSM_REF_THREADS"]
+    elif "TORCHELASTIC_RUN_ID" in os.environ or "OMP_NUM_THREADS" not in os.environ:
+        # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is ONE process that gets all host threads
+        os.environ["OMP_NUM_THREADS"] = str(cores)
+    cores = int(os.environ["OMP_NUM_THREADS"])      # what the run really uses (reported as cpu_baseline.cores)
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     from oracle import pyoracle as po
     from hierarchical_block_sparse_lib_b200 import generators as G
