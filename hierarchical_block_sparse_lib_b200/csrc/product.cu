@@ -1049,7 +1049,12 @@ void op_product_from_host(Matrix& A, const HostTiles& ha, bool tA, Matrix& B, co
         update_norms(A);
         update_norms(B);
         size_t nb = 0;
-        op_product_to_host(A, tA, B, tB, C, o, host_c_tiles, cap_tiles, 8, n_mults, &nb);
+        try {
+            op_product_to_host(A, tA, B, tB, C, o, host_c_tiles, cap_tiles, 8, n_mults, &nb);
+        } catch (...) {   // too small a host buffer is reported after C is complete: the caller still learns its size
+            if (n_blocks) *n_blocks = nb;
+            throw;
+        }
         if (n_blocks) *n_blocks = nb;
         if (nb && c_bi && c_bj) {
             std::vector<uint64_t> hk = C.keys.to_host();
