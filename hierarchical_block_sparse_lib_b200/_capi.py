@@ -66,6 +66,7 @@ SIGNATURES = {
     "hbsm_spamm": (_I, [_H, _I, _H, _I, _H, C.c_double, _I, C.POINTER(_sz), C.POINTER(_sz)]),
     "hbsm_product_begin": (_I, [_H, _I, _H, _I, _H, _I, C.c_double, _I, _I]),
     "hbsm_product_finish": (_I, [_H, _P, C.POINTER(_sz), C.POINTER(_sz)]),
+    "hbsm_product_begin_ex": (_I, [_H, _I, _H, _I, _H, _I, C.c_double, _I, _I, _I]),
     "hbsm_product_to_host": (_I, [_H, _I, _H, _I, _H, _I, C.c_double, _I, _P, _sz, C.POINTER(_sz), C.POINTER(_sz)]),
     "hbsm_product_from_host": (_I, [_H, _sz, _P, _P, _P, _I, _H, _sz, _P, _P, _P, _I, _H, _I, C.c_double, _I, _P, _sz, _P, _P,
                                     C.POINTER(_sz), C.POINTER(_sz)]),

@@ -183,17 +183,22 @@ int hbsm_spamm(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, doub
         op_product(M(A), tA != 0, M(B), tB != 0, M(C), o, n_block_multiplies, n_resizes);
     });
 }
-int hbsm_product_begin(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, int spamm, double tau, int updated,
-                       int defer_halo_tiles) {
+int hbsm_product_begin_ex(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, int spamm, double tau, int updated,
+                          int defer_halo_tiles, int upper_only) {
     return guarded([&] {
         ProductOpts o;
         o.spamm = spamm != 0;
         o.tau = tau;
         o.updated = updated != 0;
+        o.upper_only = upper_only != 0;   // symm_square / symm_rk: only C tiles with ci <= cj; finish masks the diagonal tiles
         // defer_halo_tiles: 1 = launch the own-only C tiles now; 2 = plan only, hbsm_product_finish launches them too (so that a
         // transfer queued in between gets its SMs before the persistent leaf GEMM occupies all of them)
         op_product_begin(M(A), tA != 0, M(B), tB != 0, M(C), o, defer_halo_tiles != 0, defer_halo_tiles != 2, defer_halo_tiles == 2);
     });
+}
+int hbsm_product_begin(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, int spamm, double tau, int updated,
+                       int defer_halo_tiles) {
+    return hbsm_product_begin_ex(A, tA, B, tB, C, spamm, tau, updated, defer_halo_tiles, 0);
 }
 int hbsm_product_finish(hbsm_handle C, void* cuda_event_or_null, size_t* n_block_multiplies, size_t* n_resizes) {
     const int rc = guarded([&] { op_product_finish(M(C), (cudaEvent_t)cuda_event_or_null, n_block_multiplies, n_resizes); });
@@ -330,7 +335,6 @@ int hbsm_symm_square(hbsm_handle A, hbsm_handle C) {
         ProductOpts o;
         o.upper_only = true;
         op_product(S, false, S, false, M(C), o, nullptr, nullptr);
-        mask_diag_upper(M(C));
         sync_stream();
     });
 }
@@ -341,7 +345,6 @@ int hbsm_symm_rk(hbsm_handle A, int transposed, hbsm_handle C) {
         o.upper_only = true;
         if (transposed) op_product(M(A), true, M(A), false, M(C), o, nullptr, nullptr);
         else op_product(M(A), false, M(A), true, M(C), o, nullptr, nullptr);
-        mask_diag_upper(M(C));
         sync_stream();
     });
 }
@@ -357,7 +360,6 @@ int hbsm_symm_square_spamm(hbsm_handle A, hbsm_handle C, double tau, size_t* n_b
         o.tau = tau;
         o.upper_only = true;
         op_product(S, false, S, false, M(C), o, n_block_multiplies, n_resizes);
-        mask_diag_upper(M(C));
         sync_stream();
     });
 }

@@ -778,6 +778,7 @@ struct PendingProduct {
     DevBuf<uint32_t> first;      // the other C tiles, when their launch was left to finish as well (launch_in_finish)
     size_t n_first = 0;
     bool first_pending = false, first_is_list = false;
+    bool upper_only = false;     // finish zeroes the strict lower part of C's diagonal tiles (H:3563 via triu)
     uint64_t launches0 = 0;
     EventTimer t_total, t_norm, t_index, t_task, t_gemm, t_gemm2;
 };
@@ -846,6 +847,7 @@ void op_product_begin(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix
     }
     P.t_gemm.stop();
     P.A = &A; P.B = &B; P.C = &C; P.tA = tA; P.tB = tB;
+    P.upper_only = o.upper_only;
     P.active = true;
 }
 
@@ -870,6 +872,7 @@ void op_product_finish(Matrix& C, cudaEvent_t wait_for, size_t* n_mults, size_t*
         C.task_begin = std::move(P.tl.begin);
         C.task_k = std::move(P.tl.task_k);
         C.n_tasks = P.tl.n_products;
+        if (P.upper_only) mask_diag_upper(C);   // triu of the diagonal tiles (the off-diagonal ones were never planned)
     }
     P.t_total.stop();
     sync_stream();

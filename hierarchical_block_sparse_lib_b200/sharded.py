@@ -387,7 +387,7 @@ def publish(B_loc, group=None):
     return table
 
 
-def _sharded_product_overlapped(A_loc, tA, B_loc, tB, spamm, tau, group, timers, table):
+def _sharded_product_overlapped(A_loc, tA, B_loc, tB, spamm, tau, group, timers, table, upper_only=False):
     """Published-table protocol with the tile transfer hidden behind the leaf GEMMs that need no remote tile:
 
       engine stream : hbsm_halo_plan (mask, recv counts, halo keys+norms) | line index, task list, split | GEMM(own-only C tiles) | GEMM(rest)
@@ -470,7 +470,8 @@ def _sharded_product_overlapped(A_loc, tA, B_loc, tB, spamm, tau, group, timers,
         # plan only (mode 2): the all-to-all of the tiles is queued BEFORE the first leaf GEMM, whose persistent CTAs would
         # otherwise hold every SM until they drain (HBSM_SHARD_GEMM_FIRST=1 restores the old order for comparison)
         mode = 1 if os.environ.get("HBSM_SHARD_GEMM_FIRST", "0") == "1" else 2
-        _capi.check(Lc.hbsm_product_begin(A_loc._h, int(bool(tA)), B_loc._h, int(bool(tB)), Cm._h, int(bool(spamm)), float(tau), 1, mode))
+        _capi.check(Lc.hbsm_product_begin_ex(A_loc._h, int(bool(tA)), B_loc._h, int(bool(tB)), Cm._h, int(bool(spamm)), float(tau), 1, mode,
+                                             int(bool(upper_only))))
         t1 = time.perf_counter()
         tr.mark("product_begin")
         send_counts, ev_tiles, _keep = fut.result() if fut is not None else exchange()
@@ -497,7 +498,16 @@ def _sharded_product_overlapped(A_loc, tA, B_loc, tB, spamm, tau, group, timers,
     return Cm, nm.value, nb.value
 
 
-def sharded_product(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, group=None, timers=None):
+def sharded_symm_square_spamm(F_loc, tau, group=None, timers=None):
+    """BASELINE config 3 across GPUs: this rank's block rows of triu(spamm(F, F, tau)) for a symmetric F held in FULL storage and
+    sharded by block rows like any other operand (F_loc: norms refreshed, publish(F_loc) called).  tau = None: exact symmetric
+    square.  Only C tiles with ci <= cj are planned, the diagonal tiles are masked: on one GPU this is symm_square_spamm of F's
+    upper triangle (H:3563 with the prune of H:3931).  A banded F keeps contiguous row slabs balanced (every block row owns about
+    half a band of C tiles); for a dense-ish F pair the slabs (i, G-1-i) instead."""
+    return sharded_product(F_loc, False, F_loc, False, tau is not None, 0.0 if tau is None else tau, group, timers, upper_only=True)
+
+
+def sharded_product(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, group=None, timers=None, upper_only=False):
     """C_r = op(A)_r * op(B): A_loc / B_loc are this rank's engine matrices (full logical dims, only the slab's tiles;
     norms refreshed).  Remote op(B) tiles are received straight into B_loc's halo tail (hbsm_halo_reserve/commit), the
     rank's own tiles are never copied.  If publish(B_loc) was called the two-round protocol is used, else the
@@ -507,7 +517,9 @@ def sharded_product(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, group=None, time
     table = getattr(B_loc, "_published", None)
     if (table is not None and os.environ.get("HBSM_SHARD_OVERLAP", "1") == "1"
             and os.environ.get("HBSM_SHARD_TORCH_PLAN", "0") != "1"):
-        return _sharded_product_overlapped(A_loc, tA, B_loc, tB, spamm, tau, group, timers, table)
+        return _sharded_product_overlapped(A_loc, tA, B_loc, tB, spamm, tau, group, timers, table, upper_only)
+    if upper_only:
+        raise NotImplementedError("upper_only products need the published-table protocol: call publish(B_loc) first")
     grid_side = 1 << max(A_loc.expected_depth(), B_loc.expected_depth())
     ext = torch.cuda.ExternalStream(int(_capi.lib().hbsm_stream() or 0))
     with torch.cuda.stream(ext):

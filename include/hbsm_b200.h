@@ -108,6 +108,11 @@ int hbsm_spamm(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, doub
 int hbsm_product_begin(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, int spamm, double tau, int updated,
                        int defer_halo_tiles);
 int hbsm_product_finish(hbsm_handle C, void* cuda_event_or_null, size_t* n_block_multiplies, size_t* n_resizes);
+/* the same begin with the symmetric-family option: upper_only != 0 plans only the C tiles with ci <= cj and finish zeroes
+ * the strict lower part of the diagonal tiles (symm_square H:3563 / symm_rk H:3711 on an expanded operand; sharded:
+ * triu(op(A)*op(B)) of the rank's block rows) */
+int hbsm_product_begin_ex(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, int spamm, double tau, int updated,
+                          int defer_halo_tiles, int upper_only);
 /* multiply (spamm = 0) or SpAMM whose result is ALSO delivered to host memory: the leaf GEMMs run in ranges of C's tile
  * list and every finished range is copied to `host_tiles` (pinned memory recommended; room for cap_tiles tiles, in the
  * order of hbsm_export_leaves) on a second stream while the next ranges compute.  If cap_tiles is smaller than the number

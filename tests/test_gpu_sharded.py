@@ -68,3 +68,54 @@ def test_sharded_matches_single_gpu(tmp_path, torch_plan):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "sharded ok" in r.stdout
+
+
+SYMM_SCRIPT = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+import hierarchical_block_sparse_lib_b200 as hb
+from hierarchical_block_sparse_lib_b200 import sharded as S, generators as G
+H = hb.HierarchicalBlockSparseMatrix
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr); dist.init_process_group("nccl", device_id=torch.device("cuda", lr)); hb.init(lr)
+n, b, lam = 4096, 64, 0.02
+W = G.decay_width(lam); g = n // b
+lo, hi = S.slab_bounds(g, world, rank)
+F = H(np.float64, b); F.generate_decay(n, lam, W, 3, symmetric=True); F.update_internal_info()   # full symmetric storage
+U = H(np.float64); F.get_upper_triangle(U); U.update_internal_info()
+bi, bj, _, t = F.export_leaves(norms=False)
+m = (bi >= lo) & (bi < hi)
+Fl = H(np.float64, b); Fl.resize(n, n); Fl.assign_tiles(bi[m], bj[m], t[m]); Fl.update_internal_info()
+S.publish(Fl)
+for tau in (1e-6, None):
+    Cl, nm, nb = S.sharded_symm_square_spamm(Fl, tau)
+    Cf = H(np.float64)
+    if tau is None: H.symm_square(U, Cf); nmf = Cf.get_n_block_multiplications(); nbf = Cf.get_n_blocks()
+    else: nmf, nbf = H.symm_square_spamm(U, Cf, tau)
+    tot = torch.tensor([nm, nb], dtype=torch.int64, device="cuda"); dist.all_reduce(tot)
+    assert (int(tot[0]), int(tot[1])) == (nmf, nbf), (tot.tolist(), nmf, nbf)
+    ci, cj, _, tl = Cl.export_leaves(norms=False); fi, fj, _, tf = Cf.export_leaves(norms=False)
+    mm = (fi >= lo) & (fi < hi)
+    assert np.all(ci <= cj)
+    assert np.array_equal(ci, fi[mm]) and np.array_equal(cj, fj[mm]) and np.array_equal(tl, tf[mm])   # same kernel, same k order: bitwise
+if rank == 0: print("sharded symm ok world=%%d" %% world)
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_symm_square_matches_single_gpu(tmp_path):
+    """BASELINE config 3 sharded: triu(spamm(F,F,tau)) by block rows == symm_square_spamm of the upper storage on one GPU."""
+    import torch
+    ngpu = torch.cuda.device_count()
+    world = 1
+    for wsz in (8, 4, 2):
+        if ngpu >= wsz:
+            world = wsz
+            break
+    script = tmp_path / "sharded_symm_check.py"
+    script.write_text(SYMM_SCRIPT % {"root": ROOT})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", "29518", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "sharded symm ok" in r.stdout
