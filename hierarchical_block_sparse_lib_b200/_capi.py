@@ -66,6 +66,7 @@ SIGNATURES = {
     "hbsm_spamm": (_I, [_H, _I, _H, _I, _H, C.c_double, _I, C.POINTER(_sz), C.POINTER(_sz)]),
     "hbsm_product_begin": (_I, [_H, _I, _H, _I, _H, _I, C.c_double, _I, _I]),
     "hbsm_product_finish": (_I, [_H, _P, C.POINTER(_sz), C.POINTER(_sz)]),
+    "hbsm_product_abort": (_I, []),
     "hbsm_product_begin_ex": (_I, [_H, _I, _H, _I, _H, _I, C.c_double, _I, _I, _I]),
     "hbsm_product_to_host": (_I, [_H, _I, _H, _I, _H, _I, C.c_double, _I, _P, _sz, C.POINTER(_sz), C.POINTER(_sz)]),
     "hbsm_product_from_host": (_I, [_H, _sz, _P, _P, _P, _I, _H, _sz, _P, _P, _P, _I, _H, _I, C.c_double, _I, _P, _sz, _P, _P,
@@ -92,6 +93,8 @@ SIGNATURES = {
     "hbsm_symm_square_spamm": (_I, [_H, _H, C.c_double, C.POINTER(_sz), C.POINTER(_sz)]),
     "hbsm_export_tasks": (_I, [_H, _sz, _P, _P, _P, C.POINTER(_sz)]),
     "hbsm_export_leaves": (_I, [_H, _sz, _P, _P, _P, _P, C.POINTER(_sz)]),
+    "hbsm_task_checksum": (_I, [_H, C.POINTER(C.c_uint64)]),
+    "hbsm_export_tile_tasks": (_I, [_H, _I, _I, _sz, _P, C.POINTER(_sz), C.POINTER(_I)]),
     "hbsm_stage_times_last": (_I, [C.POINTER(StageTimes)]),
     "hbsm_set_gemm_variant": (_I, [_I]),
     "hbsm_device_table": (_I, [_H, C.POINTER(_sz), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
@@ -114,7 +117,7 @@ _lib = None
 
 def build(verbose=False):
     """Compile csrc/*.cu for sm_100a into lib/libhbsm_b200.so (nvcc cross-compiles without a GPU)."""
-    r = subprocess.run(["make", "-s", "-C", CSRC], capture_output=not verbose, text=True)
+    r = subprocess.run(["make", "-s", "-j", str(min(8, os.cpu_count() or 1)), "-C", CSRC], capture_output=not verbose, text=True)
     if r.returncode != 0:
         raise RuntimeError("building libhbsm_b200.so failed:\n%s\n%s" % (r.stdout, r.stderr))
 

@@ -30,7 +30,14 @@ int guarded(F&& f) {
 
 Matrix& M(hbsm_handle h) {
     if (!h) throw Error(HBSM_E_ARG, "hbsm_b200: null matrix handle");
-    return h->m;
+    Matrix& m = h->m;
+    if (m.pending_ev) {   // device work queued by another call (possibly another thread's stream) has to land first
+        if (engine().ready) cudaStreamWaitEvent(engine().stream, m.pending_ev, 0);
+        else cudaEventSynchronize(m.pending_ev);
+        cudaEventDestroy(m.pending_ev);
+        m.pending_ev = nullptr;
+    }
+    return m;
 }
 
 void store_real(const Matrix& m, void* out, double v) {
@@ -43,9 +50,9 @@ extern "C" {
 
 int hbsm_init(int device) {
     return guarded([&] {
-        Engine& e = engine();
-        if (e.ready && e.device != device) throw Error(HBSM_E_ARG, "hbsm_b200: engine already bound to another device");
-        e.device = device;
+        int expect = -1;   // one device per process (one process per GPU); every thread's engine binds to it
+        if (!shared().device.compare_exchange_strong(expect, device) && expect != device)
+            throw Error(HBSM_E_ARG, "hbsm_b200: engine already bound to another device");
         ensure_engine();
     });
 }
@@ -71,7 +78,7 @@ int hbsm_device_info(char* name, size_t cap, int* sm_count, int* cc_major, int* 
     });
 }
 
-uint64_t hbsm_kernel_launch_count(void) { return engine().launches; }
+uint64_t hbsm_kernel_launch_count(void) { return shared().launches.load(); }
 
 int hbsm_create(int dtype, hbsm_handle* out) {
     return guarded([&] {
@@ -204,6 +211,9 @@ int hbsm_product_finish(hbsm_handle C, void* cuda_event_or_null, size_t* n_block
     const int rc = guarded([&] { op_product_finish(M(C), (cudaEvent_t)cuda_event_or_null, n_block_multiplies, n_resizes); });
     if (rc != HBSM_OK) op_product_abort();
     return rc;
+}
+int hbsm_product_abort(void) {
+    return guarded([&] { op_product_abort(); });
 }
 int hbsm_product_to_host(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, int spamm, double tau, int updated,
                          void* host_tiles, size_t cap_tiles, size_t* n_block_multiplies, size_t* n_resizes) {
@@ -381,6 +391,18 @@ int hbsm_export_tasks(hbsm_handle Ch, size_t cap, int64_t* ci, int64_t* cj, int6
     });
 }
 
+int hbsm_task_checksum(hbsm_handle Ch, uint64_t* out) {
+    return guarded([&] { *out = task_checksum(M(Ch)); });
+}
+int hbsm_export_tile_tasks(hbsm_handle Ch, int bi, int bj, size_t cap, int64_t* k, size_t* n, int* found) {
+    return guarded([&] {
+        if (bi < 0 || bj < 0) throw Error(HBSM_E_ARG, "hbsm_b200: export_tile_tasks: negative block coordinate");
+        const long long r = tile_tasks(M(Ch), (uint32_t)bi, (uint32_t)bj, cap, k);
+        *found = r >= 0 ? 1 : 0;
+        *n = r >= 0 ? (size_t)r : 0;
+    });
+}
+
 int hbsm_export_leaves(hbsm_handle h, size_t cap, int64_t* bi, int64_t* bj, void* norms_cached, void* tiles, size_t* n) {
     return guarded([&] {
         Matrix& A = M(h);
@@ -403,7 +425,7 @@ int hbsm_stage_times_last(hbsm_stage_times* out) {
     return guarded([&] { *out = engine().last; });
 }
 int hbsm_set_gemm_variant(int variant) {
-    return guarded([&] { engine().gemm_variant = variant; });
+    return guarded([&] { shared().gemm_variant.store(variant); });
 }
 
 int hbsm_device_table(hbsm_handle h, size_t* n_tiles, const uint64_t** d_morton_keys, const void** d_norms,

@@ -10,6 +10,8 @@
 #include <vector>
 #include <algorithm>
 #include <utility>
+#include <atomic>
+#include <mutex>
 #include "../../include/hbsm_b200.h"
 
 namespace hbsm_b200 {
@@ -31,20 +33,34 @@ struct Error : public std::runtime_error {
 // the reference's own exception text is preserved: "Error in HierarchicalBlockSparseMatrix<Treal>::..."
 [[noreturn]] inline void throw_ref(const char* msg) { throw Error(HBSM_E_RUNTIME, msg); }
 
+// Process-wide state.  The reference's multiply/spamm/add are re-entrant statics (H:255-305) and its stated caller is a
+// worker pool, so everything that carries per-call state lives in the per-THREAD Engine below; only the device choice, the
+// launch counter and the debug switch are shared.
+struct Shared {
+    std::atomic<int> device{-1};
+    std::atomic<uint64_t> launches{0};     // kernels launched by this library, all threads
+    std::atomic<int> gemm_variant{0};      // 0 auto (TMA-tiled DMMA), 1 generic scalar kernel, 2 bulk-copy DMMA kernel
+    std::mutex index_mutex;                // lazily built line indices of matrices shared between threads
+};
+Shared& shared();
+
+// Per host thread: its own stream, mailbox, pending product and stage times.  Two threads can run products concurrently on
+// their own streams; a handle may be used by one thread at a time (like the reference's objects), any thread after another.
 struct Engine {
     int device = -1;
     int sm_count = 0;
     int cc_major = 0, cc_minor = 0;
     cudaStream_t stream = nullptr;
-    uint64_t launches = 0;  // kernels launched by this library
+    cudaStream_t stream2 = nullptr;   // second compute stream: the halo-reading leaf GEMM of a sharded product
+    uint64_t launches = 0;  // kernels launched by this thread
     bool ready = false;
     std::string name;
-    int gemm_variant = 0;      // 0 auto (TMA-tiled DMMA), 1 generic scalar kernel, 2 bulk-copy DMMA kernel
     int last_gemm_kernel = 0;  // which leaf kernel the last product ran: 0 generic, 1 TMA-tiled DMMA, 2 bulk-copy DMMA
     hbsm_stage_times last{};
     // pinned, device-mapped host words: kernels post the few scalars the host needs between launches (sizes of the next
     // allocations) straight into host memory, so those read-backs never queue on a PCIe copy engine behind bulk transfers
     uint64_t* mailbox = nullptr;
+    ~Engine();
 };
 Engine& engine();
 void ensure_engine();
@@ -54,6 +70,7 @@ void ensure_engine();
     do {                                                                                       \
         kernel<<<(grid), (block), (smem), ::hbsm_b200::engine().stream>>>(__VA_ARGS__);        \
         ::hbsm_b200::engine().launches++;                                                      \
+        ::hbsm_b200::shared().launches.fetch_add(1, std::memory_order_relaxed);                \
         HB_CUDA(cudaGetLastError());                                                           \
     } while (0)
 

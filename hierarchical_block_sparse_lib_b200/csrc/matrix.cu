@@ -9,9 +9,22 @@ namespace hbsm_b200 {
 // ---------------------------------------------------------------------------------------------------
 // engine
 // ---------------------------------------------------------------------------------------------------
+Shared& shared() {
+    static Shared s;
+    return s;
+}
+
 Engine& engine() {
-    static Engine e;
+    thread_local Engine e;
     return e;
+}
+
+Engine::~Engine() {   // thread exit: errors are ignored (at process exit the runtime may already be gone)
+    if (!ready) return;
+    if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+    if (stream2) { cudaStreamSynchronize(stream2); cudaStreamDestroy(stream2); }
+    if (mailbox) cudaFreeHost(mailbox);
+    ready = false; stream = nullptr; stream2 = nullptr; mailbox = nullptr;   // late frees fall back to the default stream
 }
 
 void ensure_engine() {
@@ -24,7 +37,12 @@ void ensure_engine() {
     cudaError_t err = cudaGetDeviceCount(&count);
     if (err != cudaSuccess || count == 0)
         throw Error(HBSM_E_CUDA, "hbsm_b200: no CUDA device available (this engine has no CPU fallback)");
-    int dev = e.device >= 0 ? e.device : 0;
+    int dev = shared().device.load();
+    if (dev < 0) {   // first use without hbsm_init: device 0 for the whole process
+        int expect = -1;
+        shared().device.compare_exchange_strong(expect, 0);
+        dev = shared().device.load();
+    }
     if (dev >= count) throw Error(HBSM_E_CUDA, "hbsm_b200: device index out of range");
     HB_CUDA(cudaSetDevice(dev));
     cudaDeviceProp p;
@@ -37,11 +55,12 @@ void ensure_engine() {
     e.cc_minor = p.minor;
     e.name = p.name;
     HB_CUDA(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
+    HB_CUDA(cudaStreamCreateWithFlags(&e.stream2, cudaStreamNonBlocking));
     cudaMemPool_t pool;
     HB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
     uint64_t thr = UINT64_MAX;
     HB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-    HB_CUDA(cudaHostAlloc((void**)&e.mailbox, 64 * sizeof(uint64_t), cudaHostAllocMapped));
+    HB_CUDA(cudaHostAlloc((void**)&e.mailbox, 256 * sizeof(uint64_t), cudaHostAllocMapped));   // slots: 0-1 read_scalars, 2 root norm, 4 find, 8..8+64 halo edges
     e.ready = true;
 }
 
@@ -313,11 +332,85 @@ __global__ void __launch_bounds__(128) k_leaf_norms(const T* __restrict__ tiles,
     if (lane < nleaf) out[leaf0 + lane] = acc;
 }
 
-// The whole bottom-up refresh of H:3918-3923 / H:656-662 in ONE block: every node = sum of its existing children in child
-// order 0..3, starting from 0, in Treal.  Siblings are adjacent in Morton order, so one level is a head-flag compaction
-// (ballot + block scan, 1024 entries per round) whose heads add up their <= 4 followers; the levels ping-pong between two
-// scratch tables.  Only the root is kept (inner-node norms are never consulted: the prune rule is flat); it is
-// posted to the engine's host mailbox as a double, so the refresh costs no PCIe copy and no host pass.
+// Bottom-up refresh of H:3918-3923 / H:656-662: every node = sum of its existing children in child order 0..3, starting
+// from 0, in Treal.  Adding an absent child as +0.0 is exact (norms are non-negative), so a level can be folded DENSELY:
+// parent p = ((c[4p] + c[4p+1]) + c[4p+2]) + c[4p+3].  The leaves below one level-m ancestor are one contiguous key range
+// (Morton order), so a block finds the range of its ancestor by binary search, scatters the leaf norms into a dense
+// 4^m-slot shared-memory table (m <= 6) and folds m levels there; the last block to finish folds the remaining <= 6 top
+// levels the same way and posts the root to the engine's host mailbox as a double.  One launch, every SM busy, no
+// scratch proportional to L.  Only the root is kept (inner-node norms are never consulted: the prune rule is flat).
+template <typename T>
+__device__ __forceinline__ void fold_dense_smem(T* s, uint32_t cnt) {
+    // in place: after each round the first cnt/4 slots hold the parents
+    for (; cnt > 1; cnt >>= 2) {
+        const uint32_t np = cnt >> 2;
+        T v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t p = threadIdx.x + j * blockDim.x;
+            if (p < np) v[j] = DT<T>::add(DT<T>::add(DT<T>::add(s[4 * p], s[4 * p + 1]), s[4 * p + 2]), s[4 * p + 3]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t p = threadIdx.x + j * blockDim.x;
+            if (p < np) s[p] = v[j];
+        }
+        __syncthreads();
+    }
+}
+__device__ __forceinline__ size_t lower_bound_key(const uint64_t* __restrict__ keys, size_t n, uint64_t key) {
+    size_t lo = 0, hi = n;
+    while (lo < hi) {
+        const size_t mid = (lo + hi) >> 1;
+        if (keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_fold_dense(const uint64_t* __restrict__ keys, const T* __restrict__ vals, size_t n,
+                                                    int depth, int m, T* top, unsigned* done_counter,
+                                                    volatile uint64_t* mailbox_slot) {
+    __shared__ T s[4096];
+    __shared__ size_t range_s[2];
+    __shared__ unsigned last_s;
+    const uint32_t n_top = 1u << (2 * (depth - m));   // <= 4096
+    const uint32_t slots = 1u << (2 * m);             // <= 4096
+    for (uint32_t a = blockIdx.x; a < n_top; a += gridDim.x) {
+        if (threadIdx.x < 2) range_s[threadIdx.x] = lower_bound_key(keys, n, (uint64_t)(a + threadIdx.x) << (2 * m));
+        __syncthreads();
+        const size_t lo = range_s[0], hi = range_s[1];
+        if (lo < hi) {
+            for (uint32_t i = threadIdx.x; i < slots; i += blockDim.x) s[i] = (T)0;
+            __syncthreads();
+            for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) s[keys[i] & (uint64_t)(slots - 1)] = vals[i];
+            __syncthreads();
+            fold_dense_smem<T>(s, slots);
+            if (threadIdx.x == 0) top[a] = s[0];
+        } else if (threadIdx.x == 0) {
+            top[a] = (T)0;
+        }
+        __syncthreads();
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last_s = (atomicAdd(done_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!last_s) return;
+    __threadfence();
+    const volatile T* vt = top;
+    for (uint32_t i = threadIdx.x; i < n_top; i += blockDim.x) s[i] = vt[i];
+    __syncthreads();
+    fold_dense_smem<T>(s, n_top);
+    if (threadIdx.x == 0) {
+        *mailbox_slot = (uint64_t)__double_as_longlong((double)s[0]);
+        __threadfence_system();
+    }
+}
+
+// Fallback for block grids deeper than 12 levels (side > 4096): the same refresh in ONE block over sparse (key, value)
+// tables, level by level (head-flag compaction; heads add up their <= 4 followers), ping-ponging between two scratch
+// tables of L entries each -- a level is only bounded by the level below it, there is no halving guarantee.
 template <typename T>
 __global__ void __launch_bounds__(1024) k_fold_root(const uint64_t* __restrict__ keys0, const T* __restrict__ vals0, size_t n0,
                                                     int depth, uint64_t* ka, T* va, uint64_t* kb, T* vb,
@@ -972,6 +1065,56 @@ bool export_tile(const Matrix& A, uint32_t bi, uint32_t bj, void* host_buf) {
     return true;
 }
 
+// Order-independent checksum of the executed-product set recorded on C (parity hook): sum over products of
+// splitmix64(ci << 42 | cj << 21 | k), modulo 2^64.  Equal sets give equal sums whatever the order or the sharding, so
+// the per-rank checksums of a sharded product add up to the single-GPU one.
+namespace {
+__global__ void __launch_bounds__(256) k_task_checksum(const uint64_t* __restrict__ ckeys, const uint64_t* __restrict__ begin,
+                                                        const uint32_t* __restrict__ task_k, size_t n_ctiles,
+                                                        unsigned long long* __restrict__ acc) {
+    const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31;
+    unsigned long long sum = 0;
+    if (w < n_ctiles) {
+        const uint64_t key = ckeys[w];
+        const uint64_t hi = ((uint64_t)morton_row(key) << 42) | ((uint64_t)morton_col(key) << 21);
+        for (uint64_t p = begin[w] + lane; p < begin[w + 1]; p += 32) sum += splitmix64(hi | (uint64_t)task_k[p]);
+    }
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, d);
+    if (lane == 0 && sum) atomicAdd(acc, sum);
+}
+}  // namespace
+uint64_t task_checksum(const Matrix& C) {
+    if (C.n_tasks == 0 || C.L == 0 || !C.task_begin.p) return 0;
+    ensure_engine();
+    DevBuf<unsigned long long> acc(1);
+    acc.zero();
+    HB_LAUNCH(k_task_checksum, blocks_for(C.L * 32, 256), 256, 0, C.keys.p, C.task_begin.p, C.task_k.p, C.L, acc.p);
+    return (uint64_t)acc.to_host()[0];
+}
+
+// the k's of the products accumulated into C tile (bi, bj), ascending (parity hook); returns their number or -1 if absent
+long long tile_tasks(const Matrix& C, uint32_t bi, uint32_t bj, size_t cap, int64_t* k_out) {
+    if (C.empty() || C.L == 0 || C.n_tasks == 0 || !C.task_begin.p) return -1;
+    ensure_engine();
+    Engine& e = engine();
+    HB_LAUNCH(k_find_one, 1, 1, 0, C.keys.p, C.L, C.vdepth() == 0 ? 0ull : morton_encode(bi, bj), e.mailbox + 4);
+    sync_stream();
+    const long long at = (long long)e.mailbox[4];
+    if (at < 0) return -1;
+    uint64_t be[2];
+    HB_CUDA(cudaMemcpyAsync(be, C.task_begin.p + at, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, e.stream));
+    sync_stream();
+    const size_t n = (size_t)(be[1] - be[0]);
+    if (n <= cap && n > 0) {
+        std::vector<uint32_t> k(n);
+        HB_CUDA(cudaMemcpyAsync(k.data(), C.task_k.p + be[0], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, e.stream));
+        sync_stream();
+        for (size_t i = 0; i < n; ++i) k_out[i] = (int64_t)k[i];
+    }
+    return (long long)n;
+}
+
 static void tile_nnz_counts(const Matrix& A, DevBuf<uint32_t>& cnt) {
     cnt.alloc(A.L);
     dispatch(A.dtype, [&](auto z) {
@@ -1031,20 +1174,34 @@ void compute_leaf_norms_range(const Matrix& A, size_t t0, size_t cnt, void* d_ou
     }
 }
 
-// Root value of the bottom-up refresh (H:3918-3923 / H:656-662): k_fold_root, one launch, result through the mailbox.
+// Root value of the bottom-up refresh (H:3918-3923 / H:656-662): k_fold_dense, one launch, result through the mailbox.
 double hierarchical_norm(const Matrix& A, const void* d_leaf_norms) {
     if (A.L == 0) return 0.0;
     ensure_engine();
     Engine& e = engine();
-    const size_t half = (A.L + 1) / 2 + 1;   // a level has at most as many nodes as the one below; two scratch tables
-    DevBuf<uint64_t> ka(A.L), kb(half);
-    DevBuf<char> va(A.L * A.esize()), vb(half * A.esize());
-    dispatch(A.dtype, [&](auto z) {
-        using T = decltype(z);
-        HB_LAUNCH(k_fold_root<T>, 1, 1024, 0, A.keys.p, (const T*)d_leaf_norms, A.L, A.vdepth(), ka.p, (T*)va.p, kb.p, (T*)vb.p,
-                  e.mailbox + 2);
-    });
-    sync_stream();
+    const int depth = A.vdepth();
+    if (depth <= 12) {
+        const int m = std::min(depth, 6);
+        const uint32_t n_top = 1u << (2 * (depth - m));
+        DevBuf<char> top((size_t)n_top * A.esize());
+        DevBuf<unsigned> done(1);
+        done.zero();
+        const unsigned grid = std::min<unsigned>(n_top, 8u * (unsigned)e.sm_count);
+        dispatch(A.dtype, [&](auto z) {
+            using T = decltype(z);
+            HB_LAUNCH(k_fold_dense<T>, grid, 256, 0, A.keys.p, (const T*)d_leaf_norms, A.L, depth, m, (T*)top.p, done.p, e.mailbox + 2);
+        });
+        sync_stream();
+    } else {
+        DevBuf<uint64_t> ka(A.L), kb(A.L);
+        DevBuf<char> va(A.L * A.esize()), vb(A.L * A.esize());
+        dispatch(A.dtype, [&](auto z) {
+            using T = decltype(z);
+            HB_LAUNCH(k_fold_root<T>, 1, 1024, 0, A.keys.p, (const T*)d_leaf_norms, A.L, depth, ka.p, (T*)va.p, kb.p, (T*)vb.p,
+                      e.mailbox + 2);
+        });
+        sync_stream();
+    }
     double root;
     const uint64_t bits = e.mailbox[2];
     memcpy(&root, &bits, sizeof root);
@@ -1185,8 +1342,14 @@ void halo_plan(const Matrix& A, bool tA, Matrix& B, const uint64_t* d_keys_all, 
 const LineIndex& line_index(const Matrix& A, bool by_col, bool with_halo) {
     const bool ext = with_halo && A.n_halo > 0;
     LineIndex& ix = const_cast<LineIndex&>(ext ? (by_col ? A.ext_by_col : A.ext_by_row) : (by_col ? A.by_col : A.by_row));
-    if (ix.valid) return ix;
     ensure_engine();
+    // an operand may be shared (read-only) by products running on different host threads: the lazy build is serialised,
+    // and a thread that finds an index built on another thread's stream orders its own stream behind the build
+    std::lock_guard<std::mutex> lock(shared().index_mutex);
+    if (ix.valid) {
+        if (ix.built_on != engine().stream && ix.ready_ev) HB_CUDA(cudaStreamWaitEvent(engine().stream, ix.ready_ev, 0));
+        return ix;
+    }
     const int depth = A.vdepth();
     const int dbits = std::max(depth, 1);
     const size_t n = ext ? A.n_ext() : A.L;   // halo keys sit behind the owned ones, in any order
@@ -1202,6 +1365,9 @@ const LineIndex& line_index(const Matrix& A, bool by_col, bool with_halo) {
         radix_sort_pairs(skey.p, ix.tile.p, n, 2 * dbits);
         HB_LAUNCH(k_line_ptr, blocks_for(n, 256), 256, 0, skey.p, n, dbits, ix.n_lines, ix.ptr.p, ix.other.p);
     }
+    if (!ix.ready_ev) HB_CUDA(cudaEventCreateWithFlags(&ix.ready_ev, cudaEventDisableTiming));
+    HB_CUDA(cudaEventRecord(ix.ready_ev, engine().stream));
+    ix.built_on = engine().stream;
     ix.valid = true;
     return ix;
 }

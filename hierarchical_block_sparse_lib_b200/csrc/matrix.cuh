@@ -19,7 +19,13 @@ struct LineIndex {
     DevBuf<uint32_t> ptr;    // [n_lines + 1]
     DevBuf<uint32_t> other;  // [L] the other block coordinate
     DevBuf<uint32_t> tile;   // [L] index into keys/tiles/norms
+    cudaEvent_t ready_ev = nullptr;    // recorded behind the build, on ...
+    cudaStream_t built_on = nullptr;   // ... this stream (the building thread's)
     void reset() { valid = false; n_lines = 0; ptr.release(); other.release(); tile.release(); }
+    LineIndex() {}
+    LineIndex(const LineIndex&) = delete;
+    LineIndex& operator=(const LineIndex&) = delete;
+    ~LineIndex() { if (ready_ev) cudaEventDestroy(ready_ev); }
 };
 
 struct Matrix {
@@ -43,6 +49,13 @@ struct Matrix {
     DevBuf<uint64_t> task_begin;    // [L + 1]
     DevBuf<uint32_t> task_k;        // [P]
     size_t n_tasks = 0;
+    // set by the one call that returns before its device work on this matrix is complete (hbsm_product_from_host: C's table
+    // is still merging when the host results are done); the next C-ABI call on the handle orders itself behind it
+    cudaEvent_t pending_ev = nullptr;
+    Matrix() {}
+    Matrix(const Matrix&) = delete;
+    Matrix& operator=(const Matrix&) = delete;
+    ~Matrix() { if (pending_ev) cudaEventDestroy(pending_ev); }
 
     size_t esize() const { return dtype == HBSM_F64 ? 8 : 4; }
     size_t tile_elems() const { return (size_t)b * (size_t)b; }
@@ -75,6 +88,8 @@ void get_values(const Matrix& A, size_t n, const int* rows, const int* cols, voi
 size_t get_all_values(const Matrix& A, size_t cap, int* rows, int* cols, void* vals);
 size_t count_nnz(const Matrix& A);
 bool export_tile(const Matrix& A, uint32_t bi, uint32_t bj, void* host_buf);   // false = no such tile
+uint64_t task_checksum(const Matrix& C);   // order-independent checksum of C's recorded executed-product set
+long long tile_tasks(const Matrix& C, uint32_t bi, uint32_t bj, size_t cap, int64_t* k_out);   // -1 = no such tile
 void compute_leaf_norms(const Matrix& A, void* d_out);   // bit-exact sequential sum per leaf (H:646-652)
 void compute_leaf_norms_range(const Matrix& A, size_t t0, size_t cnt, void* d_out_base);
 double hierarchical_norm(const Matrix& A, const void* d_leaf_norms);   // root value of H:3918-3923 / H:656-662

@@ -586,8 +586,10 @@ struct TaskList {
 
 // builds the executed-product list; returns with the stream synchronised
 // entry_lo/entry_hi: range of op(A)'s line-index entries to join (= a block-row range of C), default all
+// a_norms / b_norms: leaf norm^2 arrays to test against instead of the operands' cached ones (spamm(updated=false))
 void build_tasks(const Matrix& A, bool tA, const Matrix& B, bool tB, const ProductOpts& o, int kbits, TaskList& tl,
-                 bool count_only, size_t entry_lo = 0, size_t entry_hi = (size_t)-1) {
+                 bool count_only, size_t entry_lo = 0, size_t entry_hi = (size_t)-1, const void* a_norms = nullptr,
+                 const void* b_norms = nullptr) {
     const LineIndex& la = line_index(A, tA);   // op(A): lines are C rows
     const LineIndex& lb = line_index(B, tB, true);   // op(B): lines are k; includes the halo tail if one is committed
     tl.n_products = tl.n_ctiles = 0;
@@ -599,7 +601,7 @@ void build_tasks(const Matrix& A, bool tA, const Matrix& B, bool tB, const Produ
     JoinArgs g{};
     g.a_ptr = la.ptr.p; g.a_other = la.other.p; g.a_tile = la.tile.p; g.a_lines = la.n_lines;
     g.b_ptr = lb.ptr.p; g.b_other = lb.other.p; g.b_tile = lb.tile.p; g.b_lines = lb.n_lines;
-    g.a_norms = A.norms.p; g.b_norms = B.norms.p;
+    g.a_norms = a_norms ? a_norms : A.norms.p; g.b_norms = b_norms ? b_norms : B.norms.p;
     g.spamm = o.spamm ? 1 : 0;
     g.upper_only = o.upper_only ? 1 : 0;
     g.tau2_d = o.tau * o.tau;                       // fl(tau*tau) in Treal, H:2008
@@ -720,16 +722,17 @@ __global__ void k_split_lists(const uint32_t* __restrict__ own_only, const uint6
 void launch_leaf_gemm(const Matrix& A, bool tA, const Matrix& B, bool tB, const TaskList& tl, const uint32_t* tile_list, size_t n,
                       char* ct) {
     Engine& e = engine();
+    const int variant = shared().gemm_variant.load();
     if (n == 0) return;
     const uint32_t nn = (uint32_t)n;
-    const bool fast64 = A.dtype == HBSM_F64 && e.gemm_variant != 1 && (A.b == 32 || A.b == 64 || A.b == 128 || A.b == 256);
+    const bool fast64 = A.dtype == HBSM_F64 && variant != 1 && (A.b == 32 || A.b == 64 || A.b == 128 || A.b == 256);
     if (fast64) {
         DevBuf<unsigned> counter(1);
         counter.zero();
         const double* At = (const double*)A.tiles.p;
         const double* Bt = (const double*)B.tiles.p;
         bool done = false;
-        if (e.gemm_variant == 0 || A.b == 256) {   // TMA-tiled kernel; falls back to the bulk-copy kernel if the driver refuses the map
+        if (variant == 0 || A.b == 256) {   // TMA-tiled kernel; falls back to the bulk-copy kernel if the driver refuses the map
             if (A.b == 64) done = launch_gemm_f64_tma<64, 64, 64>(tA, tB, A, B, tl.ab.p, tl.begin.p, nn, tile_list, counter.p, (double*)ct);
             else if (A.b == 32) done = launch_gemm_f64_tma<32, 32, 32>(tA, tB, A, B, tl.ab.p, tl.begin.p, nn, tile_list, counter.p, (double*)ct);
             else if (A.b == 128) done = launch_gemm_f64_tma<128, 128, 32>(tA, tB, A, B, tl.ab.p, tl.begin.p, nn, tile_list, counter.p, (double*)ct);
@@ -746,7 +749,7 @@ void launch_leaf_gemm(const Matrix& A, bool tA, const Matrix& B, bool tB, const 
         return;   // `counter` is released in stream order
     }
     bool done = false;
-    if (A.dtype == HBSM_F32 && e.gemm_variant != 1) {   // fp32: split-TF32 on tcgen05 (gemm_f32.cu) for b in {32,64,128,256}
+    if (A.dtype == HBSM_F32 && variant != 1) {   // fp32: split-TF32 on tcgen05 (gemm_f32.cu) for b in {32,64,128,256}
         DevBuf<unsigned> counter(1);
         counter.zero();
         done = launch_gemm_f32_tc(A, tA, B, tB, tl.ab.p, tl.begin.p, nn, tile_list, counter.p, (float*)ct);
@@ -766,7 +769,7 @@ void launch_leaf_gemm(const Matrix& A, bool tA, const Matrix& B, bool tB, const 
     }
 }
 
-// a product between op_product_begin and op_product_finish (one at a time: the engine has one stream)
+// a product between op_product_begin and op_product_finish (one at a time per host thread)
 struct PendingProduct {
     bool active = false;
     const Matrix* A = nullptr; const Matrix* B = nullptr; Matrix* C = nullptr;
@@ -783,7 +786,7 @@ struct PendingProduct {
     EventTimer t_total, t_norm, t_index, t_task, t_gemm, t_gemm2;
 };
 PendingProduct& pending() {
-    static PendingProduct p;
+    thread_local PendingProduct p;   // per host thread: products of different threads do not meet
     return p;
 }
 
@@ -806,9 +809,23 @@ void op_product_begin(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix
     if (3 * kbits > 64) throw Error(HBSM_E_ARG, "hbsm_b200: block grid too deep for 64-bit task keys (depth > 21)");
 
     P.t_norm.start();
-    if (o.spamm && !o.updated) {   // the reference's updated=false path is a use-after-free (H:6294-6307): refresh instead
-        update_norms(const_cast<Matrix&>(A));
-        if (&B != &A) update_norms(const_cast<Matrix&>(B));
+    // updated=false: the reference copies A and B, refreshes the COPIES and leaves the operands' caches alone (H:3990-4005;
+    // its batched build then reads freed memory, H:6294-6307).  Same contract here: fresh leaf norms into temporaries.
+    DevBuf<char> fresh_a, fresh_b;
+    const void* an = nullptr;
+    const void* bn = nullptr;
+    if (o.spamm && !o.updated) {
+        if (B.n_halo > 0) throw Error(HBSM_E_ARG, "hbsm_b200: spamm(updated=false) on an operand with a committed halo");
+        fresh_a.alloc(std::max<size_t>(A.L, 1) * A.esize());
+        compute_leaf_norms(A, fresh_a.p);
+        an = fresh_a.p;
+        if (&B != &A) {
+            fresh_b.alloc(std::max<size_t>(B.L, 1) * B.esize());
+            compute_leaf_norms(B, fresh_b.p);
+            bn = fresh_b.p;
+        } else {
+            bn = an;
+        }
     }
     P.t_norm.stop();
     P.t_index.start();
@@ -818,7 +835,7 @@ void op_product_begin(const Matrix& A, bool tA, const Matrix& B, bool tB, Matrix
 
     P.t_task.start();
     P.tl = TaskList();
-    build_tasks(A, tA, B, tB, o, kbits, P.tl, false);
+    build_tasks(A, tA, B, tB, o, kbits, P.tl, false, 0, (size_t)-1, an, bn);
     P.n_later = 0;
     DevBuf<uint32_t>& first = P.first;
     first.release();
@@ -911,7 +928,7 @@ void op_product_to_host(const Matrix& A, bool tA, const Matrix& B, bool tB, Matr
                         size_t cap_tiles, int n_chunks, size_t* n_mults, size_t* n_blocks) {
     ensure_engine();
     Engine& e = engine();
-    static cudaStream_t copy_stream = nullptr;
+    thread_local cudaStream_t copy_stream = nullptr;
     if (!copy_stream) HB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     op_product_begin(A, tA, B, tB, C, o, /*defer_halo_tiles=*/false, /*launch=*/false, /*launch_in_finish=*/false);
     PendingProduct& P = pending();
@@ -1017,7 +1034,7 @@ struct SideStreams {
     cudaStream_t h2d = nullptr, d2h = nullptr;
 };
 SideStreams& side_streams() {
-    static SideStreams s;
+    thread_local SideStreams s;
     if (!s.h2d) {
         HB_CUDA(cudaStreamCreateWithFlags(&s.h2d, cudaStreamNonBlocking));
         HB_CUDA(cudaStreamCreateWithFlags(&s.d2h, cudaStreamNonBlocking));
@@ -1276,6 +1293,10 @@ void op_product_from_host(Matrix& A, const HostTiles& ha, bool tA, Matrix& B, co
         throw;
     }
     destroy_events();
+    if (n_ct > 0) {   // C's table may still be merging on this thread's stream: later calls on C order themselves behind it
+        if (!C.pending_ev) HB_CUDA(cudaEventCreateWithFlags(&C.pending_ev, cudaEventDisableTiming));
+        HB_CUDA(cudaEventRecord(C.pending_ev, e.stream));
+    }
     C.n_mults = P_total;
     if (n_mults) *n_mults = P_total;
     if (n_blocks) *n_blocks = C.L;

@@ -6,6 +6,9 @@
 // The quadtree only exists on the wire: it is rebuilt from / flattened into the Morton block table here (host code; the
 // tiles cross PCIe once).  Inner-node norms on the wire are the hierarchical sums of the cached leaf norms (what
 // update_internal_info leaves behind, H:3918-3923); the root carries the matrix' cached root norm and multiply counter.
+// Known divergence: the flat table keeps ONE n_block_multiplies per matrix, so non-root nodes are written with counter 0; the
+// reference's product results carry per-node counters on inner nodes of C (H:2186-2194 sets the root only, but add() sums
+// children's counters, H:1719).  Root counter, structure, norms and values are byte-identical (tests/golden/wire_format_*).
 #include "matrix.cuh"
 
 namespace hbsm_b200 {
@@ -109,7 +112,10 @@ struct Parsed {
     std::vector<char> norms, tiles;
 };
 
-void read_node(const char* p, size_t size, size_t esize, int b, uint32_t r, uint32_t c, Parsed& out) {
+// level = levels remaining below this node (the root carries the matrix's virtual depth, a leaf 0): a buffer whose tree does
+// not have the shape the header dimensions imply (H:544-585: nRows halves per level, leaves only at level 0) is rejected
+// instead of being read into the wrong block coordinates
+void read_node(const char* p, size_t size, size_t esize, int b, int level, uint32_t r, uint32_t c, Parsed& out) {
     const char* end = p + size;
     if (size < header_bytes(esize)) throw_ref("Error in HierarchicalBlockSparseMatrix::assign_from_buffer(): buffer too small.");
     const int nRows = take<int>(p);
@@ -121,17 +127,20 @@ void read_node(const char* p, size_t size, size_t esize, int b, uint32_t r, uint
     size_t cs[4];
     for (int q = 0; q < 4; ++q) cs[q] = take<size_t>(p);
     if (bs != b) throw Error(HBSM_E_ARG, "hbsm_b200: assign_from_buffer: inconsistent blocksize inside the buffer");
+    if (level < 0 || (long long)nRows != ((long long)b << level))
+        throw Error(HBSM_E_ARG, "hbsm_b200: assign_from_buffer: node size does not match its level in the tree");
     bool any = false;
     for (int q = 0; q < 4; ++q) {
         if (!cs[q]) continue;
         any = true;
-        if (p + cs[q] > end) throw_ref("Error in HierarchicalBlockSparseMatrix::assign_from_buffer(): buffer too small.");
-        read_node(p, cs[q], esize, b, 2 * r + (q & 1), 2 * c + ((q >> 1) & 1), out);   // digit = 2*colbit + rowbit
+        if (cs[q] > (size_t)(end - p)) throw_ref("Error in HierarchicalBlockSparseMatrix::assign_from_buffer(): buffer too small.");
+        if (level == 0) throw Error(HBSM_E_ARG, "hbsm_b200: assign_from_buffer: a lowest-level node has children");
+        read_node(p, cs[q], esize, b, level - 1, 2 * r + (q & 1), 2 * c + ((q >> 1) & 1), out);   // digit = 2*colbit + rowbit
         p += cs[q];
     }
     if (!any && p < end) {   // leaf: the rest is the dense block
         const size_t tb = (size_t)b * b * esize;
-        if ((size_t)(end - p) != tb || nRows != b)
+        if ((size_t)(end - p) != tb || level != 0)
             throw Error(HBSM_E_ARG, "hbsm_b200: assign_from_buffer: malformed leaf record");
         out.bi.push_back((int)r); out.bj.push_back((int)c);
         out.norms.insert(out.norms.end(), norm_p, norm_p + esize);
@@ -183,7 +192,7 @@ void deserialize(Matrix& A, const char* buf, size_t size) {
     ensure_engine();
     A.resize(M, N);
     Parsed parsed;
-    read_node(buf, size, es, b, 0, 0, parsed);
+    read_node(buf, size, es, b, A.vdepth(), 0, 0, parsed);
     if (!parsed.bi.empty()) {
         if (A.vdepth() == 0) {
             HB_CUDA(cudaMemcpyAsync(A.tiles.p, parsed.tiles.data(), A.tile_bytes(), cudaMemcpyHostToDevice, engine().stream));

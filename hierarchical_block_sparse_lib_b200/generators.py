@@ -44,6 +44,35 @@ def decay_coo(n, lam, W, seed, symmetric=False, dtype=np.float64, rows=None):
     return r.astype(np.int32), c.astype(np.int32), v.astype(dtype)
 
 
+def decay_coo_block(n, lam, W, seed, r0, r1, c0, c1, symmetric=False, dtype=np.float64):
+    """The entries of the same banded decay matrix inside rows [r0,r1) x columns [c0,c1), as COO triplets with GLOBAL indices."""
+    table = np.exp(-float(lam) * np.arange(W + 1, dtype=np.float64))
+    r0, r1, c0, c1 = max(0, r0), min(n, r1), max(0, c0), min(n, c1)
+    if r0 >= r1 or c0 >= c1:
+        z = np.zeros(0, np.int32)
+        return z, z.copy(), np.zeros(0, dtype)
+    r, c = np.meshgrid(np.arange(r0, r1, dtype=np.int64), np.arange(c0, c1, dtype=np.int64), indexing="ij")
+    r = r.ravel(); c = c.ravel()
+    d = np.abs(r - c)
+    keep = d <= W
+    r = r[keep]; c = c[keep]; d = d[keep]
+    u = hash_u01(seed, np.minimum(r, c), np.maximum(r, c)) if symmetric else hash_u01(seed, r, c)
+    v = (0.5 + 0.5 * u) * table[d]
+    return r.astype(np.int32), c.astype(np.int32), v.astype(dtype)
+
+
+def task_hash(ci, cj, k):
+    """Per-product hash of the engine's hbsm_task_checksum: splitmix64(ci << 42 | cj << 21 | k); the checksum of a set of
+    products is the sum of these modulo 2^64."""
+    ci = np.asarray(ci, np.uint64); cj = np.asarray(cj, np.uint64); k = np.asarray(k, np.uint64)
+    return splitmix64((ci << np.uint64(42)) | (cj << np.uint64(21)) | k)
+
+
+def task_checksum(ci, cj, k):
+    with np.errstate(over="ignore"):
+        return int(np.sum(task_hash(ci, cj, k), dtype=np.uint64))
+
+
 def decay_tiles(n, b, lam, W, seed, symmetric=False, dtype=np.float64, tile_rows=None):
     """Same matrix as decay_coo but as whole column-major tiles: returns (bi, bj, tiles[n_tiles, b*b])."""
     g = -(-n // b)

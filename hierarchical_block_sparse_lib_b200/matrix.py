@@ -246,6 +246,23 @@ class HierarchicalBlockSparseMatrix:
             check(lib().hbsm_export_tasks(self._h, n.value, _ptr(ci), _ptr(cj), _ptr(k), C.byref(n)))
         return np.stack([ci, cj, k], 1)
 
+    def task_checksum(self):
+        """Order-independent checksum of the executed-product set: sum of splitmix64(ci<<42 | cj<<21 | k) mod 2^64."""
+        v = C.c_uint64(0)
+        check(lib().hbsm_task_checksum(self._h, C.byref(v)))
+        return int(v.value)
+
+    def tile_tasks(self, bi, bj):
+        """The k's (ascending) of the products accumulated into tile (bi, bj) of this product result; None if absent."""
+        n = C.c_size_t(0); found = C.c_int(0)
+        check(lib().hbsm_export_tile_tasks(self._h, int(bi), int(bj), 0, None, C.byref(n), C.byref(found)))
+        if not found.value:
+            return None
+        k = np.zeros(n.value, np.int64)
+        if n.value:
+            check(lib().hbsm_export_tile_tasks(self._h, int(bi), int(bj), n.value, _ptr(k), C.byref(n), C.byref(found)))
+        return k
+
     def export_leaves(self, tiles=True, norms=True):
         n = self.get_n_blocks()
         b = self.get_params().blocksize

@@ -337,7 +337,7 @@ def _exchange_b_engine(A_loc, tA, B_loc, tB, b_keys, b_norms, b_tiles, grid_side
     rows = hi - lo
     t0 = time.perf_counter()
     tr = _Trace(timers.setdefault("trace", {}) if timers is not None else None)
-    thr = torch.empty((grid_side,), dtype=b_norms.dtype, device=b_norms.device)
+    thr = torch.full((grid_side,), -1.0, dtype=b_norms.dtype, device=b_norms.device)   # the engine fills A's grid only
     _capi.check(L.hbsm_halo_request(A_loc._h, int(bool(tA)), C.c_void_p(thr.data_ptr())))
     tr.mark("request")
     thr_in = torch.empty_like(thr)
@@ -489,6 +489,7 @@ def _sharded_product_overlapped(A_loc, tA, B_loc, tB, spamm, tau, group, timers,
                 except Exception:
                     pass
             torch.cuda.synchronize()
+            Lc.hbsm_product_abort()      # a begin without its finish must not block every later product
         _capi.check(Lc.hbsm_halo_commit(B_loc._h, 0))
     tr.mark("halo_drop")
     if timers is not None:
@@ -540,7 +541,7 @@ def sharded_product(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, group=None, time
         if table is not None and table.counts[dist.get_rank(group)] != bk.numel():
             raise RuntimeError("sharded_product: the published table of B is stale (B changed after publish())")
         if table is not None and os.environ.get("HBSM_SHARD_TORCH_PLAN", "0") != "1":
-            thr = torch.empty((grid_side,), dtype=bn.dtype, device=bn.device)
+            thr = torch.full((grid_side,), -1.0, dtype=bn.dtype, device=bn.device)   # the engine fills A's grid only
             _capi.check(_capi.lib().hbsm_halo_request(A_loc._h, int(bool(tA)), C.c_void_p(thr.data_ptr())))
             keys, norms, tiles = exchange_b_published(thr, table, bt, tB, spamm, tau, group, timers, recv_alloc, engine=True)
         elif os.environ.get("HBSM_SHARD_TORCH_PLAN", "0") == "1":     # same plan with torch ops (what the gloo tests run)

@@ -9,9 +9,12 @@
  * Differences a caller can observe (all documented in INTEGRATION.md):
  *   - Treal must be double or float (the reference's BLAS shim offers exactly these, gblas.h:85-143);
  *   - copy construction / assignment is a deep copy (the reference's implicit copy shares children by shared_ptr);
- *   - spamm(..., updated=false) refreshes the operands' norms (the reference's path is a use-after-free, H:6294-6307);
- *   - the a-priori estimators (count_skips, get_spamm_errors, ...) and inv_chol are declared and throw
- *     "not provided by hbsm_b200"; serialisation, truncation and the small utilities are implemented.
+ *   - spamm(..., updated=false) tests against freshly computed leaf norms and leaves the operands' cached norms
+ *     untouched, which is what the reference intends (it refreshes COPIES of A and B, H:3990-4005) but cannot deliver
+ *     in its batched build (use-after-free, H:6294-6307);
+ *   - the dead recursive multiply (compiled out by the reference's own flags) and adjust_sizes throw
+ *     "not provided by hbsm_b200"; the a-priori estimators, inv_chol, serialisation, truncation and the small
+ *     utilities are implemented.
  */
 #ifndef HBSM_B200_HIERARCHICAL_BLOCK_SPARSE_MATRIX_H
 #define HBSM_B200_HIERARCHICAL_BLOCK_SPARSE_MATRIX_H

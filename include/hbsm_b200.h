@@ -108,6 +108,8 @@ int hbsm_spamm(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, doub
 int hbsm_product_begin(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, int spamm, double tau, int updated,
                        int defer_halo_tiles);
 int hbsm_product_finish(hbsm_handle C, void* cuda_event_or_null, size_t* n_block_multiplies, size_t* n_resizes);
+/* drops the calling thread's product in flight, if any (a caller whose transfer failed between begin and finish) */
+int hbsm_product_abort(void);
 /* the same begin with the symmetric-family option: upper_only != 0 plans only the C tiles with ci <= cj and finish zeroes
  * the strict lower part of the diagonal tiles (symm_square H:3563 / symm_rk H:3711 on an expanded operand; sharded:
  * triu(op(A)*op(B)) of the rank's block rows) */
@@ -174,6 +176,12 @@ int hbsm_symm_square_spamm(hbsm_handle A, hbsm_handle C, double tau, size_t* n_b
 /* ---- parity / bench hooks ---- */
 /* executed products of the call that produced C, sorted by (Morton key of (ci,cj), k); cap=0 -> count */
 int hbsm_export_tasks(hbsm_handle C, size_t cap, int64_t* ci, int64_t* cj, int64_t* k, size_t* n);
+/* order-independent checksum of that executed-product set: sum over products of splitmix64(ci<<42 | cj<<21 | k) mod 2^64
+ * (the per-rank checksums of a sharded product add up to the single-GPU value) */
+int hbsm_task_checksum(hbsm_handle C, uint64_t* out);
+/* the k's (ascending) of the products accumulated into C tile (bi, bj); *found = 0 if C has no such tile; cap too small ->
+ * only *n is set */
+int hbsm_export_tile_tasks(hbsm_handle C, int bi, int bj, size_t cap, int64_t* k, size_t* n, int* found);
 /* leaves in ascending Morton order; norms/tiles may be NULL; cap=0 -> count */
 int hbsm_export_leaves(hbsm_handle h, size_t cap, int64_t* bi, int64_t* bj, void* norms_cached, void* tiles, size_t* n);
 int hbsm_stage_times_last(hbsm_stage_times* out);

@@ -133,3 +133,45 @@ def test_flat_rule_equals_hierarchical_rule_on_port():
         flat = [(i, j, k) for i, k, na in zip(abi, abj, an) for kk, j, nb in zip(bbi, bbj, bn)
                 if kk == k and na * nb > np.float64(tau) * np.float64(tau)]
         assert np.array_equal(sort_tasks(t), sort_tasks(np.array(flat).reshape(-1, 3)))
+
+
+@pytest.mark.parametrize("dtype,spamm,tau", [(np.float64, True, 1e-4), (np.float64, False, 0.0), (np.float32, True, 1e-3)])
+def test_single_tile_subproblem_is_the_full_products_tile(dtype, spamm, tau):
+    """oracle/sampled_check.reference_tile (block row of A times block column of B, run through the unmodified
+    reference) gives, for every sampled C tile, exactly the k-list and the values of that tile in the reference's
+    FULL product -- the property bench.py --check and the full-size GPU tests rely on."""
+    if not po.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from oracle import sampled_check as sc
+    n, b, lam = 1024, 32, 0.08
+    W = min(G.decay_width(lam), n - 1)
+    (ra, ca, va) = G.decay_coo(n, lam, W, 1, dtype=dtype)
+    (rb, cb, vb) = G.decay_coo(n, lam, W, 2, dtype=dtype)
+    A = po.from_coo(po.RefMatrix, b, n, n, ra, ca, va, dtype)
+    B = po.from_coo(po.RefMatrix, b, n, n, rb, cb, vb, dtype)
+    Cf, nm, nb, tasks = po.RefMatrix.product(A, 0, B, 0, spamm=spamm, tau=tau, want_tasks=True)
+    D = Cf.to_dense()
+    cbi, cbj, _, _ = Cf.leaves(tiles=False)
+    abi, abj, an, _ = A.leaves(tiles=False)
+    have = set(zip(cbi.tolist(), cbj.tolist()))
+    rng = np.random.default_rng(3)
+    for t in [0, len(cbi) - 1] + list(rng.integers(0, len(cbi), 6)):
+        ci, cj = int(cbi[t]), int(cbj[t])
+        ks, tile, a_n, b_n = sc.reference_tile(po.RefMatrix, n, b, lam, W, (1, 2), ci, cj, spamm, tau, dtype)
+        want = np.sort(tasks[(tasks[:, 0] == ci) & (tasks[:, 1] == cj), 2])
+        assert np.array_equal(ks, want)
+        want_tile = D[ci * b:(ci + 1) * b, cj * b:(cj + 1) * b].astype(np.float64)
+        assert tile is not None
+        assert np.linalg.norm(tile - want_tile) <= (1e-6 if dtype == np.float32 else 1e-14) * np.linalg.norm(want_tile)
+        for k, v in a_n.items():       # same leaves => bit-identical leaf norms
+            assert v == an[(abi == ci) & (abj == k)][0]
+    if spamm:                          # a coordinate outside C's structure: nothing executed in the sub-problem either
+        ci = int(cbi[len(cbi) // 2])
+        cj = max(j for (i, j) in have if i == ci) + 1
+        if cj < n // b:
+            ks, tile, _, _ = sc.reference_tile(po.RefMatrix, n, b, lam, W, (1, 2), ci, cj, spamm, tau, dtype)
+            assert len(ks) == 0
+    # the flat-rule checksum over the reference's leaf norms equals the checksum of the reference's executed set
+    bbi, bbj, bn, _ = B.leaves(tiles=False)
+    cs, cnt = sc.flat_rule_checksum(abi, abj, an, bbi, bbj, bn, spamm, tau, dtype)
+    assert cnt == nm and cs == G.task_checksum(tasks[:, 0], tasks[:, 1], tasks[:, 2])
