@@ -567,8 +567,14 @@ def sharded_product(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, group=None, time
 # ---------------------------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1): strong scaling of the BASELINE workload, one rank per GPU under torchrun
 # ---------------------------------------------------------------------------------------------------
-def bench_main(args, w, workload_config, fp64_peak, ClockSampler):
+def bench_main(args, w, bm):
+    """bm = the bench.py module (config text, peaks, clock sampler, parity check)."""
     import json
+    workload_config = lambda world_: bm.case_config(w, world_, args.config)
+    fp64_peak = bm.fp64_peak
+    ClockSampler = bm.ClockSampler
+    if w["op"] != "spamm" or w["dtype"] != "f64" or w["tA"] or w["tB"]:
+        raise SystemExit("bench.py --gpus N>1 runs the fp64 SpAMM NN cases (headline, --config 2, --config 4)")
     import hierarchical_block_sparse_lib_b200 as hb
     from . import _capi
     from . import generators as G
@@ -578,11 +584,11 @@ def bench_main(args, w, workload_config, fp64_peak, ClockSampler):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hb.init(local_rank)
     n, b, lam, tau = w["n"], w["b"], w["lam"], w["tau"]
-    W = G.decay_width(lam, w["eps"])
+    W = G.decay_width(lam, 1e-12)
     g = n // b
     lo, hi = slab_bounds(g, world, rank)
-    A = H(np.float64, b); A.generate_decay(n, lam, W, w["seeds"][0], False, lo, hi); A.update_internal_info()
-    B = H(np.float64, b); B.generate_decay(n, lam, W, w["seeds"][1], False, lo, hi); B.update_internal_info()
+    A = H(np.float64, b); A.generate_decay(n, lam, W, 1, False, lo, hi); A.update_internal_info()
+    B = H(np.float64, b); B.generate_decay(n, lam, W, 2, False, lo, hi); B.update_internal_info()
     if os.environ.get("HBSM_SHARD_NO_PUBLISH", "0") != "1":
         publish(B)     # distributed half of update_internal_info(): outside the timed region like the norm refresh itself
     ext = torch.cuda.ExternalStream(int(_capi.lib().hbsm_stream()))
@@ -629,7 +635,16 @@ def bench_main(args, w, workload_config, fp64_peak, ClockSampler):
     P = int(sums[0])
     flops = 2.0 * b ** 3 * P
 
-    e2e = _e2e_sharded(hb, H, A, B, w, max(1, min(args.steps, 3)), lo, hi)
+    check = None
+    if not args.no_check:
+        try:
+            Cm, nm_c, nb_c = sharded_product(A, False, B, False, True, tau, None, None)
+            check = bm.run_check(w, [A, B], Cm, nm_c, max(2, -(-args.check_samples // world)), dist, torch)
+            del Cm
+        except Exception as ex:  # noqa: BLE001
+            check = {"pass": None, "error": repr(ex)}
+
+    e2e = None if args.no_e2e else _e2e_sharded(hb, H, A, B, w, max(1, min(args.steps, 3)), lo, hi)
 
     if rank == 0:
         peak, peak_src = fp64_peak()
@@ -646,7 +661,7 @@ def bench_main(args, w, workload_config, fp64_peak, ClockSampler):
                              "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peak_src,
                              "algorithmic": "2*b^3 flops per leaf product x %d products in rank 0's launch" % nm,
                              "kernel_ms": g_ms, "share_of_step": g_ms / ms, "traffic": None},
-                "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(sums[3]), "clocks": clocks}
+                "check": check, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(sums[3]), "clocks": clocks}
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()
 
