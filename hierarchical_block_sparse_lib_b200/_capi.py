@@ -99,13 +99,22 @@ SIGNATURES = {
     "hbsm_set_gemm_variant": (_I, [_I]),
     "hbsm_device_table": (_I, [_H, C.POINTER(_sz), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "hbsm_assign_device_tiles": (_I, [_H, _sz, _P, _P, _P]),
-    "hbsm_halo_request": (_I, [_H, _I, _P]),
-    "hbsm_halo_select": (_I, [_H, _I, _P, _I, _I, _I, _I, _I, C.c_double, _P, C.POINTER(_sz)]),
-    "hbsm_halo_mask": (_I, [_I, _P, _P, _P, _sz, _sz, _sz, _I, C.c_double, _P]),
-    "hbsm_compact_flags": (_I, [_P, _sz, _sz, C.POINTER(_sz), _sz, _P, C.POINTER(_sz)]),
-    "hbsm_halo_plan": (_I, [_H, _I, _H, _P, _P, _P, _sz, _I, _I, _P, _I, C.c_double, _P, _P, C.POINTER(_sz), C.POINTER(_P)]),
     "hbsm_halo_reserve": (_I, [_H, _sz, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "hbsm_halo_commit": (_I, [_H, _sz]),
+    "hbsm_comm_set_library": (_I, [C.c_char_p]),
+    "hbsm_comm_unique_id": (_I, [_P]),
+    "hbsm_comm_init": (_I, [_P, _I, _I]),
+    "hbsm_comm_finalize": (_I, []),
+    "hbsm_comm_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "hbsm_comm_barrier": (_I, []),
+    "hbsm_comm_allreduce_f64": (_I, [C.POINTER(C.c_double), _I, _I]),
+    "hbsm_comm_allgather_u64": (_I, [C.POINTER(C.c_uint64), _sz, C.POINTER(C.c_uint64)]),
+    "hbsm_shard_rows": (_I, [_I, _I, _I, C.POINTER(_I), C.POINTER(_I)]),
+    "hbsm_shard_rows_balanced": (_I, [C.POINTER(C.c_uint64), _I, _I, C.POINTER(_I)]),
+    "hbsm_publish": (_I, [_H]),
+    "hbsm_sharded_product": (_I, [_H, _I, _H, _I, _H, _I, C.c_double, _I, C.POINTER(_sz), C.POINTER(_sz)]),
+    "hbsm_sharded_row_weights": (_I, [_H, _I, _H, _I, _I, C.c_double, _I, _I, _P]),
+    "hbsm_shard_stats_last": (_I, [_P]),
     "hbsm_generate_decay": (_I, [_H, _I, _P, _I, C.c_uint64, _I, _I, _I]),
     "hbsm_morton_encode": (C.c_uint64, [C.c_uint32, C.c_uint32]),
     "hbsm_morton_decode": (None, [C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

@@ -446,44 +446,12 @@ int hbsm_assign_device_tiles(hbsm_handle h, size_t n_tiles, const uint64_t* d_mo
         assign_tiles_device(M(h), n_tiles, d_morton_keys, d_tiles, d_norms_or_null);
     });
 }
-int hbsm_halo_request(hbsm_handle A, int tA, void* d_thr) {
-    return guarded([&] { halo_request(M(A), tA != 0, d_thr); });
-}
-int hbsm_halo_select(hbsm_handle B, int tB, const void* d_thr_in, int world, int rank, int lo, int rows, int spamm, double tau,
-                     int64_t* d_send_idx, size_t* counts) {
-    return guarded([&] {
-        if (world < 1 || rank < 0 || rank >= world || lo < 0 || rows < 0 || !counts) throw Error(HBSM_E_ARG, "hbsm_b200: bad halo_select arguments");
-        halo_select(M(B), tB != 0, d_thr_in, world, rank, (uint32_t)lo, (uint32_t)rows, spamm != 0, tau, d_send_idx, counts);
-    });
-}
-int hbsm_halo_mask(int dtype, const void* d_thr, const int64_t* d_k_all, const void* d_norms_all, size_t n_all, size_t own_lo,
-                   size_t own_hi, int spamm, double tau, uint8_t* d_need) {
-    return guarded([&] {
-        if (dtype != HBSM_F64 && dtype != HBSM_F32) throw Error(HBSM_E_ARG, "hbsm_b200: bad dtype");
-        halo_mask(dtype, d_thr, d_k_all, d_norms_all, n_all, own_lo, own_hi, spamm != 0, tau, d_need);
-    });
-}
-int hbsm_compact_flags(const uint8_t* d_flags, size_t n, size_t n_edges, const size_t* edges, size_t modulo, int64_t* d_idx,
-                       size_t* counts) {
-    return guarded([&] {
-        if (n_edges < 1 || !edges || !counts) throw Error(HBSM_E_ARG, "hbsm_b200: bad compact_flags arguments");
-        compact_flags(d_flags, n, n_edges, edges, modulo, d_idx, counts);
-    });
-}
-int hbsm_halo_plan(hbsm_handle A, int tA, hbsm_handle B, const uint64_t* d_keys_all, const int64_t* d_k_all,
-                   const void* d_norms_all, size_t n_all, int world, int rank, const size_t* offsets, int spamm, double tau,
-                   uint8_t* d_need, size_t* recv_counts, size_t* n_in, void** d_tail_tiles) {
-    return guarded([&] {
-        halo_plan(M(A), tA != 0, M(B), d_keys_all, d_k_all, d_norms_all, n_all, world, rank, offsets, spamm != 0, tau, d_need,
-                  recv_counts, n_in, d_tail_tiles);
-    });
-}
 int hbsm_halo_reserve(hbsm_handle h, size_t capacity, uint64_t** d_keys, void** d_norms, void** d_tiles) {
     return guarded([&] { reserve_halo(M(h), capacity, d_keys, d_norms, d_tiles); });
 }
 int hbsm_halo_commit(hbsm_handle h, size_t n_halo) {
     return guarded([&] {
-        HB_CUDA(cudaDeviceSynchronize());   // the tail was filled on the caller's (NCCL) stream: order it before ours
+        HB_CUDA(cudaDeviceSynchronize());   // the tail was filled on the caller's (transport) stream: order it before ours
         commit_halo(M(h), n_halo);
     });
 }
@@ -497,5 +465,73 @@ void hbsm_morton_decode(uint64_t key, uint32_t* bi, uint32_t* bj) {
     if (bj) *bj = morton_col(key);
 }
 void* hbsm_stream(void) { return (void*)engine().stream; }
+
+// ---- multi-GPU (sharded.cu) ----
+int hbsm_comm_set_library(const char* path) { return guarded([&] { comm_set_library(path); }); }
+int hbsm_comm_unique_id(void* id_out) {
+    return guarded([&] {
+        if (!id_out) throw Error(HBSM_E_ARG, "hbsm_b200: comm_unique_id: null buffer");
+        comm_unique_id(id_out);
+    });
+}
+int hbsm_comm_init(const void* id, int rank, int world) {
+    return guarded([&] {
+        if (!id) throw Error(HBSM_E_ARG, "hbsm_b200: comm_init: null id");
+        comm_init(id, rank, world);
+    });
+}
+int hbsm_comm_finalize(void) { return guarded([&] { comm_finalize(); }); }
+int hbsm_comm_info(int* rank, int* world, int* nccl_version) { return guarded([&] { comm_info(rank, world, nccl_version); }); }
+int hbsm_comm_barrier(void) { return guarded([&] { comm_barrier(); }); }
+int hbsm_comm_allreduce_f64(double* vals, int n, int take_max) { return guarded([&] { comm_allreduce_f64(vals, n, take_max != 0); }); }
+int hbsm_comm_allgather_u64(const uint64_t* mine, size_t n, uint64_t* all) { return guarded([&] { comm_allgather_u64(mine, n, all); }); }
+int hbsm_shard_rows(int grid_side, int world, int rank, int* lo, int* hi) {
+    return guarded([&] {
+        if (grid_side < 1 || world < 1 || rank < 0 || rank >= world || !lo || !hi) throw Error(HBSM_E_ARG, "hbsm_b200: shard_rows: bad arguments");
+        *lo = (int)((long long)grid_side * rank / world);
+        *hi = (int)((long long)grid_side * (rank + 1) / world);
+    });
+}
+int hbsm_shard_rows_balanced(const uint64_t* w, int grid_side, int world, int* bounds) {
+    return guarded([&] {
+        if (!w || grid_side < 1 || world < 1 || !bounds) throw Error(HBSM_E_ARG, "hbsm_b200: shard_rows_balanced: bad arguments");
+        double total = 0;
+        for (int i = 0; i < grid_side; ++i) total += (double)w[i];
+        bounds[0] = 0;
+        double acc = 0;
+        int row = 0;
+        for (int r = 1; r < world; ++r) {   // boundary r: first row at which the prefix reaches r/world of the total (nearest side)
+            const double want = total * r / world;
+            while (row < grid_side && acc + (double)w[row] <= want) acc += (double)w[row++];
+            if (row < grid_side && want - acc > acc + (double)w[row] - want) acc += (double)w[row++];
+            bounds[r] = std::max(row, bounds[r - 1]);
+        }
+        bounds[world] = grid_side;
+    });
+}
+int hbsm_publish(hbsm_handle h) { return guarded([&] { publish(M(h)); }); }
+int hbsm_sharded_product(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, int spamm, double tau, int upper_only,
+                         size_t* n_block_multiplies, size_t* n_resizes) {
+    return guarded([&] {
+        ProductOpts o;
+        o.spamm = spamm != 0; o.tau = tau; o.updated = true; o.upper_only = upper_only != 0;
+        sharded_product(M(A), tA != 0, M(B), tB != 0, M(C), o, n_block_multiplies, n_resizes);
+    });
+}
+int hbsm_sharded_row_weights(hbsm_handle A, int tA, hbsm_handle B, int tB, int spamm, double tau, int upper_only, int grid_side,
+                             uint64_t* weights) {
+    return guarded([&] {
+        if (!weights) throw Error(HBSM_E_ARG, "hbsm_b200: row weights: null output");
+        ProductOpts o;
+        o.spamm = spamm != 0; o.tau = tau; o.updated = true; o.upper_only = upper_only != 0;
+        sharded_row_weights(M(A), tA != 0, M(B), tB != 0, o, grid_side, weights);
+    });
+}
+int hbsm_shard_stats_last(hbsm_shard_stats* out) {
+    return guarded([&] {
+        if (!out) throw Error(HBSM_E_ARG, "hbsm_b200: shard_stats_last: null");
+        *out = shard_stats_last();
+    });
+}
 
 }  // extern "C"

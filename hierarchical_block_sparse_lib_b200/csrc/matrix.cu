@@ -74,6 +74,7 @@ void Matrix::clear() {  // H:614
     L = 0; M = 0; N = 0; sized = false;
     halo_cap = 0; n_halo = 0;
     root_norm_cached = 0.0;
+    pub.reset();
 }
 
 void Matrix::resize(int m, int n) {  // H:544
@@ -95,6 +96,7 @@ void Matrix::set_table(DevBuf<uint64_t>&& k, DevBuf<char>&& t, size_t count) {
     tiles = std::move(t);
     L = count;
     halo_cap = 0; n_halo = 0;
+    pub.reset();
     norms.alloc(std::max<size_t>(count, 1) * esize());
     norms.zero();
     invalidate_indices();
@@ -742,110 +744,6 @@ __global__ void __launch_bounds__(256) k_decay_fill(const uint64_t* __restrict__
     }
 }
 
-// ---- multi-GPU halo planning (host-side orchestration in sharded.py) ----
-// request: thr[k] = max leaf norm^2 over this rank's op(A) tiles (., k), -1 where there is none.  Non-negative IEEE
-// values order like signed integers, and -1.0 is a negative integer, so a signed atomicMax on the bit pattern works.
-template <typename T> struct Bits;
-template <> struct Bits<double> { typedef long long I; };
-template <> struct Bits<float> { typedef int I; };
-template <typename T>
-__global__ void k_halo_fill(T* __restrict__ thr, uint32_t n) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) thr[i] = (T)-1;
-}
-template <typename T>
-__global__ void k_halo_request(const uint64_t* __restrict__ keys, const T* __restrict__ norms, size_t L, int by_row_k,
-                               T* __restrict__ thr) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L) return;
-    const uint32_t k = by_row_k ? morton_row(keys[i]) : morton_col(keys[i]);
-    typedef typename Bits<T>::I I;
-    T v = norms[i];
-    atomicMax(reinterpret_cast<I*>(thr) + k, *reinterpret_cast<I*>(&v));
-}
-// select: entry e = q * L + i asks "does peer q need my op(B) tile i?"  (k of the tile inside my slab, request >= 0,
-// and for SpAMM fl(max_na * nb) > fl(tau*tau): the leaf-pair predicate of H:2008 against the requester's best A tile)
-template <typename T>
-__global__ void k_halo_flags(const uint64_t* __restrict__ keys, const T* __restrict__ norms, size_t L, int by_col_k,
-                             const T* __restrict__ thr_in, int world, int rank, uint32_t lo, uint32_t rows, int spamm,
-                             T tau2, uint32_t* __restrict__ flags) {
-    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= (size_t)world * L) return;
-    const int q = (int)(e / L);
-    const size_t i = e % L;
-    const uint32_t k = by_col_k ? morton_col(keys[i]) : morton_row(keys[i]);
-    bool keep = false;
-    if (q != rank && k >= lo && k < lo + rows) {
-        const T t = thr_in[(size_t)q * rows + (k - lo)];
-        keep = t >= (T)0;
-        if (keep && spamm) keep = DT<T>::mul(t, norms[i]) > tau2;
-    }
-    flags[e] = keep ? 1u : 0u;
-}
-__global__ void k_halo_compact(const uint32_t* __restrict__ flags, const uint64_t* __restrict__ pos, size_t n, size_t L,
-                               int64_t* __restrict__ send_idx) {
-    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n || !flags[e]) return;
-    send_idx[pos[e]] = (int64_t)(e % L);
-}
-
-// published-table protocol: need[t] = 1 iff the published op(B) tile t (contraction index k_all[t], norm^2 norms_all[t])
-// is remote and touched by at least one product of this rank (request thr[k] as in k_halo_request)
-template <typename T>
-__global__ void k_halo_mask(const T* __restrict__ thr, const int64_t* __restrict__ k_all, const T* __restrict__ norms_all,
-                            size_t n_all, size_t own_lo, size_t own_hi, int spamm, T tau2, uint8_t* __restrict__ need) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_all) return;
-    bool keep = false;
-    if (i < own_lo || i >= own_hi) {
-        const T t = thr[k_all[i]];
-        keep = t >= (T)0;
-        if (keep && spamm) keep = DT<T>::mul(t, norms_all[i]) > tau2;
-    }
-    need[i] = keep ? 1 : 0;
-}
-__global__ void k_widen_u8(const uint8_t* __restrict__ in, size_t n, uint32_t* __restrict__ out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = in[i] ? 1u : 0u;
-}
-__global__ void k_compact_idx(const uint32_t* __restrict__ flags, const uint64_t* __restrict__ pos, size_t n, size_t modulo,
-                              int64_t* __restrict__ out) {
-    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n || !flags[e]) return;
-    out[pos[e]] = (int64_t)(modulo ? e % modulo : e);
-}
-
-// halo_plan: mask with a widened copy for the scan, edge read-back through the mailbox, tail fill from the published table
-template <typename T>
-__global__ void k_halo_mask_wide(const T* __restrict__ thr, const int64_t* __restrict__ k_all, const T* __restrict__ norms_all,
-                                 size_t n_all, size_t own_lo, size_t own_hi, int spamm, T tau2, uint8_t* __restrict__ need,
-                                 uint32_t* __restrict__ wide) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_all) return;
-    bool keep = false;
-    if (i < own_lo || i >= own_hi) {
-        const T t = thr[k_all[i]];
-        keep = t >= (T)0;
-        if (keep && spamm) keep = DT<T>::mul(t, norms_all[i]) > tau2;
-    }
-    need[i] = keep ? 1 : 0;
-    wide[i] = keep ? 1u : 0u;
-}
-struct EdgeList { uint64_t at[64]; int n; };
-__global__ void k_post_edges(const uint64_t* __restrict__ pos, EdgeList edges, volatile uint64_t* mailbox) {
-    if ((int)threadIdx.x < edges.n) mailbox[threadIdx.x] = pos[edges.at[threadIdx.x]];
-    __threadfence_system();
-}
-template <typename T>
-__global__ void k_halo_tail_fill(const uint32_t* __restrict__ flags, const uint64_t* __restrict__ pos, size_t n,
-                                 const uint64_t* __restrict__ keys_all, const T* __restrict__ norms_all,
-                                 uint64_t* __restrict__ tail_keys, T* __restrict__ tail_norms) {
-    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n || !flags[e]) return;
-    tail_keys[pos[e]] = keys_all[e];
-    tail_norms[pos[e]] = norms_all[e];
-}
-
 // frob_block_trunc (H:4904-4943): a subtree is dropped iff its (recomputed) norm^2 < trunc^2.  A node's norm^2 is a sum of
 // non-negative child norm^2 with monotone rounding, so a leaf survives iff its OWN norm^2 >= trunc^2 -- the flat rule.
 __global__ void k_trunc_flags(const void* __restrict__ norms, size_t n, int is_f64, double t2d, float t2f, uint32_t* __restrict__ keep) {
@@ -1209,6 +1107,7 @@ double hierarchical_norm(const Matrix& A, const void* d_leaf_norms) {
 }
 
 void update_norms(Matrix& A) {   // H:3905
+    A.pub.reset();   // a published (key, norm) table describes the previous norms
     if (A.L == 0) { A.root_norm_cached = 0.0; return; }
     compute_leaf_norms(A, A.norms.p);
     A.root_norm_cached = hierarchical_norm(A, A.norms.p);
@@ -1220,120 +1119,6 @@ double frob_squared(const Matrix& A) {   // H:641
     DevBuf<char> tmp(A.L * A.esize());
     compute_leaf_norms(A, tmp.p);
     return hierarchical_norm(A, tmp.p);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// multi-GPU halo planning
-// ---------------------------------------------------------------------------------------------------
-void halo_request(const Matrix& A, bool tA, void* d_thr) {
-    ensure_engine();
-    const uint32_t g = A.grid_side();
-    dispatch(A.dtype, [&](auto z) {
-        using T = decltype(z);
-        HB_LAUNCH(k_halo_fill<T>, blocks_for(g, 256), 256, 0, (T*)d_thr, g);
-        if (A.L) HB_LAUNCH(k_halo_request<T>, blocks_for(A.L, 256), 256, 0, A.keys.p, (const T*)A.norms.p, A.L, tA ? 1 : 0, (T*)d_thr);
-    });
-}
-
-void halo_select(const Matrix& B, bool tB, const void* d_thr_in, int world, int rank, uint32_t lo, uint32_t rows, bool spamm,
-                 double tau, int64_t* d_send_idx, size_t* h_counts) {
-    ensure_engine();
-    for (int q = 0; q < world; ++q) h_counts[q] = 0;
-    if (B.L == 0 || world <= 0) return;
-    const size_t n = (size_t)world * B.L;
-    DevBuf<uint32_t> flags(n);
-    dispatch(B.dtype, [&](auto z) {
-        using T = decltype(z);
-        const T tt = (T)tau;
-        HB_LAUNCH(k_halo_flags<T>, blocks_for(n, 256), 256, 0, B.keys.p, (const T*)B.norms.p, B.L, tB ? 1 : 0, (const T*)d_thr_in,
-                  world, rank, lo, rows, spamm ? 1 : 0, (T)(tt * tt), flags.p);
-    });
-    DevBuf<uint64_t> pos(n + 1);
-    exclusive_scan_u32(flags.p, pos.p, n);
-    HB_LAUNCH(k_halo_compact, blocks_for(n, 256), 256, 0, flags.p, pos.p, n, B.L, d_send_idx);
-    std::vector<uint64_t> edge((size_t)world + 1);
-    for (int q = 0; q <= world; ++q)
-        HB_CUDA(cudaMemcpyAsync(&edge[q], pos.p + (size_t)q * B.L, sizeof(uint64_t), cudaMemcpyDeviceToHost, engine().stream));
-    sync_stream();
-    for (int q = 0; q < world; ++q) h_counts[q] = (size_t)(edge[q + 1] - edge[q]);
-}
-
-void halo_mask(int dtype, const void* d_thr, const int64_t* d_k_all, const void* d_norms_all, size_t n_all, size_t own_lo,
-               size_t own_hi, bool spamm, double tau, uint8_t* d_need) {
-    ensure_engine();
-    if (n_all == 0) return;
-    dispatch(dtype, [&](auto z) {
-        using T = decltype(z);
-        const T tt = (T)tau;
-        HB_LAUNCH(k_halo_mask<T>, blocks_for(n_all, 256), 256, 0, (const T*)d_thr, d_k_all, (const T*)d_norms_all, n_all, own_lo,
-                  own_hi, spamm ? 1 : 0, (T)(tt * tt), d_need);
-    });
-}
-
-void compact_flags(const uint8_t* d_flags, size_t n, size_t n_edges, const size_t* edges, size_t modulo, int64_t* d_idx,
-                   size_t* counts) {
-    ensure_engine();
-    for (size_t q = 0; q + 1 < n_edges; ++q) counts[q] = 0;
-    if (n == 0) return;
-    DevBuf<uint32_t> wide(n);
-    HB_LAUNCH(k_widen_u8, blocks_for(n, 256), 256, 0, d_flags, n, wide.p);
-    DevBuf<uint64_t> pos(n + 1);
-    exclusive_scan_u32(wide.p, pos.p, n);
-    HB_LAUNCH(k_compact_idx, blocks_for(n, 256), 256, 0, wide.p, pos.p, n, modulo, d_idx);
-    std::vector<uint64_t> at(n_edges);
-    for (size_t q = 0; q < n_edges; ++q)
-        HB_CUDA(cudaMemcpyAsync(&at[q], pos.p + std::min(edges[q], n), sizeof(uint64_t), cudaMemcpyDeviceToHost, engine().stream));
-    sync_stream();
-    for (size_t q = 0; q + 1 < n_edges; ++q) counts[q] = (size_t)(at[q + 1] - at[q]);
-}
-
-// The rank-local half of the published-table protocol in one call: request thresholds of op(A), request mask over the
-// published table of op(B), receive counts per peer, and the halo tail of B filled with the keys and norms of the tiles that
-// will arrive (the tiles themselves follow over NCCL).  8 launches, one host sync, no PCIe copy.
-void halo_plan(const Matrix& A, bool tA, Matrix& B, const uint64_t* d_keys_all, const int64_t* d_k_all, const void* d_norms_all,
-               size_t n_all, int world, int rank, const size_t* offsets, bool spamm, double tau, uint8_t* d_need, size_t* recv_counts,
-               size_t* n_in_out, void** d_tail_tiles) {
-    ensure_engine();
-    Engine& e = engine();
-    if (world < 1 || world > 63 || rank < 0 || rank >= world) throw Error(HBSM_E_ARG, "hbsm_b200: halo_plan: bad world / rank");
-    if (A.dtype != B.dtype) throw Error(HBSM_E_ARG, "hbsm_b200: halo_plan: operands differ in dtype");
-    for (int q = 0; q < world; ++q) recv_counts[q] = 0;
-    *n_in_out = 0;
-    if (d_tail_tiles) *d_tail_tiles = nullptr;
-    if (n_all == 0) { commit_halo(B, 0); return; }
-    DevBuf<char> thr((size_t)A.grid_side() * A.esize());
-    halo_request(A, tA, thr.p);
-    DevBuf<uint32_t> wide(n_all);
-    DevBuf<uint64_t> pos(n_all + 1);
-    dispatch(A.dtype, [&](auto z) {
-        using T = decltype(z);
-        const T tt = (T)tau;
-        HB_LAUNCH(k_halo_mask_wide<T>, blocks_for(n_all, 256), 256, 0, (const T*)thr.p, d_k_all, (const T*)d_norms_all, n_all,
-                  offsets[rank], offsets[rank + 1], spamm ? 1 : 0, (T)(tt * tt), d_need, wide.p);
-    });
-    exclusive_scan_u32(wide.p, pos.p, n_all);
-    EdgeList el;
-    el.n = world + 1;
-    for (int q = 0; q <= world; ++q) el.at[q] = std::min(offsets[q], n_all);
-    HB_LAUNCH(k_post_edges, 1, 64, 0, pos.p, el, e.mailbox + 8);
-    sync_stream();
-    size_t n_in = 0;
-    for (int q = 0; q < world; ++q) {
-        recv_counts[q] = (size_t)(e.mailbox[8 + q + 1] - e.mailbox[8 + q]);
-        n_in += recv_counts[q];
-    }
-    *n_in_out = n_in;
-    if (n_in == 0) { commit_halo(B, 0); return; }
-    uint64_t* tk = nullptr;
-    void* tn = nullptr;
-    void* tt = nullptr;
-    reserve_halo(B, std::max(B.halo_cap, n_in > B.halo_cap ? std::max<size_t>(n_in + n_in / 4, 64) : n_in), &tk, &tn, &tt);
-    dispatch(A.dtype, [&](auto z) {
-        using T = decltype(z);
-        HB_LAUNCH(k_halo_tail_fill<T>, blocks_for(n_all, 256), 256, 0, wide.p, pos.p, n_all, d_keys_all, (const T*)d_norms_all, tk, (T*)tn);
-    });
-    commit_halo(B, n_in);
-    if (d_tail_tiles) *d_tail_tiles = tt;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -9,6 +9,7 @@
 // plus lazily built line indices (tiles grouped by block row or by block column) used by the task-list builder.
 #pragma once
 #include "common.cuh"
+#include <memory>
 
 namespace hbsm_b200 {
 
@@ -26,6 +27,16 @@ struct LineIndex {
     LineIndex(const LineIndex&) = delete;
     LineIndex& operator=(const LineIndex&) = delete;
     ~LineIndex() { if (ready_ev) cudaEventDestroy(ready_ev); }
+};
+
+// (Morton key, leaf norm^2) table of a row-sharded matrix gathered on every rank (sharded.cu, hbsm_publish): rank-major, each
+// rank's part in its own (ascending Morton) tile order
+struct Published {
+    int world = 0, rank = 0;
+    std::vector<size_t> offsets;   // [world + 1]
+    size_t n_all = 0;
+    DevBuf<uint64_t> keys_all;     // [n_all]
+    DevBuf<char> norms_all;        // [n_all] Treal
 };
 
 struct Matrix {
@@ -52,6 +63,7 @@ struct Matrix {
     // set by the one call that returns before its device work on this matrix is complete (hbsm_product_from_host: C's table
     // is still merging when the host results are done); the next C-ABI call on the handle orders itself behind it
     cudaEvent_t pending_ev = nullptr;
+    std::unique_ptr<Published> pub;   // valid until the matrix (or its cached norms) changes
     Matrix() {}
     Matrix(const Matrix&) = delete;
     Matrix& operator=(const Matrix&) = delete;
@@ -98,16 +110,6 @@ double frob_squared(const Matrix& A);
 const LineIndex& line_index(const Matrix& A, bool by_col, bool with_halo = false);
 void reserve_halo(Matrix& A, size_t cap, uint64_t** d_keys, void** d_norms, void** d_tiles);   // tail pointers
 void commit_halo(Matrix& A, size_t n_halo);
-void halo_request(const Matrix& A, bool tA, void* d_thr);
-void halo_mask(int dtype, const void* d_thr, const int64_t* d_k_all, const void* d_norms_all, size_t n_all, size_t own_lo,
-               size_t own_hi, bool spamm, double tau, uint8_t* d_need);
-void compact_flags(const uint8_t* d_flags, size_t n, size_t n_edges, const size_t* edges, size_t modulo, int64_t* d_idx,
-                   size_t* counts);
-void halo_plan(const Matrix& A, bool tA, Matrix& B, const uint64_t* d_keys_all, const int64_t* d_k_all, const void* d_norms_all,
-               size_t n_all, int world, int rank, const size_t* offsets, bool spamm, double tau, uint8_t* d_need, size_t* recv_counts,
-               size_t* n_in, void** d_tail_tiles);
-void halo_select(const Matrix& B, bool tB, const void* d_thr_in, int world, int rank, uint32_t lo, uint32_t rows, bool spamm,
-                 double tau, int64_t* d_send_idx, size_t* h_counts);
 void op_add(const Matrix& A, const Matrix& B, Matrix& C);
 void op_transpose(const Matrix& A, Matrix& C);
 void op_upper(const Matrix& A, Matrix& C);
@@ -157,6 +159,20 @@ void op_product_from_host(Matrix& A, const HostTiles& ha, bool tA, Matrix& B, co
                           const ProductOpts& o, int n_slabs, void* host_c_tiles, size_t cap_tiles, int* c_bi, int* c_bj,
                           size_t* n_mults, size_t* n_blocks);
 void op_product_abort();
+void product_row_counts(const Matrix& A, bool tA, const Matrix& B, bool tB, const ProductOpts& o, uint64_t* d_out);
+// ---- sharded.cu: one process per GPU, NCCL resolved at run time ----
+void comm_set_library(const char* path);
+void comm_unique_id(void* out128);
+void comm_init(const void* id128, int rank, int world);
+void comm_finalize();
+void comm_info(int* rank, int* world, int* nccl_version);
+void comm_allreduce_f64(double* vals, int n, bool take_max);
+void comm_allgather_u64(const uint64_t* mine, size_t n, uint64_t* all);
+void comm_barrier();
+void publish(Matrix& B);
+void sharded_product(const Matrix& A, bool tA, Matrix& B, bool tB, Matrix& C, const ProductOpts& o, size_t* n_mults, size_t* n_blocks);
+void sharded_row_weights(const Matrix& A, bool tA, const Matrix& B, bool tB, const ProductOpts& o, int grid_side, uint64_t* host_out);
+hbsm_shard_stats shard_stats_last();
 bool worth_product(const Matrix& A, bool tA, const Matrix& B, bool tB, bool spamm, double tau);
 
 }  // namespace hbsm_b200

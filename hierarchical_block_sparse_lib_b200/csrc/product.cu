@@ -92,6 +92,15 @@ __global__ void k_entry_lines(const uint32_t* __restrict__ ptr, uint32_t n_lines
     for (uint32_t e = ptr[l]; e < ptr[l + 1]; ++e) line_of[e] = l;
 }
 
+__global__ void k_row_counts(const uint32_t* __restrict__ ptr, uint32_t n_lines, const uint64_t* __restrict__ offs, size_t entry_lo,
+                             size_t n_e, uint64_t* __restrict__ out) {
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_lines) return;
+    const size_t a = min(max((size_t)ptr[l], entry_lo), entry_lo + n_e) - entry_lo;
+    const size_t b = min(max((size_t)ptr[l + 1], entry_lo), entry_lo + n_e) - entry_lo;
+    out[l] = offs[b] - offs[a];
+}
+
 __global__ void k_iota(uint32_t* __restrict__ v, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] = (uint32_t)i;
@@ -589,7 +598,7 @@ struct TaskList {
 // a_norms / b_norms: leaf norm^2 arrays to test against instead of the operands' cached ones (spamm(updated=false))
 void build_tasks(const Matrix& A, bool tA, const Matrix& B, bool tB, const ProductOpts& o, int kbits, TaskList& tl,
                  bool count_only, size_t entry_lo = 0, size_t entry_hi = (size_t)-1, const void* a_norms = nullptr,
-                 const void* b_norms = nullptr) {
+                 const void* b_norms = nullptr, uint64_t* d_row_counts = nullptr) {
     const LineIndex& la = line_index(A, tA);   // op(A): lines are C rows
     const LineIndex& lb = line_index(B, tB, true);   // op(B): lines are k; includes the halo tail if one is committed
     tl.n_products = tl.n_ctiles = 0;
@@ -624,6 +633,8 @@ void build_tasks(const Matrix& A, bool tA, const Matrix& B, bool tB, const Produ
     }
     DevBuf<uint64_t> offs(n_e + 1);
     exclusive_scan_u32(counts.p, offs.p, n_e);
+    if (d_row_counts)   // products per line of op(A) (= per C block row): differences of the scan at the line boundaries
+        HB_LAUNCH(k_row_counts, blocks_for(la.n_lines, 256), 256, 0, la.ptr.p, la.n_lines, offs.p, entry_lo, n_e, d_row_counts);
     const auto pc = read_scalars(offs.p + n_e, (const uint64_t*)ncand.p);
     const uint64_t P = pc.first;
     tl.n_candidates = pc.second;
@@ -685,6 +696,18 @@ void check_operands(const Matrix& A, bool tA, const Matrix& B, bool tB, const Ma
 }
 
 }  // namespace
+
+// leaf products per line of op(A) (C block row) that op(A)*op(B) would execute: the count pass of the task-list builder only.
+// B may be a structure-only matrix (keys + norms, no tiles: e.g. a published table).  d_out has op(A)'s grid side entries.
+void product_row_counts(const Matrix& A, bool tA, const Matrix& B, bool tB, const ProductOpts& o, uint64_t* d_out) {
+    ensure_engine();
+    const uint32_t lines = A.grid_side();
+    HB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)lines * sizeof(uint64_t), engine().stream));
+    if (A.empty() || B.empty() || A.L == 0 || B.n_ext() == 0) return;
+    TaskList tl;
+    const int kb = coord_bits(A, B, 1, 1, A.b);
+    build_tasks(A, tA, B, tB, o, kb, tl, true, 0, (size_t)-1, nullptr, nullptr, d_out);
+}
 
 bool worth_product(const Matrix& A, bool tA, const Matrix& B, bool tB, bool spamm, double tau) {
     if (A.empty() || B.empty()) return false;

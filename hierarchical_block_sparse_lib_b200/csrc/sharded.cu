@@ -133,6 +133,9 @@ void dispatch_real(int dtype, F&& f) {
 }
 
 // ---- kernels ----
+template <typename T> struct DT;   // un-fused round-to-nearest products: the predicate's arithmetic (H:2008) exactly
+template <> struct DT<double> { static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); } };
+template <> struct DT<float> { static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); } };
 template <typename T> struct IntOf;
 template <> struct IntOf<double> { typedef long long I; };
 template <> struct IntOf<float> { typedef int I; };
@@ -212,10 +215,6 @@ __global__ void __launch_bounds__(256) k_pack_tiles(const uint4* __restrict__ ti
         const uint32_t o = (uint32_t)(w % words_per_tile);
         pack[w] = __ldg(tiles + (size_t)idx[j] * words_per_tile + o);
     }
-}
-__global__ void k_copy_u64(const uint64_t* __restrict__ in, size_t n, uint64_t* __restrict__ out) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = in[i];
 }
 
 }  // namespace
@@ -473,18 +472,15 @@ void sharded_product(const Matrix& A, bool tA, Matrix& B, bool tB, Matrix& C, co
     }
 
     // 4. the engine product: own-only C tiles first, the halo readers behind the transfer
-    bool ok = false;
     try {
         op_product_begin(A, tA, B, tB, C, o, /*defer_halo_tiles=*/true, /*launch=*/true, /*launch_in_finish=*/false);
         op_product_finish(C, exchange ? c.ev_tiles : nullptr, n_mults, n_blocks);
-        ok = true;
     } catch (...) {
         if (exchange) cudaStreamSynchronize(c.stream);
         op_product_abort();
         commit_halo(B, 0);
         throw;
     }
-    (void)ok;
     commit_halo(B, 0);   // (finish synchronised the engine stream behind the transfer: pack and send_idx may go)
     st.plan_ms = t_plan.ms();
     if (exchange) {
@@ -496,6 +492,37 @@ void sharded_product(const Matrix& A, bool tA, Matrix& B, bool tB, Matrix& C, co
     st.recv_tiles = n_in;
     st.publish_ms = c.last.publish_ms;
     c.last = st;
+}
+
+// leaf products per C block row over all ranks: every rank counts its own rows against the published table of op(B) (a
+// structure-only stand-in for the whole operand), the per-row counts are summed over the ranks (rows are disjoint)
+void sharded_row_weights(const Matrix& A, bool tA, const Matrix& B, bool tB, const ProductOpts& o, int grid_side, uint64_t* host_out) {
+    Comm& c = ready_comm();
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (!B.pub || B.pub->world != c.world) throw Error(HBSM_E_ARG, "hbsm_b200: row weights: op(B) has no published table");
+    if (A.empty() || B.empty() || A.dtype != B.dtype || A.b != B.b) throw Error(HBSM_E_ARG, "hbsm_b200: row weights: bad operands");
+    const Published& pb = *B.pub;
+    const uint32_t g = std::max(A.grid_side(), B.grid_side());
+    if (grid_side != (int)g) throw Error(HBSM_E_ARG, "hbsm_b200: row weights: grid_side must be the block-grid side of the product");
+    Matrix S;   // keys + norms of the WHOLE op(B); no tiles (the count pass never touches them)
+    S.dtype = B.dtype; S.b = B.b; S.M = B.M; S.N = B.N; S.sized = true;
+    S.L = pb.n_all;
+    S.keys.alloc(std::max<size_t>(pb.n_all, 1));
+    S.norms.alloc(std::max<size_t>(pb.n_all, 1) * B.esize());
+    if (pb.n_all) {
+        HB_CUDA(cudaMemcpyAsync(S.keys.p, pb.keys_all.p, pb.n_all * sizeof(uint64_t), cudaMemcpyDeviceToDevice, engine().stream));
+        HB_CUDA(cudaMemcpyAsync(S.norms.p, pb.norms_all.p, pb.n_all * B.esize(), cudaMemcpyDeviceToDevice, engine().stream));
+    }
+    DevBuf<uint64_t> cnt((size_t)g);
+    cnt.zero();
+    {
+        DevBuf<uint64_t> mine((size_t)A.grid_side());
+        product_row_counts(A, tA, S, tB, o, mine.p);
+        HB_CUDA(cudaMemcpyAsync(cnt.p, mine.p, (size_t)A.grid_side() * sizeof(uint64_t), cudaMemcpyDeviceToDevice, engine().stream));
+    }
+    if (c.world > 1) HB_NCCL(c.api.AllReduce(cnt.p, cnt.p, (size_t)g, ncclUint64, ncclSum, c.comm, engine().stream));
+    cnt.download(host_out, (size_t)g);
+    sync_stream();
 }
 
 hbsm_shard_stats shard_stats_last() { return comm().last; }

@@ -167,14 +167,12 @@ def exchange_b(a_keys, a_norms, tA, b_keys, b_norms, b_tiles, tB, grid_side, spa
 
 
 # ---------------------------------------------------------------------------------------------------
-# published block tables: the two-round protocol
+# published block tables + the all-gather protocol (what csrc/sharded.cu runs), as device-agnostic torch ops
 # ---------------------------------------------------------------------------------------------------
 class PublishedTable:
     """The (Morton key, leaf norm^2) table of a row-sharded matrix, gathered once on every rank -- the distributed part
-    of update_internal_info() (H:3905): like the cached norms it is valid until the matrix changes, and must be
-    refreshed by the caller (publish_table) before the matrix is used as op(B) in sharded products.
-    With it a rank decides locally which remote tiles its products touch, so one product needs only
-    (1) an all_to_all of request masks and (2) an all_to_all of the tiles themselves."""
+    of update_internal_info() (H:3905): like the cached norms it is valid until the matrix changes (csrc/sharded.cu
+    publish())."""
 
     def __init__(self, keys_all, norms_all, counts):
         self.keys_all = keys_all                # [sum L_q] int64, rank-major, each rank's part in its local tile order
@@ -183,14 +181,11 @@ class PublishedTable:
         self.offsets = [0]
         for c in self.counts:
             self.offsets.append(self.offsets[-1] + c)
-        self._k = {}
 
     def k_of(self, tB):
         """Contraction index k of every published tile of op(B)."""
-        if tB not in self._k:
-            br, bc = morton_decode(self.keys_all)
-            self._k[tB] = (bc if tB else br).contiguous()
-        return self._k[tB]
+        br, bc = morton_decode(self.keys_all)
+        return (bc if tB else br).contiguous()
 
 
 def publish_table(b_keys, b_norms, group=None):
@@ -211,357 +206,177 @@ def publish_table(b_keys, b_norms, group=None):
     return PublishedTable(keys_all, norms_all, counts)
 
 
-def exchange_b_published(thr, table, b_tiles, tB, spamm, tau, group=None, timers=None, recv_alloc=None, engine=False):
-    """Two-round exchange.  `thr[k]` = this rank's request threshold per contraction index (request_thresholds or the
-    engine's hbsm_halo_request), `table` = PublishedTable of op(B), `b_tiles` = this rank's tiles (local order).
-    Returns (keys, norms, tiles) of the remote tiles this rank's products touch."""
+def exchange_b_allgather(thr, table, b_tiles, tB, spamm, tau, group=None, timers=None):
+    """The protocol of csrc/sharded.cu sharded_product(): all-gather the request thresholds; requester AND owner then
+    evaluate the same predicate  thr_q[k] >= 0 and (not spamm or fl(thr_q[k] * nsq) > fl(tau*tau))  on the same published
+    numbers, so both know the transfer lists without another message; one all-to-all moves the tiles.
+    Returns (keys, norms, tiles) of the remote tiles this rank's products touch (peer-major, owner's tile order)."""
     world = dist.get_world_size(group); rank = dist.get_rank(group)
-    tr = _Trace(timers.setdefault("trace", {}) if timers is not None else None)
-    t0 = time.perf_counter()
+    thr_all = [torch.empty_like(thr) for _ in range(world)]
+    dist.all_gather(thr_all, thr, group=group)
+    thr_all = torch.stack(thr_all)                                   # [world, g]
     k_all = table.k_of(bool(tB))
     lo_r, hi_r = table.offsets[rank], table.offsets[rank + 1]
-    L_r = table.counts[rank]
-    n_all = table.offsets[-1]
-    if engine:     # the engine's kernels: 1 launch for the mask, scan + compaction for the index lists
-        from . import _capi
-        Lc = _capi.lib()
-        dt_code = _capi.HBSM_F64 if table.norms_all.dtype == torch.float64 else _capi.HBSM_F32
-        need_u8 = torch.empty((max(n_all, 1),), dtype=torch.uint8, device=thr.device)
-        _capi.check(Lc.hbsm_halo_mask(dt_code, C.c_void_p(thr.data_ptr()), C.c_void_p(k_all.data_ptr()),
-                                      C.c_void_p(table.norms_all.data_ptr()), n_all, lo_r, hi_r, int(bool(spamm)), float(tau),
-                                      C.c_void_p(need_u8.data_ptr())))
-        need_u8 = need_u8[:n_all]
-    else:
-        t = thr[k_all]
-        need = t >= 0
+    tau2 = torch.tensor(tau, dtype=table.norms_all.dtype)
+    tau2 = tau2 * tau2
+
+    def wanted_by(q, sl):
+        t = thr_all[q][k_all[sl]]
+        keep = t >= 0
         if spamm:
-            tau2 = torch.tensor(tau, dtype=table.norms_all.dtype, device=t.device)
-            tau2 = tau2 * tau2
-            need &= (t * table.norms_all) > tau2          # same fl(max_na*nb) > fl(tau^2) test as the three-round protocol
-        need[lo_r:hi_r] = False                           # own tiles are already here
-        need_u8 = need.to(torch.uint8)
-    t = thr
-    tr.mark("mask")
-    # round 1: every owner learns which of its tiles each requester wants (fixed sizes: L_q bytes to owner q)
-    asked = torch.empty((world * L_r,), dtype=torch.uint8, device=t.device)
-    dist.all_to_all_single(asked, need_u8, [L_r] * world, table.counts, group=group)
-    tr.mark("a2a_mask")
-    if engine:
-        send_idx = torch.empty((max(world * L_r, 1),), dtype=torch.int64, device=t.device)
-        recv_idx = torch.empty((max(n_all, 1),), dtype=torch.int64, device=t.device)
-        e1 = (C.c_size_t * (world + 1))(*[q * L_r for q in range(world + 1)]); c1 = (C.c_size_t * world)()
-        e2 = (C.c_size_t * (world + 1))(*table.offsets); c2 = (C.c_size_t * world)()
-        _capi.check(Lc.hbsm_compact_flags(C.c_void_p(asked.data_ptr()), world * L_r, world + 1, e1, L_r, C.c_void_p(send_idx.data_ptr()), c1))
-        _capi.check(Lc.hbsm_compact_flags(C.c_void_p(need_u8.data_ptr()), n_all, world + 1, e2, 0, C.c_void_p(recv_idx.data_ptr()), c2))
-        send_counts = [int(c) for c in c1]; recv_counts = [int(c) for c in c2]
-        send_idx = send_idx[:sum(send_counts)]; recv_idx = recv_idx[:sum(recv_counts)]
-    else:
-        nz = torch.nonzero(asked.view(world, L_r), as_tuple=False)      # grouped by requester, ascending local tile index
-        send_idx = nz[:, 1].contiguous()
-        recv_idx = torch.nonzero(need, as_tuple=False).flatten()        # ascending = grouped by owner, owner's tile order
-        owner_edges = torch.tensor(table.offsets, dtype=torch.int64, device=t.device)
-        cnt = torch.cat([torch.bincount(nz[:, 0], minlength=world),
-                         torch.bincount(torch.bucketize(recv_idx, owner_edges[1:], right=True), minlength=world)]).tolist()
-        send_counts = [int(c) for c in cnt[:world]]; recv_counts = [int(c) for c in cnt[world:2 * world]]
-    n_in = sum(recv_counts)
-    tr.mark("counts")
-    t1 = time.perf_counter()
-    tiles_out = b_tiles.index_select(0, send_idx)
-    tr.mark("pack")
-    if recv_alloc is not None:
-        keys_in, norms_in, tiles_in = recv_alloc(n_in)
-    else:
-        keys_in = torch.empty((n_in,), dtype=table.keys_all.dtype, device=t.device)
-        norms_in = torch.empty((n_in,), dtype=table.norms_all.dtype, device=t.device)
-        tiles_in = torch.empty((n_in, b_tiles.shape[1]), dtype=b_tiles.dtype, device=t.device)
-    # keys and norms of the incoming tiles are already known locally
-    torch.index_select(table.keys_all, 0, recv_idx, out=keys_in)
-    torch.index_select(table.norms_all, 0, recv_idx, out=norms_in)
-    # round 2: the tiles
+            keep &= (t * table.norms_all[sl]) > tau2
+        return keep
+
+    need = wanted_by(rank, slice(0, table.offsets[-1])).clone()
+    need[lo_r:hi_r] = False                                           # own tiles are already here
+    recv_idx = torch.nonzero(need).flatten()
+    recv_counts = [int(need[table.offsets[q]:table.offsets[q + 1]].sum()) for q in range(world)]
+    send_lists = [torch.nonzero(wanted_by(q, slice(lo_r, hi_r))).flatten() if q != rank else torch.zeros(0, dtype=torch.int64)
+                  for q in range(world)]
+    send_counts = [int(x.numel()) for x in send_lists]
+    tiles_out = b_tiles.index_select(0, torch.cat(send_lists))
+    tiles_in = torch.empty((sum(recv_counts), b_tiles.shape[1]), dtype=b_tiles.dtype)
     dist.all_to_all_single(tiles_in, tiles_out, recv_counts, send_counts, group=group)
-    tr.mark("a2a_tiles")
     if timers is not None:
-        timers["plan_s"] = t1 - t0
         timers["sent_tiles"] = sum(send_counts)
-        timers["recv_tiles"] = n_in
-    return keys_in, norms_in, tiles_in
+        timers["recv_tiles"] = sum(recv_counts)
+    return table.keys_all[recv_idx], table.norms_all[recv_idx], tiles_in
+
+
+def balanced_bounds(row_weights, world):
+    """Slab boundaries on the prefix sums of per-block-row weights (same rule as hbsm_shard_rows_balanced): boundary r is
+    the row at which the running weight is nearest to r/world of the total."""
+    w = np.asarray(row_weights, np.float64)
+    g = len(w)
+    total = float(w.sum())
+    bounds = [0]
+    acc = 0.0
+    row = 0
+    for r in range(1, world):
+        want = total * r / world
+        while row < g and acc + w[row] <= want:
+            acc += w[row]; row += 1
+        if row < g and want - acc > acc + w[row] - want:
+            acc += w[row]; row += 1
+        bounds.append(max(row, bounds[-1]))
+    bounds.append(g)
+    return bounds
 
 
 # ---------------------------------------------------------------------------------------------------
-# engine glue (GPU only)
+# engine glue (GPU only): thin callers of the C ABI (include/hbsm_b200.h "multi-GPU"); NCCL lives inside the library
 # ---------------------------------------------------------------------------------------------------
-class _DevArray:
-    def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+class ShardStats(C.Structure):
+    _fields_ = [("plan_ms", C.c_double), ("exchange_ms", C.c_double), ("publish_ms", C.c_double),
+                ("sent_tiles", C.c_uint64), ("recv_tiles", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-def device_views(Mx):
-    """Zero-copy torch views (keys int64 [L], norms [L], tiles [L, b*b]) of an engine matrix's block table."""
-    from . import _capi
-    n = C.c_size_t(0); pk = C.c_void_p(); pn = C.c_void_p(); pt = C.c_void_p()
-    _capi.check(_capi.lib().hbsm_device_table(Mx._h, C.byref(n), C.byref(pk), C.byref(pn), C.byref(pt)))
-    L = n.value
-    b = Mx.get_params().blocksize
-    ts = "<f8" if Mx.dtype == np.float64 else "<f4"
-    dt = torch.float64 if Mx.dtype == np.float64 else torch.float32
-    dev = torch.device("cuda", torch.cuda.current_device())
-    if L == 0:
-        return (torch.zeros(0, dtype=torch.int64, device=dev), torch.zeros(0, dtype=dt, device=dev),
-                torch.zeros((0, b * b), dtype=dt, device=dev))
-    keys = torch.as_tensor(_DevArray(pk.value, (L,), "<i8"), device=dev)
-    norms = torch.as_tensor(_DevArray(pn.value, (L,), ts), device=dev)
-    tiles = torch.as_tensor(_DevArray(pt.value, (L, b * b), ts), device=dev)
-    return keys, norms, tiles
-
-
-def _tail_views(Mx, cap):
-    """Reserve room for `cap` halo tiles behind Mx's own tiles; zero-copy torch views of the three tail arrays."""
-    from . import _capi
-    pk = C.c_void_p(); pn = C.c_void_p(); pt = C.c_void_p()
-    _capi.check(_capi.lib().hbsm_halo_reserve(Mx._h, cap, C.byref(pk), C.byref(pn), C.byref(pt)))
-    b = Mx.get_params().blocksize
-    ts = "<f8" if Mx.dtype == np.float64 else "<f4"
-    dev = torch.device("cuda", torch.cuda.current_device())
-    return (torch.as_tensor(_DevArray(pk.value, (cap,), "<i8"), device=dev),
-            torch.as_tensor(_DevArray(pn.value, (cap,), ts), device=dev),
-            torch.as_tensor(_DevArray(pt.value, (cap, b * b), ts), device=dev))
-
-
-def _exchange_b_engine(A_loc, tA, B_loc, tB, b_keys, b_norms, b_tiles, grid_side, spamm, tau, group, timers, recv_alloc):
-    """exchange_b with steps 1-2 done by the engine's own kernels (hbsm_halo_request / hbsm_halo_select): two launches
-    instead of ~50 small torch ops.  Must be called with the engine stream current."""
+def comm_init(group=None):
+    """Creates the library's own NCCL communicator over the ranks of `group` (default: the world): rank 0 makes the
+    unique id, torch.distributed only carries its 128 bytes to the peers (any transport would do)."""
     from . import _capi
     L = _capi.lib()
-    world = dist.get_world_size(group); rank = dist.get_rank(group)
-    lo, hi = slab_bounds(grid_side, world, rank)
-    rows = hi - lo
-    t0 = time.perf_counter()
-    tr = _Trace(timers.setdefault("trace", {}) if timers is not None else None)
-    thr = torch.full((grid_side,), -1.0, dtype=b_norms.dtype, device=b_norms.device)   # the engine fills A's grid only
-    _capi.check(L.hbsm_halo_request(A_loc._h, int(bool(tA)), C.c_void_p(thr.data_ptr())))
-    tr.mark("request")
-    thr_in = torch.empty_like(thr)
-    dist.all_to_all_single(thr_in, thr, group=group)
-    tr.mark("a2a_thr")
-    nB = b_keys.numel()
-    send_idx = torch.empty((max(1, world * nB),), dtype=torch.int64, device=b_keys.device)
-    cnt = (C.c_size_t * world)()
-    _capi.check(L.hbsm_halo_select(B_loc._h, int(bool(tB)), C.c_void_p(thr_in.data_ptr()), world, rank, lo, rows,
-                                   int(bool(spamm)), float(tau), C.c_void_p(send_idx.data_ptr()), cnt))
-    counts = [int(c) for c in cnt]
-    send_idx = send_idx[:sum(counts)]
-    tr.mark("select")
-    cnt_out = torch.tensor(counts, dtype=torch.int64, device=b_keys.device)
-    cnt_in = torch.empty_like(cnt_out)
-    dist.all_to_all_single(cnt_in, cnt_out, group=group)
-    recv_counts = [int(x) for x in cnt_in.tolist()]
-    n_in = sum(recv_counts)
-    tr.mark("a2a_counts")
-    t1 = time.perf_counter()
-    keys_out = b_keys.index_select(0, send_idx)
-    norms_out = b_norms.index_select(0, send_idx)
-    tiles_out = b_tiles.index_select(0, send_idx)
-    tr.mark("pack")
-    keys_in, norms_in, tiles_in = recv_alloc(n_in)
-    dist.all_to_all_single(keys_in, keys_out, recv_counts, counts, group=group)
-    dist.all_to_all_single(norms_in, norms_out, recv_counts, counts, group=group)
-    dist.all_to_all_single(tiles_in, tiles_out, recv_counts, counts, group=group)
-    tr.mark("a2a_tiles")
-    if timers is not None:
-        timers["plan_s"] = t1 - t0
-        timers["sent_tiles"] = sum(counts)
-        timers["recv_tiles"] = n_in
-    return keys_in, norms_in, tiles_in
+    rank = dist.get_rank(group); world = dist.get_world_size(group)
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        _capi.check(L.hbsm_comm_unique_id(buf))
+    box = [bytes(buf)]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ident = (C.c_ubyte * 128).from_buffer_copy(box[0])
+    _capi.check(L.hbsm_comm_init(ident, rank, world))
 
 
-def publish(B_loc, group=None):
-    """Distributed half of update_internal_info() for a matrix that will be the right operand of sharded products:
-    gathers its (key, norm) table on every rank.  Call after the norms are refreshed; valid until B_loc changes."""
+def comm_finalize():
     from . import _capi
-    ext = torch.cuda.ExternalStream(int(_capi.lib().hbsm_stream() or 0))
-    with torch.cuda.stream(ext):
-        bk, bn, _ = device_views(B_loc)
-        table = publish_table(bk.clone(), bn.clone(), group)
-        ext.synchronize()
-    B_loc._published = table
-    return table
+    _capi.check(_capi.lib().hbsm_comm_finalize())
 
 
-def _sharded_product_overlapped(A_loc, tA, B_loc, tB, spamm, tau, group, timers, table, upper_only=False):
-    """Published-table protocol with the tile transfer hidden behind the leaf GEMMs that need no remote tile:
+def comm_info():
+    from . import _capi
+    r = C.c_int(0); w = C.c_int(1); v = C.c_int(0)
+    _capi.check(_capi.lib().hbsm_comm_info(C.byref(r), C.byref(w), C.byref(v)))
+    return r.value, w.value, v.value
 
-      engine stream : hbsm_halo_plan (mask, recv counts, halo keys+norms) | line index, task list, split | GEMM(own-only C tiles) | GEMM(rest)
-      comm stream   :                 a2a(request masks) ................... send list, pack, a2a(tiles -> halo tail) -----event----^
-    (the tile transfer is queued before the first GEMM launch and runs beside it)
 
-    The task list needs only keys and norms of the halo tiles, and those are known locally from the published table."""
+def allreduce(vals, take_max=False):
+    """Sum (or max) of a few host scalars over the ranks through the library's communicator."""
+    from . import _capi
+    a = (C.c_double * len(vals))(*[float(v) for v in vals])
+    _capi.check(_capi.lib().hbsm_comm_allreduce_f64(a, len(vals), int(bool(take_max))))
+    return [float(x) for x in a]
+
+
+def shard_stats():
+    from . import _capi
+    st = ShardStats()
+    _capi.check(_capi.lib().hbsm_shard_stats_last(C.byref(st)))
+    return st.as_dict()
+
+
+def publish(B_loc):
+    """Distributed half of update_internal_info() for a matrix that will be the right operand of sharded products
+    (hbsm_publish): call after the norms are refreshed; valid until B_loc changes.  Collective."""
+    from . import _capi
+    _capi.check(_capi.lib().hbsm_publish(B_loc._h))
+
+
+def row_weights(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, upper_only=False):
+    """Leaf products per C block row of op(A)*op(B) over ALL ranks (count-only join of each rank's rows against the
+    published table of op(B), summed over the ranks): the weights hbsm_shard_rows_balanced wants.  Collective."""
+    from . import _capi
+    g = 1 << max(A_loc.expected_depth(), B_loc.expected_depth())
+    w = np.zeros(g, np.uint64)
+    _capi.check(_capi.lib().hbsm_sharded_row_weights(A_loc._h, int(bool(tA)), B_loc._h, int(bool(tB)), int(bool(spamm)), float(tau),
+                                                      int(bool(upper_only)), g, w.ctypes.data_as(C.c_void_p)))
+    return w
+
+
+def sharded_product(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, upper_only=False):
+    """C_r = op(A)_r * op(B): A_loc / B_loc are this rank's engine matrices (full logical dims, only the slab's tiles; norms
+    refreshed, publish(B_loc) called).  Returns (C_loc, n_mults_local, n_blocks_local).  Collective (hbsm_sharded_product)."""
     from . import _capi
     from .matrix import HierarchicalBlockSparseMatrix as H
-    Lc = _capi.lib()
-    world = dist.get_world_size(group); rank = dist.get_rank(group)
-    grid_side = 1 << max(A_loc.expected_depth(), B_loc.expected_depth())
-    ext = torch.cuda.ExternalStream(int(Lc.hbsm_stream() or 0))
-    comm = getattr(sharded_product, "_comm_stream", None)
-    if comm is None:
-        comm = torch.cuda.Stream()
-        sharded_product._comm_stream = comm
-    tr = _Trace(timers.setdefault("trace", {}) if timers is not None else None)
-    t0 = time.perf_counter()
-    k_all = table.k_of(bool(tB))
-    L_r = table.counts[rank]; n_all = table.offsets[-1]
-    b = B_loc.get_params().blocksize
-    ts = "<f8" if B_loc.dtype == np.float64 else "<f4"
-    dev = table.norms_all.device
-    if B_loc.get_n_blocks() != L_r:
-        raise RuntimeError("sharded_product: the published table of B is stale (B changed after publish())")
-    scratch = getattr(table, "_scratch", None)     # request mask out / in: buffers, not results -- reused across products
-    if scratch is None:
-        with torch.cuda.stream(ext):
-            scratch = (torch.empty((max(n_all, 1),), dtype=torch.uint8, device=dev),
-                       torch.empty((max(world * L_r, 1),), dtype=torch.uint8, device=dev),
-                       (C.c_size_t * (world + 1))(*table.offsets))
-        table._scratch = scratch
-    need_u8, asked, offs_c = scratch
-    rc = (C.c_size_t * world)(); n_in_c = C.c_size_t(0); tail = C.c_void_p()
-    # one engine call: thresholds, mask, receive counts, halo keys + norms from the table, commit (8 launches, 1 sync)
-    _capi.check(Lc.hbsm_halo_plan(A_loc._h, int(bool(tA)), B_loc._h, C.c_void_p(table.keys_all.data_ptr()), C.c_void_p(k_all.data_ptr()),
-                                  C.c_void_p(table.norms_all.data_ptr()), n_all, world, rank, offs_c, int(bool(spamm)), float(tau),
-                                  C.c_void_p(need_u8.data_ptr()), rc, C.byref(n_in_c), C.byref(tail)))
-    recv_counts = [int(c) for c in rc]
-    n_in = n_in_c.value
-    tr.mark("halo_plan")
-    # The exchange (both all-to-alls, the send list, the pack) runs on a helper THREAD with its own stream while this thread
-    # builds the task list through the C ABI (ctypes drops the GIL): the two host-side chains, each with its own syncs,
-    # overlap instead of adding up.  All collectives of a product are issued by that one thread, in the same order on
-    # every rank.  HBSM_SHARD_COMM_THREAD=0 runs the same steps inline.
-    if n_in:
-        tiles_in = torch.as_tensor(_DevArray(tail.value, (n_in, b * b), ts), device=dev)
-    else:
-        tiles_in = torch.empty((0, b * b), dtype=table.norms_all.dtype, device=dev)
-    _, _, bt = device_views(B_loc)
-    dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
-
-    def exchange():
-        torch.cuda.set_device(dev_index)            # the current device is per thread
-        with torch.cuda.stream(comm):
-            # (hbsm_halo_plan returned with the engine stream idle, so the mask is complete: no event needed)
-            dist.all_to_all_single(asked[:world * L_r], need_u8[:n_all], [L_r] * world, table.counts, group=group)
-            nz = torch.nonzero(asked[:world * L_r].view(world, L_r), as_tuple=False)       # syncs the comm stream only
-            counts = np.bincount(nz[:, 0].cpu().numpy(), minlength=world).tolist()
-            tiles_out = bt.index_select(0, nz[:, 1].contiguous())
-            dist.all_to_all_single(tiles_in, tiles_out, recv_counts, counts, group=group)
-            ev = torch.cuda.Event(); ev.record(comm)
-        return counts, ev, tiles_out
-
-    use_thread = os.environ.get("HBSM_SHARD_COMM_THREAD", "1") == "1"
-    fut = None
-    if use_thread:
-        pool = getattr(sharded_product, "_comm_pool", None)
-        if pool is None:
-            from concurrent.futures import ThreadPoolExecutor
-            pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="hbsm-comm")
-            sharded_product._comm_pool = pool
-        fut = pool.submit(exchange)
-    tr.mark("exchange_submit")
     Cm = H(A_loc.dtype)
-    ok = False
-    send_counts = []
-    try:
-        # plan only (mode 2): the all-to-all of the tiles is queued BEFORE the first leaf GEMM, whose persistent CTAs would
-        # otherwise hold every SM until they drain (HBSM_SHARD_GEMM_FIRST=1 restores the old order for comparison)
-        mode = 1 if os.environ.get("HBSM_SHARD_GEMM_FIRST", "0") == "1" else 2
-        _capi.check(Lc.hbsm_product_begin_ex(A_loc._h, int(bool(tA)), B_loc._h, int(bool(tB)), Cm._h, int(bool(spamm)), float(tau), 1, mode,
-                                             int(bool(upper_only))))
-        t1 = time.perf_counter()
-        tr.mark("product_begin")
-        send_counts, ev_tiles, _keep = fut.result() if fut is not None else exchange()
-        fut = None
-        tr.mark("exchange_joined")
-        nm = C.c_size_t(0); nb = C.c_size_t(0)
-        _capi.check(Lc.hbsm_product_finish(Cm._h, C.c_void_p(ev_tiles.cuda_event), C.byref(nm), C.byref(nb)))
-        tr.mark("product_finish")
-        ok = True
-    finally:
-        if not ok:
-            if fut is not None:
-                try:
-                    fut.result()
-                except Exception:
-                    pass
-            torch.cuda.synchronize()
-            Lc.hbsm_product_abort()      # a begin without its finish must not block every later product
-        _capi.check(Lc.hbsm_halo_commit(B_loc._h, 0))
-    tr.mark("halo_drop")
-    if timers is not None:
-        timers["plan_s"] = t1 - t0
-        timers["sent_tiles"] = sum(send_counts)
-        timers["recv_tiles"] = n_in
+    nm = C.c_size_t(0); nb = C.c_size_t(0)
+    _capi.check(_capi.lib().hbsm_sharded_product(A_loc._h, int(bool(tA)), B_loc._h, int(bool(tB)), Cm._h, int(bool(spamm)), float(tau),
+                                                  int(bool(upper_only)), C.byref(nm), C.byref(nb)))
     return Cm, nm.value, nb.value
 
 
-def sharded_symm_square_spamm(F_loc, tau, group=None, timers=None):
-    """BASELINE config 3 across GPUs: this rank's block rows of triu(spamm(F, F, tau)) for a symmetric F held in FULL storage and
-    sharded by block rows like any other operand (F_loc: norms refreshed, publish(F_loc) called).  tau = None: exact symmetric
-    square.  Only C tiles with ci <= cj are planned, the diagonal tiles are masked: on one GPU this is symm_square_spamm of F's
-    upper triangle (H:3563 with the prune of H:3931).  A banded F keeps contiguous row slabs balanced (every block row owns about
-    half a band of C tiles); for a dense-ish F pair the slabs (i, G-1-i) instead."""
-    return sharded_product(F_loc, False, F_loc, False, tau is not None, 0.0 if tau is None else tau, group, timers, upper_only=True)
+def sharded_symm_square_spamm(F_loc, tau):
+    """BASELINE config 3 across GPUs: this rank's block rows of triu(spamm(F, F, tau)) for a symmetric F held in FULL storage
+    and sharded by block rows like any other operand (norms refreshed, publish(F_loc) called).  tau = None: exact symmetric
+    square.  Only C tiles with ci <= cj are planned, the diagonal tiles are masked: on one GPU this is symm_square_spamm of
+    F's upper triangle (H:3563 with the prune of H:3931).  The triangular load is balanced by the slab boundaries
+    (row_weights(..., upper_only=True) + balanced_bounds), not by pairing slabs."""
+    return sharded_product(F_loc, False, F_loc, False, tau is not None, 0.0 if tau is None else tau, upper_only=True)
 
 
-def sharded_product(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, group=None, timers=None, upper_only=False):
-    """C_r = op(A)_r * op(B): A_loc / B_loc are this rank's engine matrices (full logical dims, only the slab's tiles;
-    norms refreshed).  Remote op(B) tiles are received straight into B_loc's halo tail (hbsm_halo_reserve/commit), the
-    rank's own tiles are never copied.  If publish(B_loc) was called the two-round protocol is used, else the
-    self-contained three-round one.  Returns (C_loc, n_mults_local, n_blocks_local)."""
-    from . import _capi
-    from .matrix import HierarchicalBlockSparseMatrix as H
-    table = getattr(B_loc, "_published", None)
-    if (table is not None and os.environ.get("HBSM_SHARD_OVERLAP", "1") == "1"
-            and os.environ.get("HBSM_SHARD_TORCH_PLAN", "0") != "1"):
-        return _sharded_product_overlapped(A_loc, tA, B_loc, tB, spamm, tau, group, timers, table, upper_only)
-    if upper_only:
-        raise NotImplementedError("upper_only products need the published-table protocol: call publish(B_loc) first")
-    grid_side = 1 << max(A_loc.expected_depth(), B_loc.expected_depth())
-    ext = torch.cuda.ExternalStream(int(_capi.lib().hbsm_stream() or 0))
-    with torch.cuda.stream(ext):
-        ak, an, _ = device_views(A_loc)
-        bk, bn, bt = device_views(B_loc)
-
-        def recv_alloc(n):
-            if n == 0:
-                return bk[:0], bn[:0], bt[:0]
-            cap = getattr(B_loc, "_halo_cap", 0)
-            if n > cap:                                   # grow geometrically; steady state: no reallocation
-                cap = max(n + n // 4, 64)
-                B_loc._halo_cap = cap
-            k, nr, t = _tail_views(B_loc, cap)            # (re)reads the pointers: a growth moves the arrays
-            return k[:n], nr[:n], t[:n]
-
-        table = getattr(B_loc, "_published", None)
-        if table is not None and table.counts[dist.get_rank(group)] != bk.numel():
-            raise RuntimeError("sharded_product: the published table of B is stale (B changed after publish())")
-        if table is not None and os.environ.get("HBSM_SHARD_TORCH_PLAN", "0") != "1":
-            thr = torch.full((grid_side,), -1.0, dtype=bn.dtype, device=bn.device)   # the engine fills A's grid only
-            _capi.check(_capi.lib().hbsm_halo_request(A_loc._h, int(bool(tA)), C.c_void_p(thr.data_ptr())))
-            keys, norms, tiles = exchange_b_published(thr, table, bt, tB, spamm, tau, group, timers, recv_alloc, engine=True)
-        elif os.environ.get("HBSM_SHARD_TORCH_PLAN", "0") == "1":     # same plan with torch ops (what the gloo tests run)
-            keys, norms, tiles = exchange_b(ak, an, tA, bk, bn, bt, tB, grid_side, spamm, tau, group, timers, recv_alloc)
-        else:
-            keys, norms, tiles = _exchange_b_engine(A_loc, tA, B_loc, tB, bk, bn, bt, grid_side, spamm, tau, group, timers,
-                                                    recv_alloc)
-        ext.synchronize()
-    tr = _Trace(timers.setdefault("trace", {}) if timers is not None else None)
-    _capi.check(_capi.lib().hbsm_halo_commit(B_loc._h, keys.numel()))
-    Cm = H(A_loc.dtype)
+def bind_near_gpu(local_rank):
+    """Pin this rank's host threads to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function) BEFORE pinned
+    host buffers are allocated: first touch then places them on the GPU's NUMA node, and 8 ranks stop sharing one socket's
+    memory controllers for their PCIe traffic.  Returns the cpulist used or None."""
     try:
-        if spamm:
-            nm, nb = H.spamm(A_loc, tA, B_loc, tB, Cm, tau, True)
-        else:
-            nm, nb = H.multiply(A_loc, tA, B_loc, tB, Cm)
-    finally:
-        _capi.check(_capi.lib().hbsm_halo_commit(B_loc._h, 0))
-    tr.mark("engine_product")
-    return Cm, nm, nb
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        txt = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use:
+            os.sched_setaffinity(0, use)
+            return txt
+    except Exception:
+        pass
+    return None
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -570,105 +385,126 @@ def sharded_product(A_loc, tA, B_loc, tB, spamm=False, tau=0.0, group=None, time
 def bench_main(args, w, bm):
     """bm = the bench.py module (config text, peaks, clock sampler, parity check)."""
     import json
-    workload_config = lambda world_: bm.case_config(w, world_, args.config)
-    fp64_peak = bm.fp64_peak
-    ClockSampler = bm.ClockSampler
-    if w["op"] != "spamm" or w["dtype"] != "f64" or w["tA"] or w["tB"]:
-        raise SystemExit("bench.py --gpus N>1 runs the fp64 SpAMM NN cases (headline, --config 2, --config 4)")
     import hierarchical_block_sparse_lib_b200 as hb
     from . import _capi
     from . import generators as G
     H = hb.HierarchicalBlockSparseMatrix
+    if w["op"] != "spamm" or w["dtype"] != "f64" or w["tA"] or w["tB"]:
+        raise SystemExit("bench.py --gpus N>1 runs the fp64 SpAMM NN cases (headline, --config 2, --config 4)")
     world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"]); local_rank = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local_rank)
+    cpulist = bind_near_gpu(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hb.init(local_rank)
+    comm_init()
     n, b, lam, tau = w["n"], w["b"], w["lam"], w["tau"]
     W = G.decay_width(lam, 1e-12)
     g = n // b
-    lo, hi = slab_bounds(g, world, rank)
-    A = H(np.float64, b); A.generate_decay(n, lam, W, 1, False, lo, hi); A.update_internal_info()
-    B = H(np.float64, b); B.generate_decay(n, lam, W, 2, False, lo, hi); B.update_internal_info()
-    if os.environ.get("HBSM_SHARD_NO_PUBLISH", "0") != "1":
-        publish(B)     # distributed half of update_internal_info(): outside the timed region like the norm refresh itself
     ext = torch.cuda.ExternalStream(int(_capi.lib().hbsm_stream()))
-    timers = {}
+
+    def build(lo, hi):
+        A = H(np.float64, b); A.generate_decay(n, lam, W, 1, False, lo, hi); A.update_internal_info()
+        B = H(np.float64, b); B.generate_decay(n, lam, W, 2, False, lo, hi); B.update_internal_info()
+        publish(B)     # the distributed half of update_internal_info(): outside the timed region like the norm refresh itself
+        return A, B
+
+    # slabs: equal block rows first; then boundaries on the prefix sums of the per-row product counts (the band is clipped at
+    # the matrix edges, so equal slabs leave the edge ranks lighter), and the operands are re-made on the balanced slabs
+    lo, hi = slab_bounds(g, world, rank)
+    A, B = build(lo, hi)
+    bounds = [int(g * r // world) for r in range(world + 1)]
+    if os.environ.get("HBSM_SHARD_BALANCE", "1") == "1":
+        wts = row_weights(A, False, B, False, True, tau)
+        bounds = balanced_bounds(wts, world)
+        if (bounds[rank], bounds[rank + 1]) != (lo, hi):
+            del A, B
+            lo, hi = bounds[rank], bounds[rank + 1]
+            A, B = build(lo, hi)
+    publish_ms = shard_stats()["publish_ms"]
 
     def step():
-        Cm, nm, nb = sharded_product(A, False, B, False, True, tau, None, timers)
-        return Cm, nm, nb, hb.stage_times()
+        Cm, nm, nb = sharded_product(A, False, B, False, True, tau)
+        return Cm, nm, nb, hb.stage_times(), shard_stats()
 
     for _ in range(args.warmup):
-        Cm, nm, nb, st = step()
+        Cm, nm, nb, st, ss = step()
         del Cm
-    sampler = ClockSampler(local_rank)
+    sampler = bm.ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     l0 = hb.kernel_launch_count()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
-    gemm_ms, task_ms, plan_ms = [], [], []
-    timers["trace"] = {}
+    gemm_ms, task_ms, plan_ms, xchg_ms, host_ms = [], [], [], [], []
     ev0.record(ext)
     for _ in range(args.steps):
-        Cm, nm, nb, st = step()
-        gemm_ms.append(st["gemm_ms"]); task_ms.append(st["tasklist_ms"]); plan_ms.append(1e3 * timers["plan_s"])
+        t0 = time.perf_counter()
+        Cm, nm, nb, st, ss = step()
+        host_ms.append(1e3 * (time.perf_counter() - t0))
+        gemm_ms.append(st["gemm_ms"]); task_ms.append(st["tasklist_ms"]); plan_ms.append(ss["plan_ms"]); xchg_ms.append(ss["exchange_ms"])
         del Cm
     ev1.record(ext)
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     launches = hb.kernel_launch_count() - l0
-    trace = {k: round(1e3 * v / args.steps, 4) for k, v in timers.get("trace", {}).items()} or None   # ms per step
-    if trace is not None:     # every rank's phases (+ its engine stage times) on rank 0's line
-        mine = dict(trace, rank=rank, gemm_ms=float(np.mean(gemm_ms)), tasklist_ms=float(np.mean(task_ms)), index_ms=float(st["index_ms"]),
-                    engine_total_ms=float(st["total_ms"]))
-        allr = [None] * world
-        dist.all_gather_object(allr, mine)
-        trace = allr
     clocks = sampler.stop() if rank == 0 else None
     ms_local = ev0.elapsed_time(ev1) / args.steps
-    stats = torch.tensor([ms_local, float(np.mean(gemm_ms))], dtype=torch.float64, device="cuda")
-    dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    sums = torch.tensor([float(nm), float(nb), float(st["n_candidates"]), float(launches), float(timers["recv_tiles"])],
-                        dtype=torch.float64, device="cuda")
-    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms = float(stats[0]); g_ms_max = float(stats[1])
-    P = int(sums[0])
+    mine = {"rank": rank, "rows": [lo, hi], "step_ms": ms_local, "host_ms": float(np.mean(host_ms)), "plan_ms": float(np.mean(plan_ms)),
+            "exchange_ms": float(np.mean(xchg_ms)), "tasklist_ms": float(np.mean(task_ms)), "gemm_ms": float(np.mean(gemm_ms)),
+            "index_ms": float(st["index_ms"]), "products": int(nm), "c_tiles": int(nb), "recv_tiles": int(ss["recv_tiles"]),
+            "sent_tiles": int(ss["sent_tiles"]), "launches_per_step": launches / args.steps}
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, mine)
+    ms = max(r["step_ms"] for r in per_rank)
+    P = sum(r["products"] for r in per_rank)
     flops = 2.0 * b ** 3 * P
 
     check = None
     if not args.no_check:
         try:
-            Cm, nm_c, nb_c = sharded_product(A, False, B, False, True, tau, None, None)
+            Cm, nm_c, nb_c = sharded_product(A, False, B, False, True, tau)
             check = bm.run_check(w, [A, B], Cm, nm_c, max(2, -(-args.check_samples // world)), dist, torch)
             del Cm
         except Exception as ex:  # noqa: BLE001
             check = {"pass": None, "error": repr(ex)}
+            objs = [None] * world
+            dist.all_gather_object(objs, check)
 
-    e2e = None if args.no_e2e else _e2e_sharded(hb, H, A, B, w, max(1, min(args.steps, 3)), lo, hi)
+    e2e = None if args.no_e2e else _e2e_sharded(hb, H, A, B, w, max(1, min(args.steps, 3)), local_rank)
 
     if rank == 0:
-        peak, peak_src = fp64_peak()
+        peak, peak_src = bm.fp64_peak()
         g_ms = float(np.mean(gemm_ms))
+        g_max = max(r["gemm_ms"] for r in per_rank); g_mean = float(np.mean([r["gemm_ms"] for r in per_rank]))
         achieved = 2.0 * b ** 3 * nm / (g_ms * 1e-3) / 1e12
+        slow = max(per_rank, key=lambda r: r["step_ms"])
+        resid = {"imbalance_ms": g_max - g_mean, "plan_ms": slow["plan_ms"], "tasklist_ms": slow["tasklist_ms"],
+                 "other_ms": ms - slow["gemm_ms"] - slow["plan_ms"] - slow["tasklist_ms"]}
+        cfg = bm.case_config(w, world, args.config)
+        cfg["slabs"] = {"bounds": bounds, "rule": "prefix sums of per-block-row leaf-product counts (hbsm_sharded_row_weights + "
+                                                  "hbsm_shard_rows_balanced)" if os.environ.get("HBSM_SHARD_BALANCE", "1") == "1" else "equal block rows"}
         line = {"metric": "spamm_fp64_leaf_tflops", "value": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
-                "products_per_multiply": P, "c_tiles": int(sums[1]), "candidates": int(sums[2]),
-                "stage_ms": {"exchange_plan_rank0": float(np.mean(plan_ms)), "tasklist_rank0": float(np.mean(task_ms)),
-                             "gemm_rank0": g_ms, "gemm_max_over_ranks": g_ms_max},
-                "halo_tiles_received_total": int(sums[4]), "trace_rank0_ms": trace,
-                "roofline": {"bound": "tensor", "kernel": "k_gemm_f64_tma<64,64> (FP64 DMMA leaf GEMM), rank 0's launch",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                "products_per_multiply": P, "c_tiles": sum(r["c_tiles"] for r in per_rank),
+                "stage_ms": {"plan_slowest_rank": slow["plan_ms"], "tasklist_slowest_rank": slow["tasklist_ms"], "gemm_slowest_rank": slow["gemm_ms"],
+                             "gemm_max_over_ranks": g_max, "gemm_mean_over_ranks": g_mean, "exchange_max_over_ranks": max(r["exchange_ms"] for r in per_rank),
+                             "publish_ms_outside_timed_region": publish_ms},
+                "residual_over_mean_gemm": dict(resid, largest=max(resid, key=resid.get)),
+                "halo_tiles_received_total": sum(r["recv_tiles"] for r in per_rank), "per_rank": per_rank,
+                "roofline": {"bound": "tensor", "kernel": "k_gemm_f64_tma<%d> (FP64 DMMA leaf GEMM), rank 0's launches" % b,
                              "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peak_src,
-                             "algorithmic": "2*b^3 flops per leaf product x %d products in rank 0's launch" % nm,
+                             "algorithmic": "2*b^3 flops per leaf product x %d products in rank 0's launches" % nm,
                              "kernel_ms": g_ms, "share_of_step": g_ms / ms, "traffic": None},
-                "check": check, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(sums[3]), "clocks": clocks}
+                "check": check, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(sum(r["launches_per_step"] for r in per_rank) * args.steps),
+                "host_cpulist_rank0": cpulist, "clocks": clocks}
         print(json.dumps(line), flush=True)
+    comm_finalize()
     dist.destroy_process_group()
 
 
-def _e2e_sharded(hb, H, A, B, w, steps, lo, hi):
-    """Per rank: pinned host tiles of its slabs -> device, norm refresh, halo exchange, SpAMM, all local C tiles back to
-    pinned host memory.  Max over ranks of the wall time between two barriers."""
+def _e2e_sharded(hb, H, A, B, w, steps, local_rank):
+    """Per rank: pinned host tiles of its slabs -> device, norm refresh, publish, halo exchange, SpAMM, all local C tiles back
+    to pinned host memory.  Max over ranks of the wall time between two barriers."""
     from . import _capi
     b, n, tau = w["b"], w["n"], w["tau"]
 
@@ -685,13 +521,13 @@ def _e2e_sharded(hb, H, A, B, w, steps, lo, hi):
     times = []
     nm_tot = 0
     d2h = 0
+    phases = None
     for i in range(steps + 2):      # two untimed passes: the stream-ordered memory pool reaches its steady state
         torch.cuda.synchronize(); dist.barrier()
         t0 = time.perf_counter()
         A2 = H(np.float64, b); A2.resize(n, n); A2.assign_tiles(abi, abj, at.numpy()); A2.update_internal_info()
         B2 = H(np.float64, b); B2.resize(n, n); B2.assign_tiles(bbi, bbj, bt.numpy()); B2.update_internal_info()
-        if os.environ.get("HBSM_SHARD_NO_PUBLISH", "0") != "1":
-            publish(B2)                      # inside the e2e region: B2 is a new matrix every step
+        publish(B2)                      # inside the e2e region: B2 is a new matrix every step
         t_up = time.perf_counter() - t0
         Cm, nm, nr = sharded_product(A2, False, B2, False, True, tau)
         t_prod = time.perf_counter() - t0 - t_up
@@ -709,10 +545,10 @@ def _e2e_sharded(hb, H, A, B, w, steps, lo, hi):
         sm = v.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         if i > 1:
             times.append(float(mx[0]))
-            phases = {"upload_assign_norms_ms": 1e3 * t_up, "product_ms": 1e3 * t_prod, "download_ms": 1e3 * (dt - t_up - t_prod)}
+            phases = {"upload_assign_norms_publish_ms": 1e3 * t_up, "product_ms": 1e3 * t_prod, "download_ms": 1e3 * (dt - t_up - t_prod)}
         nm_tot = int(sm[1]); h2d_tot = int(sm[2]); d2h = int(sm[3])
     ms = 1e3 * float(np.mean(times))
     return {"value": 2.0 * b ** 3 * nm_tot / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ms,
             "h2d_bytes_per_step": h2d_tot, "d2h_bytes_per_step": d2h, "rank0_phases": phases,
-            "path": "per rank: hbsm_assign_tiles(A_r,B_r from pinned host) + hbsm_update_norms + halo exchange (NCCL) + "
-                    "hbsm_spamm + hbsm_export_leaves(C_r to pinned host); max over ranks"}
+            "path": "per rank: hbsm_assign_tiles(A_r,B_r from pinned host) + hbsm_update_norms + hbsm_publish + hbsm_sharded_product "
+                    "(NCCL halo exchange inside the library) + hbsm_export_leaves(C_r to pinned host); max over ranks"}

@@ -198,32 +198,9 @@ int hbsm_assign_device_tiles(hbsm_handle h, size_t n_tiles, const uint64_t* d_mo
  * ones and return device pointers to the tail of its key / leaf-norm / tile arrays, so that tiles owned by peer ranks
  * can be received in place (NCCL writes straight into the tail).  hbsm_halo_commit(h, n) makes the first n tail tiles
  * part of the NEXT products in which h is the right operand (they never enter h's own block table: readback, add,
- * norms of h are unaffected); n = 0 drops them.  Any modification of h drops the halo. */
-/* Halo planning kernels (run on the engine stream; device pointers belong to the caller):
- *  request: d_thr[k] (Treal, grid_side entries) = max cached leaf norm^2 over A's tiles with contraction index k
- *           (k = column of A, or row if tA), -1 where A has no such tile;
- *  select : d_thr_in[q*rows + (k-lo)] is peer q's request for my k in [lo, lo+rows).  Writes to d_send_idx (room for
- *           world * n_blocks(B) entries) the indices of B's tiles to ship, grouped by peer q != rank, ascending inside a
- *           group, keeping tile i for q iff request >= 0 and (exact multiply or fl(request * nsq(B_i)) > fl(tau*tau));
- *           counts[q] (host, `world` entries) = group sizes. */
-int hbsm_halo_request(hbsm_handle A, int tA, void* d_thr);
-int hbsm_halo_select(hbsm_handle B, int tB, const void* d_thr_in, int world, int rank, int lo, int rows, int spamm, double tau,
-                     int64_t* d_send_idx, size_t* counts);
-/* Published-table protocol (sharded.py, PublishedTable): d_need[t] = 1 iff published tile t -- contraction index
- * d_k_all[t], leaf norm^2 d_norms_all[t] -- lies outside [own_lo, own_hi) and d_thr[d_k_all[t]] >= 0 and (exact multiply
- * or fl(d_thr[..] * norm) > fl(tau*tau)).  hbsm_compact_flags: indices (mod `modulo` if non-zero) of the non-zero flags,
- * ascending, into d_idx; counts[q] = number of flags set in [edges[q], edges[q+1]) for the n_edges-1 intervals. */
-int hbsm_halo_mask(int dtype, const void* d_thr, const int64_t* d_k_all, const void* d_norms_all, size_t n_all, size_t own_lo,
-                   size_t own_hi, int spamm, double tau, uint8_t* d_need);
-int hbsm_compact_flags(const uint8_t* d_flags, size_t n, size_t n_edges, const size_t* edges, size_t modulo, int64_t* d_idx,
-                       size_t* counts);
-/* The rank-local half of the published-table protocol in ONE call (8 launches, one host sync): request thresholds of
- * op(A); d_need[t] as hbsm_halo_mask (the mask to send to the owners; offsets[q]..offsets[q+1] = rank q's tiles in the
- * table, world + 1 entries); recv_counts[q] = tiles to expect from peer q; B's halo tail is reserved, filled with the keys
- * and norms of those n_in tiles (table order = peer-major) and committed; *d_tail_tiles = where NCCL must deliver them. */
-int hbsm_halo_plan(hbsm_handle A, int tA, hbsm_handle B, const uint64_t* d_keys_all, const int64_t* d_k_all,
-                   const void* d_norms_all, size_t n_all, int world, int rank, const size_t* offsets, int spamm, double tau,
-                   uint8_t* d_need, size_t* recv_counts, size_t* n_in, void** d_tail_tiles);
+ * norms of h are unaffected); n = 0 drops them.  Any modification of h drops the halo.
+ * (The library's own multi-GPU product, hbsm_sharded_product below, uses exactly this; the entry points stay public for
+ * callers that bring their own transport.) */
 int hbsm_halo_reserve(hbsm_handle h, size_t capacity, uint64_t** d_keys, void** d_norms, void** d_tiles);
 int hbsm_halo_commit(hbsm_handle h, size_t n_halo);
 /* banded decay generator a_ij = (0.5+0.5u(seed,i,j)) * table[|i-j|], |i-j| <= W (table has W+1 entries, e.g.
@@ -234,6 +211,50 @@ int hbsm_generate_decay(hbsm_handle h, int n, const double* table, int W, uint64
 uint64_t hbsm_morton_encode(uint32_t bi, uint32_t bj);
 void hbsm_morton_decode(uint64_t key, uint32_t* bi, uint32_t* bj);
 void* hbsm_stream(void);                  /* cudaStream_t of the engine */
+
+/* ---- multi-GPU: one process per GPU, C sharded by block rows --------------------------------------------
+ * The reference has no distributed layer; its static multiply/spamm (H:255-305) see one address space.  Here rank r holds, of
+ * every operand, the tiles whose block ROW (C row for op(A), contraction index k for op(B), after the transposition flags)
+ * lies in its slab, in matrices that carry the full logical dimensions, and gets the same slab of C.  NCCL is loaded at run
+ * time (libnccl.so.2; hbsm_comm_set_library or $HBSM_NCCL_LIB override the search), so single-GPU hosts need none.
+ * Every call below except set_library / unique_id / info is COLLECTIVE: all ranks call it, in the same order. */
+#define HBSM_COMM_ID_BYTES 128
+int hbsm_comm_set_library(const char* path);
+/* rank 0 creates the id and hands its 128 bytes to the other ranks by any means (MPI, a file, torch's store ...) */
+int hbsm_comm_unique_id(void* id_out);
+int hbsm_comm_init(const void* id, int rank, int world);    /* after hbsm_init(device); world <= 64 */
+int hbsm_comm_finalize(void);
+int hbsm_comm_info(int* rank, int* world, int* nccl_version);
+int hbsm_comm_barrier(void);
+int hbsm_comm_allreduce_f64(double* vals, int n, int take_max);         /* host scalars: sum (or max) over the ranks */
+int hbsm_comm_allgather_u64(const uint64_t* mine, size_t n, uint64_t* all);   /* all has n * world entries */
+/* equal slabs of block rows: rank r owns [lo, hi); for world in {2,4,8} these are the top-level quadtree block rows */
+int hbsm_shard_rows(int grid_side, int world, int rank, int* lo, int* hi);
+/* balanced slabs: bounds[world + 1] chosen on the prefix sums of per-block-row weights (e.g. leaf products per C block row) so
+ * that every slab carries about the same weight (the band of a decay matrix is clipped at the matrix edge: equal slabs leave
+ * the edge ranks ~7 % lighter) */
+int hbsm_shard_rows_balanced(const uint64_t* row_weights, int grid_side, int world, int* bounds);
+/* the distributed half of update_internal_info() (H:3905): all-gathers this matrix' (Morton key, leaf norm^2) table.  Call it
+ * after the norms are refreshed on a matrix that will be the RIGHT operand of sharded products; valid until h changes. */
+int hbsm_publish(hbsm_handle h);
+/* C_r = this rank's block rows of op(A)*op(B).  A, B: this rank's slabs with refreshed norms, B published.  Remote op(B)
+ * tiles that at least one executed product of this rank touches are received straight behind B's own tiles (NCCL send/recv
+ * over NVLink) while the leaf GEMMs of the C tiles that need none of them already run; there is no reduction.  upper_only:
+ * plan only C tiles with ci <= cj and mask the diagonal tiles (sharded symm_square / symm_rk on a full-storage symmetric
+ * operand, H:3563 / H:3711).  n_block_multiplies / n_resizes are this rank's (sum them with hbsm_comm_allreduce_f64). */
+int hbsm_sharded_product(hbsm_handle A, int tA, hbsm_handle B, int tB, hbsm_handle C, int spamm, double tau, int upper_only,
+                         size_t* n_block_multiplies, size_t* n_resizes);
+/* leaf products per C block row of op(A)*op(B) summed over the ranks (count pass only; B published): weights[grid_side], the
+ * input of hbsm_shard_rows_balanced.  grid_side = block-grid side of the product (max of the operands'). */
+int hbsm_sharded_row_weights(hbsm_handle A, int tA, hbsm_handle B, int tB, int spamm, double tau, int upper_only, int grid_side,
+                             uint64_t* weights);
+typedef struct hbsm_shard_stats {
+    double plan_ms;       /* thresholds + all-gather + flags + scan + count read-back + halo keys/norms (engine stream) */
+    double exchange_ms;   /* pack + grouped ncclSend/ncclRecv of the tiles (comm stream; overlaps the task list and first GEMM) */
+    double publish_ms;    /* last hbsm_publish */
+    uint64_t sent_tiles, recv_tiles;
+} hbsm_shard_stats;
+int hbsm_shard_stats_last(hbsm_shard_stats* out);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -1,5 +1,6 @@
-"""-m gpu: the sharded path end to end on however many GPUs the box has (world_size = 1 also exercises the
-request/select/exchange code: every tile is 'sent' to self), compared with the single-GPU engine result."""
+"""-m gpu: the sharded path (hbsm_comm_init / hbsm_publish / hbsm_sharded_product, NCCL inside the library) end to end on
+however many GPUs the box has (world_size = 1 runs the same entry points with an empty exchange), compared with the
+single-GPU engine result; equal and balanced slabs."""
 import os
 import subprocess
 import sys
@@ -17,10 +18,14 @@ import hierarchical_block_sparse_lib_b200 as hb
 from hierarchical_block_sparse_lib_b200 import sharded as S, generators as G
 H = hb.HierarchicalBlockSparseMatrix
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
-torch.cuda.set_device(lr); dist.init_process_group("nccl", device_id=torch.device("cuda", lr)); hb.init(lr)
+torch.cuda.set_device(lr); dist.init_process_group("nccl", device_id=torch.device("cuda", lr)); hb.init(lr); S.comm_init()
+assert S.comm_info()[:2] == (rank, world)
 n, b, lam = 4096, 64, 0.02
 W = G.decay_width(lam); g = n // b
 lo, hi = S.slab_bounds(g, world, rank)
+if os.environ.get("HBSM_TEST_BALANCED") == "1":     # uneven slabs (what balanced_bounds produces for a clipped band)
+    bounds = S.balanced_bounds(10 + np.minimum(np.minimum(np.arange(g), np.arange(g)[::-1]), 9), world)
+    lo, hi = bounds[rank], bounds[rank + 1]
 for (tA, tB, spamm, tau) in [(0, 0, True, 1e-6), (0, 0, False, 0.0), (0, 1, True, 1e-4), (1, 0, True, 1e-4)]:
     # full matrices (every rank, for the check) and the slabs (what a rank really holds)
     Af = H(np.float64, b); Af.generate_decay(n, lam, W, 1); Af.update_internal_info()
@@ -31,13 +36,16 @@ for (tA, tB, spamm, tau) in [(0, 0, True, 1e-6), (0, 0, False, 0.0), (0, 1, True
         m = (line >= lo) & (line < hi)
         X = H(np.float64, b); X.resize(n, n); X.assign_tiles(bi[m], bj[m], t[m]); X.update_internal_info(); return X
     Al = slab(Af, bool(tA)); Bl = slab(Bf, bool(tB))
-    if os.environ.get("HBSM_TEST_PUBLISH") == "1": S.publish(Bl)      # two-round protocol over the published table
+    S.publish(Bl)
     Cl, nm, nb = S.sharded_product(Al, tA, Bl, tB, spamm, tau)
+    wts = S.row_weights(Al, tA, Bl, tB, spamm, tau)
     Cf = H(np.float64)
     nmf, nbf = (H.spamm(Af, tA, Bf, tB, Cf, tau, True) if spamm else H.multiply(Af, tA, Bf, tB, Cf))
     tot = torch.tensor([nm, nb], dtype=torch.int64, device="cuda"); dist.all_reduce(tot)
     assert (int(tot[0]), int(tot[1])) == (nmf, nbf), (tot.tolist(), nmf, nbf)
+    assert S.allreduce([nm, nb]) == [float(nmf), float(nbf)]          # the library's own all-reduce
     tl = Cl.export_tasks(); tf = Cf.export_tasks()
+    assert np.array_equal(wts, np.bincount(tf[:, 0], minlength=g).astype(np.uint64)), "row weights != products per C block row"
     mine = tf[(tf[:, 0] >= lo) & (tf[:, 0] < hi)]
     key = lambda t: t[np.lexsort((t[:, 2], t[:, 1], t[:, 0]))]
     assert np.array_equal(key(tl), key(mine)), "per-rank executed set differs from the single-GPU set restricted to the slab"
@@ -45,12 +53,12 @@ for (tA, tB, spamm, tau) in [(0, 0, True, 1e-6), (0, 0, False, 0.0), (0, 1, True
     m = (fbi >= lo) & (fbi < hi)
     assert np.array_equal(bi, fbi[m]) and np.array_equal(bj, fbj[m]) and np.array_equal(t, ft[m])   # same kernel, same k order: bitwise
 if rank == 0: print("sharded ok world=%%d" %% world)
-dist.destroy_process_group()
+S.comm_finalize(); dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("torch_plan", ["0", "1", "published", "published_no_overlap"])
-def test_sharded_matches_single_gpu(tmp_path, torch_plan):
+@pytest.mark.parametrize("slabs", ["equal", "balanced"])
+def test_sharded_matches_single_gpu(tmp_path, slabs):
     import torch
     ngpu = torch.cuda.device_count()
     world = 1
@@ -62,9 +70,7 @@ def test_sharded_matches_single_gpu(tmp_path, torch_plan):
     script.write_text(SCRIPT % {"root": ROOT})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)]
-    env = dict(os.environ, HBSM_SHARD_TORCH_PLAN="1" if torch_plan == "1" else "0",
-               HBSM_TEST_PUBLISH="1" if torch_plan.startswith("published") else "0",
-               HBSM_SHARD_OVERLAP="0" if torch_plan == "published_no_overlap" else "1")   # engine kernels (default) or the torch-op plan of the gloo tests
+    env = dict(os.environ, HBSM_TEST_BALANCED="1" if slabs == "balanced" else "0")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "sharded ok" in r.stdout
@@ -77,7 +83,7 @@ import hierarchical_block_sparse_lib_b200 as hb
 from hierarchical_block_sparse_lib_b200 import sharded as S, generators as G
 H = hb.HierarchicalBlockSparseMatrix
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
-torch.cuda.set_device(lr); dist.init_process_group("nccl", device_id=torch.device("cuda", lr)); hb.init(lr)
+torch.cuda.set_device(lr); dist.init_process_group("nccl", device_id=torch.device("cuda", lr)); hb.init(lr); S.comm_init()
 n, b, lam = 4096, 64, 0.02
 W = G.decay_width(lam); g = n // b
 lo, hi = S.slab_bounds(g, world, rank)
@@ -99,7 +105,7 @@ for tau in (1e-6, None):
     assert np.all(ci <= cj)
     assert np.array_equal(ci, fi[mm]) and np.array_equal(cj, fj[mm]) and np.array_equal(tl, tf[mm])   # same kernel, same k order: bitwise
 if rank == 0: print("sharded symm ok world=%%d" %% world)
-dist.destroy_process_group()
+S.comm_finalize(); dist.destroy_process_group()
 '''
 
 

@@ -47,10 +47,11 @@ def _worker(rank, world, port, n, b, lam, tA, tB, spamm, tau, dtype_name, ret):
         am = (a_line >= lo) & (a_line < hi); bm = (b_line >= lo) & (b_line < hi)
         timers = {}
         keys, norms, tiles = S.exchange_b(ak[am], an[am], tA, bk[bm], bn[bm], bt[bm], tB, g, spamm, tau, None, timers)
-        # the two-round protocol over a published table must deliver exactly the same tiles
+        # the all-gather protocol csrc/sharded.cu runs (published table + gathered thresholds, requester and owner evaluate
+        # the same predicate, one all-to-all of tiles) must deliver exactly the same tiles
         table = S.publish_table(bk[bm], bn[bm])
         thr = S.request_thresholds(ak[am], an[am], tA, g)
-        k2, n2, t2 = S.exchange_b_published(thr, table, bt[bm], tB, spamm, tau)
+        k2, n2, t2 = S.exchange_b_allgather(thr, table, bt[bm], tB, spamm, tau)
         o1 = torch.argsort(keys); o2 = torch.argsort(k2)
         assert torch.equal(keys[o1], k2[o2]) and torch.equal(norms[o1], n2[o2]) and torch.equal(tiles[o1], t2[o2])
         # received (remote) tiles are the global ones, bit for bit, and none of them is owned by this rank
@@ -114,6 +115,28 @@ def test_slab_partition_is_top_level_quadtree_rows():
         assert cover == list(range(g))
     with pytest.raises(ValueError):
         S.slab_bounds(4, 8, 0)
+
+
+def test_balanced_bounds_follow_the_weights():
+    """Slab boundaries on prefix sums of per-row weights (python model == hbsm_shard_rows_balanced): monotone, cover every
+    row, equal slabs for equal weights, and a clipped-band profile moves rows from the middle ranks to the edge ranks."""
+    import ctypes as C
+    from hierarchical_block_sparse_lib_b200 import _capi
+    L = _capi.lib()
+    for g, world in ((64, 4), (1024, 8), (16, 8), (8, 8)):
+        assert S.balanced_bounds(np.ones(g), world) == [g * r // world for r in range(world + 1)]
+        d = np.minimum(np.arange(g), np.arange(g)[::-1])
+        w = (10 + np.minimum(d, 9)).astype(np.uint64)                 # band clipped at both matrix edges
+        b = S.balanced_bounds(w, world)
+        out = (C.c_int * (world + 1))()
+        _capi.check(L.hbsm_shard_rows_balanced(w.ctypes.data_as(C.POINTER(C.c_uint64)), g, world, out))
+        assert list(out) == b
+        assert b[0] == 0 and b[-1] == g and all(x <= y for x, y in zip(b, b[1:]))
+        if g >= 64:
+            loads = [float(w[b[r]:b[r + 1]].sum()) for r in range(world)]
+            eq = [float(w[g * r // world:g * (r + 1) // world].sum()) for r in range(world)]
+            assert max(loads) - min(loads) <= max(eq) - min(eq)
+            assert b[1] - b[0] >= g // world                                # the edge slab grew
 
 
 def test_morton_roundtrip_matches_engine_convention():
