@@ -525,11 +525,19 @@ def _e2e_sharded(hb, H, A, B, w, steps, local_rank):
     for i in range(steps + 2):      # two untimed passes: the stream-ordered memory pool reaches its steady state
         torch.cuda.synchronize(); dist.barrier()
         t0 = time.perf_counter()
-        A2 = H(np.float64, b); A2.resize(n, n); A2.assign_tiles(abi, abj, at.numpy()); A2.update_internal_info()
-        B2 = H(np.float64, b); B2.resize(n, n); B2.assign_tiles(bbi, bbj, bt.numpy()); B2.update_internal_info()
-        publish(B2)                      # inside the e2e region: B2 is a new matrix every step
+        marks = []
+
+        def mark(name):
+            marks.append((name, time.perf_counter()))
+
+        # B first: its norms and published table are what the peers wait for
+        B2 = H(np.float64, b); B2.resize(n, n); B2.assign_tiles(bbi, bbj, bt.numpy()); mark("upload_B")
+        B2.update_internal_info(); mark("norms_B")
+        publish(B2); mark("publish_B")                      # inside the e2e region: B2 is a new matrix every step
+        A2 = H(np.float64, b); A2.resize(n, n); A2.assign_tiles(abi, abj, at.numpy()); mark("upload_A")
+        A2.update_internal_info(); mark("norms_A")
         t_up = time.perf_counter() - t0
-        Cm, nm, nr = sharded_product(A2, False, B2, False, True, tau)
+        Cm, nm, nr = sharded_product(A2, False, B2, False, True, tau); mark("sharded_product")
         t_prod = time.perf_counter() - t0 - t_up
         if out is None or out.shape[0] < nr:
             out = torch.empty((nr, b * b), dtype=torch.float64, pin_memory=True)
@@ -545,7 +553,13 @@ def _e2e_sharded(hb, H, A, B, w, steps, local_rank):
         sm = v.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         if i > 1:
             times.append(float(mx[0]))
-            phases = {"upload_assign_norms_publish_ms": 1e3 * t_up, "product_ms": 1e3 * t_prod, "download_ms": 1e3 * (dt - t_up - t_prod)}
+            phases = {}
+            prev = t0
+            for name, t in marks:
+                phases[name + "_ms"] = round(1e3 * (t - prev), 3); prev = t
+            phases["download_C_ms"] = round(1e3 * (t0 + dt - prev), 3)
+            phases["engine_stage_ms"] = {k: round(v, 3) for k, v in hb.stage_times().items() if k.endswith("_ms")}
+            phases["shard_stats"] = shard_stats()
         nm_tot = int(sm[1]); h2d_tot = int(sm[2]); d2h = int(sm[3])
     ms = 1e3 * float(np.mean(times))
     return {"value": 2.0 * b ** 3 * nm_tot / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ms,

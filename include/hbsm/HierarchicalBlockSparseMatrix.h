@@ -197,6 +197,37 @@ public:
         if (no_of_resizes) *no_of_resizes = nr;
     }
     hbsm_handle handle() const { return h_; }
+    // ---- multi-GPU extras (not in the reference; one process per GPU, see hbsm::comm below and INTEGRATION.md) ----
+    // Every rank holds matrices with the FULL logical dimensions but only the tiles of its slab of block rows (C row for
+    // op(A), contraction index for op(B)) and receives the same slab of C.  publish() is the distributed half of
+    // update_internal_info() for a right operand; the sharded_* statics are collective and mirror multiply (H:260) /
+    // spamm (H:305) / symm_square (H:277) argument for argument; the counters they return are this rank's.
+    void publish() { detail::check(hbsm_publish(h_)); }
+    static void sharded_multiply(HierarchicalBlockSparseMatrix<Treal> const& A, bool tA, HierarchicalBlockSparseMatrix<Treal>& B, bool tB,
+                                 HierarchicalBlockSparseMatrix<Treal>& C, size_t* no_of_block_multiplies = NULL,
+                                 size_t* no_of_resizes = NULL) {
+        size_t nm = 0, nr = 0;
+        detail::check(hbsm_sharded_product(A.h_, tA ? 1 : 0, B.h_, tB ? 1 : 0, C.h_, 0, 0.0, 0, &nm, &nr));
+        if (no_of_block_multiplies) *no_of_block_multiplies = nm;
+        if (no_of_resizes) *no_of_resizes = nr;
+    }
+    static void sharded_spamm(HierarchicalBlockSparseMatrix<Treal> const& A, bool tA, HierarchicalBlockSparseMatrix<Treal>& B, bool tB,
+                              HierarchicalBlockSparseMatrix<Treal>& C, const Treal tau, size_t* no_of_block_multiplies = NULL,
+                              size_t* no_of_resizes = NULL) {
+        size_t nm = 0, nr = 0;
+        detail::check(hbsm_sharded_product(A.h_, tA ? 1 : 0, B.h_, tB ? 1 : 0, C.h_, 1, (double)tau, 0, &nm, &nr));
+        if (no_of_block_multiplies) *no_of_block_multiplies = nm;
+        if (no_of_resizes) *no_of_resizes = nr;
+    }
+    // F: a symmetric matrix in FULL storage, row-sharded and published; C = this rank's block rows of triu(F*F), SpAMM-pruned
+    // with tau (prune = false: exact, symm_square H:3563 of F's upper triangle)
+    static void sharded_symm_square(HierarchicalBlockSparseMatrix<Treal>& F, HierarchicalBlockSparseMatrix<Treal>& C, bool prune,
+                                    const Treal tau, size_t* no_of_block_multiplies = NULL, size_t* no_of_resizes = NULL) {
+        size_t nm = 0, nr = 0;
+        detail::check(hbsm_sharded_product(F.h_, 0, F.h_, 0, C.h_, prune ? 1 : 0, (double)tau, 1, &nm, &nr));
+        if (no_of_block_multiplies) *no_of_block_multiplies = nm;
+        if (no_of_resizes) *no_of_resizes = nr;
+    }
     // Host-to-host multiply / SpAMM in one pipelined call (hbsm_product_from_host): A and B are sized matrices without
     // tiles; their dense column-major tiles come from host arrays (tile t at block (a_bi[t], a_bj[t])), C's tiles go to
     // c_tiles (room for cap_tiles tiles; c_bi/c_bj receive their block coordinates).  PCIe upload, norm refresh, leaf
@@ -528,6 +559,25 @@ private:
         return child[0] + child[1] + child[2] + child[3];
     }
 };
+
+// One communicator per process (NCCL inside libhbsm_b200.so).  Rank 0 makes the id and hands its bytes to the other ranks by
+// whatever the host program has (MPI_Bcast, a file, a socket); then every rank calls init after hbsm_init(device).
+namespace comm {
+inline std::vector<unsigned char> unique_id() {
+    std::vector<unsigned char> id(HBSM_COMM_ID_BYTES);
+    detail::check(hbsm_comm_unique_id(id.data()));
+    return id;
+}
+inline void init(const std::vector<unsigned char>& id, int rank, int world) {
+    if (id.size() != HBSM_COMM_ID_BYTES) throw std::runtime_error("hbsm::comm::init: the id must have HBSM_COMM_ID_BYTES bytes");
+    detail::check(hbsm_comm_init(id.data(), rank, world));
+}
+inline void finalize() { detail::check(hbsm_comm_finalize()); }
+inline void barrier() { detail::check(hbsm_comm_barrier()); }
+inline void rows_of(int grid_side, int world, int rank, int& lo, int& hi) { detail::check(hbsm_shard_rows(grid_side, world, rank, &lo, &hi)); }
+inline double sum(double v) { detail::check(hbsm_comm_allreduce_f64(&v, 1, 0)); return v; }
+inline double max(double v) { detail::check(hbsm_comm_allreduce_f64(&v, 1, 1)); return v; }
+}  // namespace comm
 
 }  // namespace hbsm
 

@@ -47,3 +47,21 @@ def test_reference_own_test_programs_pass_against_the_dropin(name, argv):
         pytest.skip("reference test binaries were not built (no /root/reference at build time)")
     r = subprocess.run([exe] + argv, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout[-2000:] + r.stderr[-2000:])
+
+
+@pytest.mark.gpu
+def test_sharded_product_through_the_cpp_class():
+    """tests/cpp/test_sharded.cc: forks one process per GPU, NCCL id handed over a pipe, hbsm::comm::init, publish() and the
+    sharded_multiply / sharded_spamm / sharded_symm_square statics of the drop-in class against the single-GPU product."""
+    import torch
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "test_sharded")
+    assert os.path.exists(exe), "tests/cpp/_build/test_sharded missing (run __graft_entry__.build())"
+    ngpu = torch.cuda.device_count()
+    world = 1
+    for wsz in (8, 4, 2):
+        if ngpu >= wsz:
+            world = wsz
+            break
+    r = subprocess.run([exe, str(world)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "sharded c++ ok world=%d" % world in r.stdout
