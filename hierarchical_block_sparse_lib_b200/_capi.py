@@ -101,6 +101,7 @@ SIGNATURES = {
     "hbsm_assign_device_tiles": (_I, [_H, _sz, _P, _P, _P]),
     "hbsm_halo_reserve": (_I, [_H, _sz, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "hbsm_halo_commit": (_I, [_H, _sz]),
+    "hbsm_leaf_inv_chol": (_I, [_H, _H, _I, _I]),
     "hbsm_comm_set_library": (_I, [C.c_char_p]),
     "hbsm_comm_unique_id": (_I, [_P]),
     "hbsm_comm_init": (_I, [_P, _I, _I]),

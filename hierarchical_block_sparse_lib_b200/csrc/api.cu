@@ -466,6 +466,10 @@ void hbsm_morton_decode(uint64_t key, uint32_t* bi, uint32_t* bj) {
 }
 void* hbsm_stream(void) { return (void*)engine().stream; }
 
+int hbsm_leaf_inv_chol(hbsm_handle A, hbsm_handle Z, int zdim, int valid) {
+    return guarded([&] { op_leaf_inv_chol(M(A), M(Z), zdim, valid); });
+}
+
 // ---- multi-GPU (sharded.cu) ----
 int hbsm_comm_set_library(const char* path) { return guarded([&] { comm_set_library(path); }); }
 int hbsm_comm_unique_id(void* id_out) {

@@ -369,9 +369,18 @@ k_gemm_f32_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------------
 template <int BS>
 struct Q4Cfg {
-    static constexpr int KC = BS;                            // whole leaf product per pipeline stage
+    static constexpr int KC = BS;                            // whole leaf products per pipeline stage
     static constexpr int OPER_BYTES = BS * KC * 4;
-    static constexpr int STAGE_BYTES = 4 * OPER_BYTES;       // A (hi+lo) | B (hi+lo)
+    static constexpr int PROD_BYTES = 4 * OPER_BYTES;        // one product: A (hi+lo) | B (hi+lo)
+    // Products per pipeline stage.  The producer lane, the MMA-issuing lane and the hand-offs between the roles cost several
+    // hundred clocks PER STAGE whatever its size (measured with HBSM_F32_PROF: at one 32-leaf product per stage the issuing
+    // lane was busy 656 clk per product for 188 clk of MMAs), so a stage carries up to GP consecutive products of one C tile:
+    // 64 KiB of operands per stage at both leaf sizes.  The GP products are chained into ONE TMEM accumulator set (16 MMAs at
+    // 32-leaves, 8 at 64; the tensor core truncates when it adds into the accumulator, so chains stay short: bias ~16 * 2^-24
+    // relative, inside the 1e-5 bar); the epilogue adds the chains in k order with round-to-nearest fp32 adds.
+    static constexpr int GP = BS == 32 ? 4 : 1;
+    static constexpr int CH = BS == 32 ? 1 : 2;              // stages chained into one accumulator set (16 MMAs either way)
+    static constexpr int STAGE_BYTES = GP * PROD_BYTES;
     static constexpr int NST = (192 * 1024 / STAGE_BYTES) > 8 ? 8 : (192 * 1024 / STAGE_BYTES);
     static constexpr int MM = 2 * BS, NN = 2 * BS;           // stacked MMA shape
     static constexpr int SLAB_MN = KC * 128, SLAB_K = BS * 128;
@@ -386,7 +395,13 @@ struct Q4Cfg {
     static constexpr int NSETS = 512 / NN;
     static constexpr int TMEM_COLS = NSETS * NN;
     static constexpr int THREADS = 512;
-    static constexpr int CVT_WARPS = 4;
+    // hi/lo split warps (warps 2..7) in CVT_GROUPS groups of CVT_WPG warps: group g owns the pipeline stages of iterations
+    // g, g + CVT_GROUPS, ..., so CVT_GROUPS products are being split at once -- one product's split is a dependent chain
+    // (load, subtract, store, proxy fence, arrive) of several hundred clocks.  Never more groups than stages: a group's first
+    // wait would otherwise alias the parity of a phase that has not started.
+    static constexpr int CVT_WARPS = 6;
+    static constexpr int CVT_GROUPS = NST >= 6 ? 6 : (NST >= 3 ? 3 : 2);
+    static constexpr int CVT_WPG = CVT_WARPS / CVT_GROUPS;
     static constexpr int KSTEPS = KC / 8;
 };
 
@@ -394,8 +409,13 @@ template <int BS, bool TA, bool TB>
 __global__ void __launch_bounds__(Q4Cfg<BS>::THREADS, 1)
 k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
               const uint2* __restrict__ ab, const uint64_t* __restrict__ begin, uint32_t n_ctiles,
-              const uint32_t* __restrict__ tile_list, unsigned* __restrict__ next_tile, float* __restrict__ Ct) {
+              const uint32_t* __restrict__ tile_list, unsigned* __restrict__ next_tile, float* __restrict__ Ct,
+              int dbg /* timing ablations with WRONG results, see f32_mode(): 4 no split, 8 no drain, 16 no MMAs, 64 no TMA */,
+              unsigned long long* __restrict__ prof /* null, or 16 counters: block 0's wait / total clocks per role (HBSM_F32_PROF=1) */) {
     using Cfg = Q4Cfg<BS>;
+    const bool profiling = prof != nullptr && blockIdx.x == 0;
+    long long t_role0 = 0, t_wait = 0, t_wait2 = 0;
+#define HB_PWAIT(acc, call) do { if (profiling) { const long long t_ = clock64(); call; acc += clock64() - t_; } else { call; } } while (0)
     constexpr int NST = Cfg::NST, KC = Cfg::KC;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -407,7 +427,7 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) {
             mbar_init(smem_u32(&hd->full_raw[s]), 1);
-            mbar_init(smem_u32(&hd->full_cvt[s]), Cfg::CVT_WARPS);
+            mbar_init(smem_u32(&hd->full_cvt[s]), Cfg::CVT_WPG);   // the split warps of the group that owns the stage
             mbar_init(smem_u32(&hd->empty[s]), 1);
         }
         for (int a = 0; a < Cfg::NSETS; ++a) {
@@ -421,6 +441,7 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hd->tmem_base;
+    if (profiling) t_role0 = clock64();
 
     if (warp == 0) {
         // ===== TMA producer: raw operand slabs land in the "hi" positions of the stacked layout.  The warp walks the task
@@ -441,21 +462,26 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             const uint64_t bnd = begin[tile + (lane & 1u)];
             const uint64_t p0 = __shfl_sync(0xffffffffu, bnd, 0), p1 = __shfl_sync(0xffffffffu, bnd, 1);
             for (uint64_t pb = p0; pb < p1; pb += 32) {
-                const uint2 mine = (pb + lane < p1) ? ab[pb + lane] : make_uint2(0u, 0u);
+                const uint2 mine = (pb + lane < p1) ? ab[pb + lane] : make_uint2(0u, 0u);   // lane l: operands of product pb + l
                 const int cnt = (int)((p1 - pb) < 32 ? (p1 - pb) : 32);
-                for (int j = 0; j < cnt; ++j, ++it) {
-                    uint2 t;
-                    t.x = __shfl_sync(0xffffffffu, mine.x, j);
-                    t.y = __shfl_sync(0xffffffffu, mine.y, j);
+                for (int j0 = 0; j0 < cnt; j0 += Cfg::GP, ++it) {      // one stage = products [pb + j0, pb + j0 + n)
+                    const int n = cnt - j0 < Cfg::GP ? cnt - j0 : Cfg::GP;
+                    const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                    const uint32_t fb = smem_u32(&hd->full_raw[s]);
                     if (lane == 0) {
-                        const uint64_t p = pb + j;
-                        const uint32_t s = it % NST, ph = (it / NST) & 1u;
-                        mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
-                        const uint32_t fb = smem_u32(&hd->full_raw[s]);
+                        HB_PWAIT(t_wait, mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u));
                         hd->meta[s].ctile = (int)tile;
-                        hd->meta[s].flags = (p == p0 ? 1 : 0) | (p + 1 == p1 ? 2 : 0);
-                        mbar_arrive_expect_tx(fb, 2 * Cfg::OPER_BYTES);
-                        const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
+                        hd->meta[s].flags = (pb + j0 == p0 ? 1 : 0) | (pb + j0 + n == p1 ? 2 : 0) | (n << 8);
+                        if (dbg & 64) mbar_arrive(fb);
+                        else mbar_arrive_expect_tx(fb, (uint32_t)n * 2u * Cfg::OPER_BYTES);
+                    }
+                    if (Cfg::GP > 1) __syncwarp();
+                    // lanes j0 .. j0 + n - 1 issue one product's copies each (GP = 1: lane 0 issues for lane j0)
+                    const int l = Cfg::GP > 1 ? (int)lane - j0 : (lane == 0 ? 0 : -1);
+                    const uint2 tj = Cfg::GP > 1 ? mine : make_uint2(__shfl_sync(0xffffffffu, mine.x, j0), __shfl_sync(0xffffffffu, mine.y, j0));
+                    if (l >= 0 && l < n && !(dbg & 64)) {
+                        const uint2 t = tj;
+                        const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES + (size_t)l * Cfg::PROD_BYTES);
                         const uint32_t sb = sa + 2 * Cfg::OPER_BYTES;
                         if (TA) {   // K-major: [BS mn][32 k] slabs, hi slab j at 2j * SLAB_K
 #pragma unroll
@@ -476,12 +502,15 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 }
             }
         }
-        if (lane == 0) {
-            const uint32_t s = it % NST, ph = (it / NST) & 1u;
-            mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
-            hd->meta[s].ctile = -1;
-            hd->meta[s].flags = 4;
-            mbar_arrive(smem_u32(&hd->full_raw[s]));
+        if (profiling && lane == 0) { prof[0] = (unsigned long long)t_wait; prof[1] = (unsigned long long)(clock64() - t_role0); prof[2] = it; }
+        if (lane == 0) {   // one terminal stage per split group (each of them watches only its own stages)
+            for (int e = 0; e < Cfg::CVT_GROUPS; ++e, ++it) {
+                const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
+                hd->meta[s].ctile = -1;
+                hd->meta[s].flags = 4;
+                mbar_arrive(smem_u32(&hd->full_raw[s]));
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: one stacked MMA per K-step =====
@@ -493,13 +522,16 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             constexpr uint32_t A_LT = TA ? 2 : 1, B_LT = TB ? 1 : 2;
             // (Interleaving the K-steps of consecutive products over their accumulator sets was tried and is SLOWER:
             // 100 -> 72 TF/s at 64-leaves, 23.6 -> 20.8 at 32 -- the issuer then waits for whole batches of stages.)
+            uint32_t chain = 0;       // accumulator-set uses so far
+            int in_chain = 0, chain_flags = 0;
             for (uint32_t it = 0;; ++it) {
                 const uint32_t s = it % NST, ph = (it / NST) & 1u;
-                mbar_wait(smem_u32(&hd->full_cvt[s]), ph);
+                HB_PWAIT(t_wait, mbar_wait(smem_u32(&hd->full_cvt[s]), ph));
                 const GemmMeta m = hd->meta[s];
-                const uint32_t as = it % Cfg::NSETS;
-                mbar_wait(smem_u32(&hd->tmem_empty[as]), ((it / Cfg::NSETS) & 1u) ^ 1u);   // epilogue drained this accumulator set
-                if (m.flags & 4) {
+                const uint32_t as = chain % Cfg::NSETS;
+                if (in_chain == 0) HB_PWAIT(t_wait2, mbar_wait(smem_u32(&hd->tmem_empty[as]), ((chain / Cfg::NSETS) & 1u) ^ 1u));   // epilogue drained this set
+                if (m.flags & 4) {   // (a chain never spans C tiles, so none is open here)
+                    if (profiling) { prof[3] = (unsigned long long)t_wait; prof[4] = (unsigned long long)t_wait2; prof[5] = (unsigned long long)(clock64() - t_role0); }
                     hd->acc_flags[as] = 4;
                     __threadfence_block();
                     mbar_arrive(smem_u32(&hd->tmem_full[as]));
@@ -507,29 +539,44 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 }
                 tc_fence_after();
                 const uint32_t d = tmem_base + as * Cfg::NN;
-                const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES), sb = sa + 2 * Cfg::OPER_BYTES;
+                const int n = Cfg::GP == 1 ? 1 : (m.flags >> 8);
+                const uint32_t s0 = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
+                // descriptors of the stage's first product, first K-step; the others differ in the start-address field only
+                const uint64_t da0 = umma_desc(s0, A_LBO, A_SBO, A_LT), db0 = umma_desc(s0 + 2 * Cfg::OPER_BYTES, B_LBO, B_SBO, B_LT);
+                if (!(dbg & 16))
+                for (int j = 0; j < n; ++j) {
 #pragma unroll
-                for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
-                    const uint32_t ao = TA ? (uint32_t)((ks >> 2) * 2 * Cfg::SLAB_K + (ks & 3) * 32) : (uint32_t)(ks * 1024);
-                    const uint32_t bo = TB ? (uint32_t)(ks * 1024) : (uint32_t)((ks >> 2) * 2 * Cfg::SLAB_K + (ks & 3) * 32);
-                    mma_tf32(d, umma_desc(sa + ao, A_LBO, A_SBO, A_LT), umma_desc(sb + bo, B_LBO, B_SBO, B_LT), IDESC, ks ? 1u : 0u);
+                    for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+                        const uint32_t ao = TA ? (uint32_t)((ks >> 2) * 2 * Cfg::SLAB_K + (ks & 3) * 32) : (uint32_t)(ks * 1024);
+                        const uint32_t bo = TB ? (uint32_t)(ks * 1024) : (uint32_t)((ks >> 2) * 2 * Cfg::SLAB_K + (ks & 3) * 32);
+                        mma_tf32(d, da0 + (uint64_t)((j * Cfg::PROD_BYTES + ao) >> 4), db0 + (uint64_t)((j * Cfg::PROD_BYTES + bo) >> 4), IDESC,
+                                 (ks || j || in_chain) ? 1u : 0u);
+                    }
                 }
                 tc_commit(smem_u32(&hd->empty[s]));
-                hd->acc_tile[as] = m.ctile;
-                hd->acc_flags[as] = m.flags & 3;
-                __threadfence_block();
-                tc_commit(smem_u32(&hd->tmem_full[as]));
+                chain_flags |= m.flags & 3;
+                if ((m.flags & 2) || ++in_chain == Cfg::CH) {   // hand the set to the epilogue
+                    hd->acc_tile[as] = m.ctile;
+                    hd->acc_flags[as] = chain_flags;
+                    __threadfence_block();
+                    tc_commit(smem_u32(&hd->tmem_full[as]));
+                    ++chain;
+                    in_chain = 0;
+                    chain_flags = 0;
+                }
             }
         }
-    } else if (warp >= 4 && warp < 4 + Cfg::CVT_WARPS) {
-        // ===== lo = x - trunc_tf32(x) next to every raw slab (the raw slab itself serves as hi) =====
-        const unsigned tid = threadIdx.x - 128;
-        for (uint32_t it = 0;; ++it) {
+    } else if (warp >= 2 && warp < 2 + Cfg::CVT_WARPS) {
+        // ===== lo = x - trunc_tf32(x) next to every raw slab (the raw slab itself serves as hi); group g owns iterations g, g+G, ... =====
+        const unsigned tid = ((warp - 2) % Cfg::CVT_WPG) * 32 + lane;
+        for (uint32_t it = (warp - 2) / Cfg::CVT_WPG;; it += Cfg::CVT_GROUPS) {
             const uint32_t s = it % NST, ph = (it / NST) & 1u;
-            mbar_wait(smem_u32(&hd->full_raw[s]), ph);
+            HB_PWAIT(t_wait, mbar_wait(smem_u32(&hd->full_raw[s]), ph));
             const int flags = hd->meta[s].flags;
-            if (!(flags & 4)) {
-                unsigned char* st = stages + (size_t)s * Cfg::STAGE_BYTES;
+            if (profiling && (flags & 4) && warp == 2 && lane == 0) { prof[6] = (unsigned long long)t_wait; prof[7] = (unsigned long long)(clock64() - t_role0); }
+            if (!(flags & 4) && !(dbg & 4))
+            for (int pj = 0; pj < (Cfg::GP == 1 ? 1 : (flags >> 8)); ++pj) {
+                unsigned char* st = stages + (size_t)s * Cfg::STAGE_BYTES + (size_t)pj * Cfg::PROD_BYTES;
 #pragma unroll
                 for (int op = 0; op < 2; ++op) {
                     const bool kmajor = op == 0 ? TA : !TB;
@@ -541,7 +588,7 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                         const float4* hi = reinterpret_cast<const float4*>(st + op * 2 * Cfg::OPER_BYTES + rg * 2 * range_bytes);
                         float4* lo = reinterpret_cast<float4*>(st + op * 2 * Cfg::OPER_BYTES + rg * 2 * range_bytes + lo_off);
 #pragma unroll 4
-                        for (int i = (int)tid; i < range_bytes / 16; i += Cfg::CVT_WARPS * 32) {
+                        for (int i = (int)tid; i < range_bytes / 16; i += Cfg::CVT_WPG * 32) {
                             const float4 x = hi[i];
                             float4 l;
                             l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
@@ -552,8 +599,8 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                         }
                     }
                 }
-                fence_proxy_async();
             }
+            if (!(flags & 4) && !(dbg & 4)) fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&hd->full_cvt[s]));
             if (flags & 4) break;
@@ -568,15 +615,23 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         float acc[32];
         for (uint32_t pc = 0;; ++pc) {
             const uint32_t as = pc % Cfg::NSETS;
-            mbar_wait(smem_u32(&hd->tmem_full[as]), (pc / Cfg::NSETS) & 1u);
+            HB_PWAIT(t_wait, mbar_wait(smem_u32(&hd->tmem_full[as]), (pc / Cfg::NSETS) & 1u));
             const int flags = hd->acc_flags[as];
-            if (flags & 4) break;
+            if (flags & 4) {
+                if (profiling && warp == 8 && lane == 0) { prof[8] = (unsigned long long)t_wait; prof[9] = (unsigned long long)(clock64() - t_role0); prof[10] = pc; }
+                break;
+            }
             const int ctile = hd->acc_tile[as];
             tc_fence_after();
             uint32_t r1[32], r2[32];
-            tmem_ld32(tmem_base + ((q * 32u) << 16) + as * Cfg::NN + BS + h * 32, r2);   // x * B_lo
-            tmem_ld32(tmem_base + ((q * 32u) << 16) + as * Cfg::NN + h * 32, r1);        // x * B_hi
-            tmem_ld_wait();
+            if (!(dbg & 8)) {
+                tmem_ld32(tmem_base + ((q * 32u) << 16) + as * Cfg::NN + BS + h * 32, r2);   // x * B_lo
+                tmem_ld32(tmem_base + ((q * 32u) << 16) + as * Cfg::NN + h * 32, r1);        // x * B_hi
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { r1[j] = 0u; r2[j] = 0u; }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&hd->tmem_empty[as]));
@@ -606,10 +661,12 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+#undef HB_PWAIT
 }
 
 // development switches (HBSM_F32_MODE): bit 0 = leave the raw operand in place as "hi", bit 1 = issue M = 64 MMAs for leaves <= 64;
-// timing experiments with WRONG results: 4 = skip the hi/lo split, 8 = skip the TMEM drain, 16 = skip the MMAs;
+// timing experiments with WRONG results: 4 = skip the hi/lo split, 8 = skip the TMEM drain, 16 = skip the MMAs, 64 = skip the
+// TMA loads (stacked kernel only);
 // 32 = use the three-MMA kernel for leaves of 32 / 64 as well (instead of the stacked-operand kernel)
 int f32_mode() {
     static int mode = -1;
@@ -674,7 +731,17 @@ bool launch_q4_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uin
         configured = true;
     }
     unsigned grid = std::min<unsigned>(n_ctiles, (unsigned)engine().sm_count);
-    HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, ab, begin, n_ctiles, tile_list, counter, Ct);
+    static const bool want_prof = getenv("HBSM_F32_PROF") != nullptr;
+    DevBuf<unsigned long long> prof;
+    if (want_prof) { prof.alloc(16); prof.zero(); }
+    HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, ab, begin, n_ctiles, tile_list, counter, Ct, f32_mode() & (4 | 8 | 16 | 64),
+              prof.p);
+    if (want_prof) {   // diagnosis only: synchronises
+        const std::vector<unsigned long long> h = prof.to_host();
+        fprintf(stderr, "[f32 q4<%d> block 0, clocks] producer: wait-empty %llu of %llu (%llu stages) | issuer: wait-split %llu wait-drain %llu of %llu | "
+                        "split warp 2: wait-TMA %llu of %llu | epilogue warp 8: wait-MMA %llu of %llu (%llu chains)\n",
+                BS, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10]);
+    }
     return true;
 }
 

@@ -760,6 +760,44 @@ __global__ void k_rekey(const uint64_t* __restrict__ in, size_t n, uint64_t mask
     if (i < n) out[i] = (in[i] & mask) | add;
 }
 
+
+// Leaf step of inv_chol (H:3118-3147): Z = inverse Cholesky factor of one dense SPD leaf (upper triangular, Z^T A Z = I) by
+// the reference's column recurrence -- column i starts as e_i, is made A-orthogonal to the finished columns j < i one after
+// the other (the order matters: each projection sees the previous update) and is normalised in the A-norm.  One block; thread
+// k owns row k of the column in flight; the A-inner products are block reductions (not the reference's sequential sum: the
+// result agrees to rounding, the reference's own tests ask for 1e-10).
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* red) {
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();                      // red[] of the previous reduction has been read by everyone
+    if ((threadIdx.x & 31) == 0) red[w] = v;
+    __syncthreads();
+    T s = 0;
+    for (int i = 0; i < nw; ++i) s += red[i];
+    return s;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_leaf_inv_chol(const T* __restrict__ a, int b, int n, T* __restrict__ z) {
+    __shared__ T red[8];
+    const int k = threadIdx.x;
+    const bool live = k < n;
+    for (int i = 0; i < n; ++i) {
+        T zi = (live && k == i) ? (T)1 : (T)0;
+        for (int j = 0; j < i; ++j) {
+            // R = sum_k A(j,k) * zi[k], times Z(j,j); column i loses its component along column j
+            T R = block_sum<T>(live ? a[(size_t)k * b + j] * zi : (T)0, red);
+            R *= z[(size_t)j * b + j];
+            if (live) zi -= z[(size_t)j * b + k] * R;
+        }
+        T R = block_sum<T>(live ? a[(size_t)k * b + i] * zi : (T)0, red);
+        R = sqrt((T)1 / R);
+        if (live) z[(size_t)i * b + k] = zi * R;
+        __syncthreads();                  // column i is read (diagonal and entries) by the following columns
+        __threadfence_block();
+    }
+}
+
 template <typename F>
 void dispatch(int dtype, F&& f) {
     if (dtype == HBSM_F64) f((double)0);
@@ -1398,6 +1436,25 @@ void op_assemble_quadrants(Matrix& C, int M, int N, const Matrix* quads[4]) {
         at += Q->L;
     }
     C.set_table(std::move(keys), std::move(tiles), total);
+    sync_stream();
+}
+
+// inv_chol leaf (H:3118-3147): A is a single-leaf matrix, Z becomes the zdim x zdim single-leaf inverse factor of its leading
+// `valid` x `valid` block (identity pattern elsewhere is NOT written: rows/columns >= valid stay zero, as upstream)
+void op_leaf_inv_chol(const Matrix& A, Matrix& Z, int zdim, int valid) {
+    ensure_engine();
+    if (A.empty() || A.vdepth() != 0 || A.L != 1) throw Error(HBSM_E_ARG, "hbsm_b200: leaf_inv_chol wants a single-leaf matrix");
+    if (zdim <= 0 || zdim > A.b) throw Error(HBSM_E_ARG, "hbsm_b200: leaf_inv_chol: bad result dimension");
+    if (A.b > 256) throw Error(HBSM_E_ARG, "hbsm_b200: leaf_inv_chol supports leaves up to 256");
+    Z.dtype = A.dtype;
+    Z.b = A.b;
+    Z.resize(zdim, zdim);                 // one zero-filled leaf
+    const int n = std::min(valid, A.b);
+    if (n <= 0) return;
+    dispatch(A.dtype, [&](auto zt) {
+        using T = decltype(zt);
+        HB_LAUNCH(k_leaf_inv_chol<T>, 1, 256, 0, (const T*)A.tiles.p, A.b, n, (T*)Z.tiles.p);
+    });
     sync_stream();
 }
 

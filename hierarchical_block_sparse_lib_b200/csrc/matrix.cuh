@@ -118,6 +118,7 @@ void op_copy(Matrix& C, const Matrix& A);
 bool op_trunc(const Matrix& A, Matrix& C, double trunc_value);   // frob_block_trunc, H:4935; true if something was removed
 bool op_extract_quadrant(const Matrix& A, int q, Matrix& C);        // false = absent; child q (0=TL 1=BL 2=TR 3=BR, H:52-56) as its own matrix
 void op_assemble_quadrants(Matrix& C, int M, int N, const Matrix* quads[4]);   // inverse; null / empty = absent child
+void op_leaf_inv_chol(const Matrix& A, Matrix& Z, int zdim, int valid);   // dense leaf step of inv_chol, H:3118-3147
 void sym_expand(const Matrix& A, Matrix& S);             // S = triu(A) + striu(A)^T as a full matrix
 void mask_diag_upper(Matrix& C);                         // zero the strict lower part of diagonal tiles in place
 void generate_decay(Matrix& A, int n, const double* table, int W, uint64_t seed, bool symmetric, int lo, int hi);

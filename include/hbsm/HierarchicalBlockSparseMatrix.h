@@ -453,31 +453,8 @@ private:
     // Z receives dims (zdim, zdim)
     static void inv_chol_rec(Self const& A, Self& Z, int zdim, int valid) {
         const int b = A.get_params().blocksize;
-        if (A.expected_depth() == 0) {   // leaf factor, H:3118-3140
-            Z.resize(zdim, zdim);
-            const int n = valid < b ? valid : b;
-            if (n <= 0) return;
-            std::vector<int> r((size_t)n * n), c((size_t)n * n);
-            for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) { r[(size_t)j * n + i] = i; c[(size_t)j * n + i] = j; }
-            std::vector<Treal> a;
-            A.get_values(r, c, a);                      // a[j*n + i] = A(i,j)
-            std::vector<Treal> z((size_t)n * n, (Treal)0);   // z[col*n + row]
-            for (int i = 0; i < n; ++i) z[(size_t)i * n + i] = (Treal)1;
-            z[0] = std::sqrt(1 / a[0]);
-            for (int i = 1; i < n; ++i) {
-                Treal R;
-                for (int j = 0; j < i; ++j) {
-                    R = 0;
-                    for (int k = 0; k < n; ++k) R += a[(size_t)k * n + j] * z[(size_t)i * n + k];
-                    R *= z[(size_t)j * n + j];
-                    for (int k = 0; k < n; ++k) z[(size_t)i * n + k] -= z[(size_t)j * n + k] * R;
-                }
-                R = 0;
-                for (int k = 0; k < n; ++k) R += a[(size_t)k * n + i] * z[(size_t)i * n + k];
-                R = std::sqrt(1 / R);
-                for (int k = 0; k < n; ++k) z[(size_t)i * n + k] *= R;
-            }
-            Z.assign_from_vectors(r, c, z);
+        if (A.expected_depth() == 0) {   // leaf factor, H:3118-3147: one kernel on the leaf where it lies (hbsm_leaf_inv_chol)
+            detail::check(hbsm_leaf_inv_chol(A.h_, Z.h_, zdim, valid));
             return;
         }
         long long v = b;
