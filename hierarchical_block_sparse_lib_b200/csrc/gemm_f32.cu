@@ -468,6 +468,9 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     const int n = cnt - j0 < Cfg::GP ? cnt - j0 : Cfg::GP;
                     const uint32_t s = it % NST, ph = (it / NST) & 1u;
                     const uint32_t fb = smem_u32(&hd->full_raw[s]);
+                    // (operand indices are fetched BEFORE the wait: with three 64 KiB stages the time from "stage freed" to
+                    // "copies issued" is on the critical path)
+                    const uint2 tj = Cfg::GP > 1 ? mine : make_uint2(__shfl_sync(0xffffffffu, mine.x, j0), __shfl_sync(0xffffffffu, mine.y, j0));
                     if (lane == 0) {
                         HB_PWAIT(t_wait, mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u));
                         hd->meta[s].ctile = (int)tile;
@@ -478,7 +481,6 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     if (Cfg::GP > 1) __syncwarp();
                     // lanes j0 .. j0 + n - 1 issue one product's copies each (GP = 1: lane 0 issues for lane j0)
                     const int l = Cfg::GP > 1 ? (int)lane - j0 : (lane == 0 ? 0 : -1);
-                    const uint2 tj = Cfg::GP > 1 ? mine : make_uint2(__shfl_sync(0xffffffffu, mine.x, j0), __shfl_sync(0xffffffffu, mine.y, j0));
                     if (l >= 0 && l < n && !(dbg & 64)) {
                         const uint2 t = tj;
                         const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES + (size_t)l * Cfg::PROD_BYTES);

@@ -608,6 +608,42 @@ __global__ void __launch_bounds__(256) k_transpose_tiles(const T* __restrict__ t
         }
 }
 
+// same for leaves that are a multiple of 32: NSUB 32x32 sub-blocks per phase, so every thread has 4*NSUB independent loads
+// in flight before the first barrier (the one-sub-block-per-phase loop above is latency-bound: 0.43 of the HBM copy rate
+// for fp32 tiles, profiles/r01_hbm_stages.md)
+template <typename T, int NSUB>
+__global__ void __launch_bounds__(256) k_transpose_tiles_wide(const T* __restrict__ tin, const uint32_t* __restrict__ src,
+                                                               int b, T* __restrict__ tout) {
+    __shared__ T s[NSUB][32][33];
+    const size_t bb = (size_t)b * b;
+    const T* in = tin + (size_t)src[blockIdx.x] * bb;
+    T* out = tout + (size_t)blockIdx.x * bb;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const int nb = b >> 5, total = nb * nb;
+    for (int q0 = 0; q0 < total; q0 += NSUB) {
+#pragma unroll
+        for (int u = 0; u < NSUB; ++u) {
+            const int q = q0 + u;
+            if (q < total) {
+                const int r0 = (q % nb) * 32, c0 = (q / nb) * 32;
+#pragma unroll
+                for (int j = ty; j < 32; j += 8) s[u][j][tx] = in[(size_t)(c0 + j) * b + r0 + tx];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < NSUB; ++u) {
+            const int q = q0 + u;
+            if (q < total) {
+                const int r0 = (q % nb) * 32, c0 = (q / nb) * 32;
+#pragma unroll
+                for (int j = ty; j < 32; j += 8) out[(size_t)(r0 + j) * b + c0 + tx] = s[u][tx][j];   // out(r,c) = in(c,r)
+            }
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void k_transpose_keys(const uint64_t* __restrict__ keys, size_t n, uint64_t* __restrict__ okeys,
                                  uint32_t* __restrict__ idx) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1255,7 +1291,9 @@ void op_transpose(const Matrix& A, Matrix& C) {   // H:3733
     DevBuf<char> t(A.L * A.tile_bytes());
     dispatch(A.dtype, [&](auto z) {
         using T = decltype(z);
-        HB_LAUNCH(k_transpose_tiles<T>, (unsigned)A.L, 256, 0, (const T*)A.tiles.p, idx.p, A.b, (T*)t.p);
+        if (A.b % 32 == 0 && A.b >= 64) HB_LAUNCH((k_transpose_tiles_wide<T, 4>), (unsigned)A.L, 256, 0, (const T*)A.tiles.p, idx.p, A.b, (T*)t.p);
+        else if (A.b == 32) HB_LAUNCH((k_transpose_tiles_wide<T, 1>), (unsigned)A.L, 256, 0, (const T*)A.tiles.p, idx.p, A.b, (T*)t.p);
+        else HB_LAUNCH(k_transpose_tiles<T>, (unsigned)A.L, 256, 0, (const T*)A.tiles.p, idx.p, A.b, (T*)t.p);
     });
     C.set_table(std::move(okeys), std::move(t), A.L);
     sync_stream();
