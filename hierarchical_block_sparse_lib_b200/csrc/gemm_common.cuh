@@ -57,7 +57,9 @@ inline EncodeTiledFn encode_tiled_fn() {
 struct GemmMeta { int ctile; int flags; };   // flags: 1 = first chunk of a C tile, 2 = last chunk, 4 = no more work
 
 // fp32 leaf GEMM on the 5th-generation tensor cores (gemm_f32.cu); false = blocksize/driver not supported
+// ckeys / task_k (C's Morton keys and the k of every product, may be null) let the 32-leaf path pair neighbouring C tiles
 bool launch_gemm_f32_tc(const Matrix& A, bool tA, const Matrix& B, bool tB, const uint2* ab, const uint64_t* begin,
-                        uint32_t n_ctiles, const uint32_t* tile_list, unsigned* counter, float* Ct);
+                        uint32_t n_ctiles, const uint32_t* tile_list, unsigned* counter, float* Ct, const uint64_t* ckeys = nullptr,
+                        const uint32_t* task_k = nullptr, size_t n_products = 0);
 
 }  // namespace hbsm_b200

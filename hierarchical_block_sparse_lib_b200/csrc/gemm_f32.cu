@@ -117,6 +117,12 @@ struct F32Header {
     int acc_tile[8];
     int acc_flags[8];     // 1 = first product of its C tile, 2 = last product, 4 = no more work
     uint32_t tmem_base;
+    // stacked kernel: per-STAGE-SEQUENCE meta written once by the producer and read by every later role (split warps, MMA
+    // issuer, epilogue), so that the issuing lane never stores to shared memory: a store would need a fence before the
+    // tcgen05.commit that publishes it, and a fence in that lane waits for its MMAs in flight -- the tensor pipe then
+    // idles for the whole per-stage hand-off (measured: 135 clk per M=N=64 MMA instead of 47).  The producer leads the
+    // epilogue by at most NST + NSETS * CH <= 11 stages, the ring has 16 entries.
+    GemmMeta ring[16];
 };
 
 // LS = leaf size (H:167 blocksize), BS = the square compute tile one CTA accumulates (BS == LS for leaves up to 128; a
@@ -473,8 +479,8 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     const uint2 tj = Cfg::GP > 1 ? mine : make_uint2(__shfl_sync(0xffffffffu, mine.x, j0), __shfl_sync(0xffffffffu, mine.y, j0));
                     if (lane == 0) {
                         HB_PWAIT(t_wait, mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u));
-                        hd->meta[s].ctile = (int)tile;
-                        hd->meta[s].flags = (pb + j0 == p0 ? 1 : 0) | (pb + j0 + n == p1 ? 2 : 0) | (n << 8);
+                        hd->ring[it & 15u].ctile = (int)tile;
+                        hd->ring[it & 15u].flags = (pb + j0 == p0 ? 1 : 0) | (pb + j0 + n == p1 ? 2 : 0) | (n << 8);
                         if (dbg & 64) mbar_arrive(fb);
                         else mbar_arrive_expect_tx(fb, (uint32_t)n * 2u * Cfg::OPER_BYTES);
                     }
@@ -509,8 +515,8 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             for (int e = 0; e < Cfg::CVT_GROUPS; ++e, ++it) {
                 const uint32_t s = it % NST, ph = (it / NST) & 1u;
                 mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
-                hd->meta[s].ctile = -1;
-                hd->meta[s].flags = 4;
+                hd->ring[it & 15u].ctile = -1;
+                hd->ring[it & 15u].flags = 4;
                 mbar_arrive(smem_u32(&hd->full_raw[s]));
             }
         }
@@ -525,18 +531,16 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             // (Interleaving the K-steps of consecutive products over their accumulator sets was tried and is SLOWER:
             // 100 -> 72 TF/s at 64-leaves, 23.6 -> 20.8 at 32 -- the issuer then waits for whole batches of stages.)
             uint32_t chain = 0;       // accumulator-set uses so far
-            int in_chain = 0, chain_flags = 0;
+            int in_chain = 0;
             for (uint32_t it = 0;; ++it) {
                 const uint32_t s = it % NST, ph = (it / NST) & 1u;
                 HB_PWAIT(t_wait, mbar_wait(smem_u32(&hd->full_cvt[s]), ph));
-                const GemmMeta m = hd->meta[s];
+                const GemmMeta m = hd->ring[it & 15u];
                 const uint32_t as = chain % Cfg::NSETS;
                 if (in_chain == 0) HB_PWAIT(t_wait2, mbar_wait(smem_u32(&hd->tmem_empty[as]), ((chain / Cfg::NSETS) & 1u) ^ 1u));   // epilogue drained this set
                 if (m.flags & 4) {   // (a chain never spans C tiles, so none is open here)
                     if (profiling) { prof[3] = (unsigned long long)t_wait; prof[4] = (unsigned long long)t_wait2; prof[5] = (unsigned long long)(clock64() - t_role0); }
-                    hd->acc_flags[as] = 4;
-                    __threadfence_block();
-                    mbar_arrive(smem_u32(&hd->tmem_full[as]));
+                    mbar_arrive(smem_u32(&hd->tmem_full[as]));   // the epilogue finds the terminal entry in the ring itself
                     break;
                 }
                 tc_fence_after();
@@ -556,15 +560,10 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     }
                 }
                 tc_commit(smem_u32(&hd->empty[s]));
-                chain_flags |= m.flags & 3;
-                if ((m.flags & 2) || ++in_chain == Cfg::CH) {   // hand the set to the epilogue
-                    hd->acc_tile[as] = m.ctile;
-                    hd->acc_flags[as] = chain_flags;
-                    __threadfence_block();
+                if ((m.flags & 2) || ++in_chain == Cfg::CH) {   // hand the set to the epilogue (which reads the same ring entries)
                     tc_commit(smem_u32(&hd->tmem_full[as]));
                     ++chain;
                     in_chain = 0;
-                    chain_flags = 0;
                 }
             }
         }
@@ -574,7 +573,7 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         for (uint32_t it = (warp - 2) / Cfg::CVT_WPG;; it += Cfg::CVT_GROUPS) {
             const uint32_t s = it % NST, ph = (it / NST) & 1u;
             HB_PWAIT(t_wait, mbar_wait(smem_u32(&hd->full_raw[s]), ph));
-            const int flags = hd->meta[s].flags;
+            const int flags = hd->ring[it & 15u].flags;
             if (profiling && (flags & 4) && warp == 2 && lane == 0) { prof[6] = (unsigned long long)t_wait; prof[7] = (unsigned long long)(clock64() - t_role0); }
             if (!(flags & 4) && !(dbg & 4))
             for (int pj = 0; pj < (Cfg::GP == 1 ? 1 : (flags >> 8)); ++pj) {
@@ -615,15 +614,26 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         const int crow = BS == 64 ? (int)((q & 1) * 32 + lane) : (lane < 16 ? (int)((q & 1) * 16 + lane) : BS);
         float* my_stg = stg + (size_t)(((q & 1) * Cfg::EPI_H + h) * 32 * 32);
         float acc[32];
+        uint32_t it_e = 0;            // stage sequence number of the next ring entry this warp consumes
         for (uint32_t pc = 0;; ++pc) {
             const uint32_t as = pc % Cfg::NSETS;
             HB_PWAIT(t_wait, mbar_wait(smem_u32(&hd->tmem_full[as]), (pc / Cfg::NSETS) & 1u));
-            const int flags = hd->acc_flags[as];
+            // the accumulator set holds the stages [it_e, ...) of one chain: up to CH stages, closed early by the end of the C tile
+            GemmMeta m = hd->ring[it_e & 15u];
+            int flags = m.flags & 7;
             if (flags & 4) {
                 if (profiling && warp == 8 && lane == 0) { prof[8] = (unsigned long long)t_wait; prof[9] = (unsigned long long)(clock64() - t_role0); prof[10] = pc; }
                 break;
             }
-            const int ctile = hd->acc_tile[as];
+            ++it_e;
+#pragma unroll
+            for (int c = 1; c < Cfg::CH; ++c) {
+                if (flags & 2) break;
+                m = hd->ring[it_e & 15u];
+                flags |= m.flags & 3;
+                ++it_e;
+            }
+            const int ctile = m.ctile;
             tc_fence_after();
             uint32_t r1[32], r2[32];
             if (!(dbg & 8)) {
@@ -669,7 +679,8 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 // development switches (HBSM_F32_MODE): bit 0 = leave the raw operand in place as "hi", bit 1 = issue M = 64 MMAs for leaves <= 64;
 // timing experiments with WRONG results: 4 = skip the hi/lo split, 8 = skip the TMEM drain, 16 = skip the MMAs, 64 = skip the
 // TMA loads (stacked kernel only);
-// 32 = use the three-MMA kernel for leaves of 32 / 64 as well (instead of the stacked-operand kernel)
+// 32 = use the three-MMA kernel for leaves of 32 / 64 as well (instead of the stacked-operand kernel); 128 = 32-leaves: the
+// unpaired stacked kernel instead of the paired one
 int f32_mode() {
     static int mode = -1;
     if (mode < 0) { const char* e = getenv("HBSM_F32_MODE"); mode = e ? atoi(e) : 1; }   // default: raw operand as "hi"
@@ -687,6 +698,351 @@ bool make_f32_map(CUtensorMap* map, const void* tiles, size_t n_tiles, int LS, i
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(tiles), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// 32-leaves, paired: two C tiles per MMA.
+//
+// Measured (tools/mma_probe.cu, profiles/r02_mma_probe.json): a kind::tf32 MMA with fresh operands costs ~66-76 clk
+// whatever its shape up to M = 128, N = 128, so the M = N = 64 MMA of the stacked kernel above wastes most of the
+// instruction.  The C tiles (ci, cj) and (ci+1, cj), ci even, are NEIGHBOURS in C's Morton-ordered table (keys k and
+// k+1: the lowest key bit is the row bit, H:52-56) and every product of either reads the same op(B) tile B(k, cj).
+// A group = such a pair (or a single tile without its partner); its k-list is the union of the two k-lists, and one
+// "super-product" per k is the M = 128, N = 64 MMA
+//        [A1_hi ; A1_lo ; A2_hi ; A2_lo] (128 x 32)  x  [B_hi | B_lo] (32 x 64)
+// whose TMEM lane quadrants 0..3 hold  C1 (hi rows), C1 (lo rows), C2 (hi rows), C2 (lo rows).  A member without a
+// product at this k gets a ZERO tile (its own tensor map over one zero leaf): the extra term is an exact +0, so the
+// executed-product set and every partial sum are those of the unpaired kernel.  The groups and their merged lists
+// are built on the device from the task list (three small kernels, no host round trip).
+// ---------------------------------------------------------------------------------------------------
+struct P32Cfg {
+    static constexpr int BS = 32;
+    static constexpr int SLAB = 32 * 128;                    // one 32 x 32 fp32 slab, either major
+    static constexpr int SP_BYTES = 6 * SLAB;                // A: hi1 lo1 hi2 lo2 | B: hi lo
+    static constexpr int GP = 2;                             // super-products per pipeline stage (= chained into one accumulator set)
+    static constexpr int STAGE_BYTES = GP * SP_BYTES;        // 48 KiB
+    static constexpr int NST = 4;
+    static constexpr int MM = 128, NN = 64;
+    static constexpr int NSETS = 512 / NN;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int THREADS = 512;
+    static constexpr int CVT_WARPS = 6, CVT_GROUPS = 3, CVT_WPG = 2;   // groups <= stages (parity aliasing, see Q4Cfg)
+    static constexpr int EPI_WARPS = 4;
+    static constexpr int KSTEPS = 4;
+    static constexpr int STG_BYTES = 2 * 32 * 32 * 4;        // lo-row partial tiles of the two members
+    static constexpr int HEADER_BYTES = 1024;
+    static constexpr int SMEM_BYTES = 1024 + HEADER_BYTES + NST * STAGE_BYTES + STG_BYTES;
+};
+struct PairMeta { int t1, t2, flags, pad; };                 // flags: 1 first stage of the group, 2 last, 4 end; n << 8
+struct P32Header {
+    uint64_t full_raw[8], full_cvt[8], empty[8], tmem_full[8], tmem_empty[8];
+    uint32_t tmem_base;
+    uint32_t pad_[3];
+    PairMeta ring[16];
+};
+static_assert(sizeof(P32Header) <= P32Cfg::HEADER_BYTES, "header");
+
+constexpr uint32_t P32_NONE = 0xFFFFFFFFu;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(P32Cfg::THREADS, 1)
+k_gemm_f32_p32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapZ,
+               const uint4* __restrict__ gops /* {A1 tile, A2 tile, B tile, -} per super-product; P32_NONE = zero tile */,
+               const uint64_t* __restrict__ gbegin, const uint2* __restrict__ gtiles /* {C tile 1, C tile 2 or NONE} */,
+               const uint64_t* __restrict__ n_groups_dev, unsigned* __restrict__ next_group, float* __restrict__ Ct) {
+    using Cfg = P32Cfg;
+    constexpr int NST = Cfg::NST, BS = Cfg::BS;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    P32Header* hd = reinterpret_cast<P32Header*>(smem);
+    unsigned char* stages = smem + Cfg::HEADER_BYTES;
+    float* stg = reinterpret_cast<float*>(stages + (size_t)NST * Cfg::STAGE_BYTES);
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned n_groups = (unsigned)*n_groups_dev;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(smem_u32(&hd->full_raw[s]), 1);
+            mbar_init(smem_u32(&hd->full_cvt[s]), Cfg::CVT_WPG);
+            mbar_init(smem_u32(&hd->empty[s]), 1);
+        }
+        for (int a = 0; a < Cfg::NSETS; ++a) {
+            mbar_init(smem_u32(&hd->tmem_full[a]), 1);
+            mbar_init(smem_u32(&hd->tmem_empty[a]), Cfg::EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&hd->tmem_base), Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = hd->tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer: the warp walks the group list together, lanes issue one super-product's three copies each =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapZ) : "memory");
+        }
+        uint32_t it = 0;
+        unsigned claimed = 0;
+        if (lane == 0) claimed = atomicAdd(next_group, 1u);
+        for (;;) {
+            const unsigned g = __shfl_sync(0xffffffffu, claimed, 0);
+            if (g >= n_groups) break;
+            if (lane == 0) claimed = atomicAdd(next_group, 1u);
+            const uint64_t bnd = gbegin[g + (lane & 1u)];
+            const uint64_t p0 = __shfl_sync(0xffffffffu, bnd, 0), p1 = __shfl_sync(0xffffffffu, bnd, 1);
+            const uint2 ct = gtiles[g];
+            for (uint64_t pb = p0; pb < p1; pb += 32) {
+                const uint4 mine = (pb + lane < p1) ? gops[pb + lane] : make_uint4(0u, 0u, 0u, 0u);
+                const int cnt = (int)((p1 - pb) < 32 ? (p1 - pb) : 32);
+                for (int j0 = 0; j0 < cnt; j0 += Cfg::GP, ++it) {
+                    const int n = cnt - j0 < Cfg::GP ? cnt - j0 : Cfg::GP;
+                    const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                    const uint32_t fb = smem_u32(&hd->full_raw[s]);
+                    if (lane == 0) {
+                        mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
+                        PairMeta pm;
+                        pm.t1 = (int)ct.x; pm.t2 = (int)ct.y;
+                        pm.flags = (pb + j0 == p0 ? 1 : 0) | (pb + j0 + n == p1 ? 2 : 0) | (n << 8);
+                        pm.pad = 0;
+                        hd->ring[it & 15u] = pm;
+                        mbar_arrive_expect_tx(fb, (uint32_t)n * 3u * Cfg::SLAB);
+                    }
+                    __syncwarp();
+                    const int l = (int)lane - j0;
+                    if (l >= 0 && l < n) {
+                        const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES + (size_t)l * Cfg::SP_BYTES);
+                        // raw tiles land in the "hi" slabs 0, 2 (A) and 4 (B); for BS = 32 both majors are one 32 x 32 box
+                        if (mine.x != P32_NONE) tma_box_g2s(sa, &mapA, 0, (int)mine.x * BS, fb);
+                        else tma_box_g2s(sa, &mapZ, 0, 0, fb);
+                        if (mine.y != P32_NONE) tma_box_g2s(sa + 2 * Cfg::SLAB, &mapA, 0, (int)mine.y * BS, fb);
+                        else tma_box_g2s(sa + 2 * Cfg::SLAB, &mapZ, 0, 0, fb);
+                        tma_box_g2s(sa + 4 * Cfg::SLAB, &mapB, 0, (int)mine.z * BS, fb);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        if (lane == 0) {   // one terminal stage per split group
+            for (int e = 0; e < Cfg::CVT_GROUPS; ++e, ++it) {
+                const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
+                PairMeta pm;
+                pm.t1 = -1; pm.t2 = -1; pm.flags = 4; pm.pad = 0;
+                hd->ring[it & 15u] = pm;
+                mbar_arrive(smem_u32(&hd->full_raw[s]));
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one M = 128, N = 64 MMA per K-step of a super-product; this lane never stores to shared memory =====
+        if (lane == 0) {
+            constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TA ? 0u : 1u) << 15) | ((TB ? 1u : 0u) << 16) |
+                                       ((uint32_t)(Cfg::NN >> 3) << 17) | ((uint32_t)(Cfg::MM >> 4) << 24);
+            constexpr uint32_t A_LBO = TA ? 16 : Cfg::SLAB, B_LBO = TB ? Cfg::SLAB : 16;
+            constexpr uint32_t A_SBO = TA ? 1024 : 512, B_SBO = TB ? 512 : 1024;
+            constexpr uint32_t A_LT = TA ? 2 : 1, B_LT = TB ? 1 : 2;
+            for (uint32_t it = 0;; ++it) {
+                const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                mbar_wait(smem_u32(&hd->full_cvt[s]), ph);
+                const int flags = hd->ring[it & 15u].flags;
+                const uint32_t as = it % Cfg::NSETS;
+                mbar_wait(smem_u32(&hd->tmem_empty[as]), ((it / Cfg::NSETS) & 1u) ^ 1u);
+                if (flags & 4) {
+                    mbar_arrive(smem_u32(&hd->tmem_full[as]));
+                    break;
+                }
+                tc_fence_after();
+                const uint32_t d = tmem_base + as * Cfg::NN;
+                const int n = flags >> 8;
+                const uint32_t s0 = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
+                const uint64_t da0 = umma_desc(s0, A_LBO, A_SBO, A_LT), db0 = umma_desc(s0 + 4 * Cfg::SLAB, B_LBO, B_SBO, B_LT);
+                for (int j = 0; j < n; ++j) {
+#pragma unroll
+                    for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+                        const uint32_t ao = TA ? (uint32_t)(ks * 32) : (uint32_t)(ks * 1024);
+                        const uint32_t bo = TB ? (uint32_t)(ks * 1024) : (uint32_t)(ks * 32);
+                        mma_tf32(d, da0 + (uint64_t)((j * Cfg::SP_BYTES + ao) >> 4), db0 + (uint64_t)((j * Cfg::SP_BYTES + bo) >> 4), IDESC,
+                                 (ks || j) ? 1u : 0u);
+                    }
+                }
+                tc_commit(smem_u32(&hd->empty[s]));
+                tc_commit(smem_u32(&hd->tmem_full[as]));
+            }
+        }
+    } else if (warp >= 2 && warp < 2 + Cfg::CVT_WARPS) {
+        // ===== lo = x - trunc_tf32(x): slabs 1, 3, 5 of every super-product from the raw slabs 0, 2, 4 =====
+        const unsigned tid = ((warp - 2) % Cfg::CVT_WPG) * 32 + lane;
+        for (uint32_t it = (warp - 2) / Cfg::CVT_WPG;; it += Cfg::CVT_GROUPS) {
+            const uint32_t s = it % NST, ph = (it / NST) & 1u;
+            mbar_wait(smem_u32(&hd->full_raw[s]), ph);
+            const int flags = hd->ring[it & 15u].flags;
+            if (!(flags & 4)) {
+                for (int pj = 0; pj < (flags >> 8); ++pj) {
+                    unsigned char* st = stages + (size_t)s * Cfg::STAGE_BYTES + (size_t)pj * Cfg::SP_BYTES;
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const float4* hi = reinterpret_cast<const float4*>(st + r * 2 * Cfg::SLAB);
+                        float4* lo = reinterpret_cast<float4*>(st + r * 2 * Cfg::SLAB + Cfg::SLAB);
+#pragma unroll 4
+                        for (int i = (int)tid; i < Cfg::SLAB / 16; i += Cfg::CVT_WPG * 32) {
+                            const float4 x = hi[i];
+                            float4 l;
+                            l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                            l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                            l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                            l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                            lo[i] = l;
+                        }
+                    }
+                }
+                fence_proxy_async();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&hd->full_cvt[s]));
+            if (flags & 4) break;
+        }
+    } else if (warp >= 8 && (warp - 8) < Cfg::EPI_WARPS) {
+        // ===== epilogue: warp q owns TMEM lane quadrant q: member q >> 1, hi rows (q even) or lo rows (q odd); row = lane =====
+        const unsigned q = warp - 8;
+        const bool lo_rows = (q & 1u) != 0;
+        float* my_stg = stg + (size_t)((q >> 1) * 32 * 32);
+        float acc[32];
+        for (uint32_t pc = 0;; ++pc) {
+            const uint32_t as = pc % Cfg::NSETS;
+            mbar_wait(smem_u32(&hd->tmem_full[as]), (pc / Cfg::NSETS) & 1u);
+            const PairMeta m = hd->ring[pc & 15u];
+            if (m.flags & 4) break;
+            tc_fence_after();
+            uint32_t r1[32], r2[32];
+            tmem_ld32(tmem_base + ((q * 32u) << 16) + as * Cfg::NN + BS, r2);   // x * B_lo
+            tmem_ld32(tmem_base + ((q * 32u) << 16) + as * Cfg::NN, r1);        // x * B_hi
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&hd->tmem_empty[as]));
+            if (m.flags & 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = __fadd_rn(__uint_as_float(r2[j]), __uint_as_float(r1[j]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = __fadd_rn(__fadd_rn(acc[j], __uint_as_float(r2[j])), __uint_as_float(r1[j]));
+            }
+            if (m.flags & 2) {   // the group's k-list is done: lo-row partial sums -> hi-row warps -> global
+                if (lo_rows) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) my_stg[j * 32 + lane] = acc[j];
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(Cfg::EPI_WARPS * 32) : "memory");
+                const int ctile = (q >> 1) ? m.t2 : m.t1;
+                if (!lo_rows && ctile >= 0) {
+                    float* C = Ct + (size_t)ctile * BS * BS + lane;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) C[(size_t)j * BS] = __fadd_rn(acc[j], my_stg[j * 32 + lane]);
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(Cfg::EPI_WARPS * 32) : "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---- groups and merged k-lists, built from the task list on the device ----
+// head[t] = 1 unless tile t is the lower member (odd key) of a pair whose upper member exists right before it
+__global__ void k_p32_heads(const uint64_t* __restrict__ ckeys, uint32_t n, uint32_t* __restrict__ head) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint64_t key = ckeys[t];
+    head[t] = ((key & 1ull) && t > 0 && ckeys[t - 1] == key - 1ull) ? 0u : 1u;
+}
+// two sorted k-lists -> their union, one thread per group (a few dozen entries): count pass and fill pass
+template <bool FILL>
+__global__ void k_p32_merge(const uint64_t* __restrict__ ckeys, uint32_t n, const uint32_t* __restrict__ head, const uint64_t* __restrict__ gpos,
+                            const uint64_t* __restrict__ begin, const uint2* __restrict__ ab, const uint32_t* __restrict__ task_k,
+                            uint32_t* __restrict__ cnt, const uint64_t* __restrict__ gbegin, uint2* __restrict__ gtiles, uint4* __restrict__ gops) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n || !head[t]) return;
+    const uint64_t key = ckeys[t];
+    const bool paired = !(key & 1ull) && t + 1 < n && ckeys[t + 1] == key + 1ull;
+    const uint64_t g = gpos[t];
+    uint64_t i = begin[t], ie = begin[t + 1];
+    uint64_t j = paired ? begin[t + 1] : 0, je = paired ? begin[t + 2] : 0;
+    uint64_t out = FILL ? gbegin[g] : 0;
+    uint32_t c = 0;
+    while (i < ie || j < je) {
+        const uint32_t ki = i < ie ? task_k[i] : 0xFFFFFFFFu, kj = j < je ? task_k[j] : 0xFFFFFFFFu;
+        if (FILL) {
+            uint4 o;
+            o.x = ki <= kj ? ab[i].x : P32_NONE;
+            o.y = kj <= ki ? ab[j].x : P32_NONE;
+            o.z = ki <= kj ? ab[i].y : ab[j].y;       // the same op(B) tile for both members
+            o.w = 0u;
+            gops[out++] = o;
+        }
+        ++c;
+        if (ki <= kj) ++i;
+        if (kj <= ki) ++j;
+    }
+    if (!FILL) cnt[g] = c;
+    else gtiles[g] = make_uint2(t, paired ? t + 1 : P32_NONE);
+}
+
+const float* zero_leaf_f32() {   // one zero leaf (32 x 32 fp32) for the members of a pair that have no product at some k
+    static float* z = nullptr;
+    if (!z) {
+        HB_CUDA(cudaMalloc((void**)&z, 32 * 32 * sizeof(float)));
+        HB_CUDA(cudaMemset(z, 0, 32 * 32 * sizeof(float)));
+    }
+    return z;
+}
+
+template <bool TA, bool TB>
+bool launch_p32_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, const uint64_t* ckeys, const uint32_t* task_k,
+                     uint32_t n_ctiles, size_t n_products, float* Ct) {
+    using Cfg = P32Cfg;
+    CUtensorMap mapA, mapB, mapZ;
+    if (!make_f32_map(&mapA, A.tiles.p, A.L, 32, 32, 32, !TA)) return false;
+    if (!make_f32_map(&mapB, B.tiles.p, B.n_ext(), 32, 32, 32, TB)) return false;
+    if (!make_f32_map(&mapZ, zero_leaf_f32(), 1, 32, 32, 32, !TA)) return false;
+    // groups
+    DevBuf<uint32_t> head(n_ctiles), cnt(n_ctiles);
+    DevBuf<uint64_t> gpos((size_t)n_ctiles + 1), gbegin((size_t)n_ctiles + 1);
+    DevBuf<uint2> gtiles(n_ctiles);
+    DevBuf<uint4> gops(std::max<size_t>(n_products, 1));
+    cnt.zero();
+    const unsigned gb = (n_ctiles + 255) / 256;
+    HB_LAUNCH(k_p32_heads, gb, 256, 0, ckeys, n_ctiles, head.p);
+    exclusive_scan_u32(head.p, gpos.p, n_ctiles);
+    HB_LAUNCH((k_p32_merge<false>), gb, 256, 0, ckeys, n_ctiles, head.p, gpos.p, begin, ab, task_k, cnt.p, (const uint64_t*)nullptr,
+              (uint2*)nullptr, (uint4*)nullptr);
+    exclusive_scan_u32(cnt.p, gbegin.p, n_ctiles);          // (entries past the last group are zero)
+    HB_LAUNCH((k_p32_merge<true>), gb, 256, 0, ckeys, n_ctiles, head.p, gpos.p, begin, ab, task_k, (uint32_t*)nullptr, gbegin.p, gtiles.p,
+              gops.p);
+    DevBuf<unsigned> counter(1);
+    counter.zero();
+    auto kfn = k_gemm_f32_p32<TA, TB>;
+    static bool configured = false;
+    if (!configured) {
+        HB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const unsigned grid = std::min<unsigned>(n_ctiles, (unsigned)engine().sm_count);
+    HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, mapZ, gops.p, gbegin.p, gtiles.p, gpos.p + n_ctiles, counter.p, Ct);
+    return true;   // (the scratch arrays are released in stream order)
+}
+
+bool launch_p32(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, const uint64_t* ckeys,
+                const uint32_t* task_k, uint32_t n, size_t n_products, float* Ct) {
+    if (!tA && !tB) return launch_p32_inst<false, false>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
+    if (!tA && tB) return launch_p32_inst<false, true>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
+    if (tA && !tB) return launch_p32_inst<true, false>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
+    return launch_p32_inst<true, true>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
 }
 
 template <int LS, int BS, int MM, bool TA, bool TB>
@@ -759,7 +1115,11 @@ bool launch_q4(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* 
 }  // namespace
 
 bool launch_gemm_f32_tc(const Matrix& A, bool tA, const Matrix& B, bool tB, const uint2* ab, const uint64_t* begin,
-                        uint32_t n_ctiles, const uint32_t* tile_list, unsigned* counter, float* Ct) {
+                        uint32_t n_ctiles, const uint32_t* tile_list, unsigned* counter, float* Ct, const uint64_t* ckeys,
+                        const uint32_t* task_k, size_t n_products) {
+    // 32-leaves over the whole task list: vertical C-tile pairs, M = 128 MMAs (HBSM_F32_MODE bit 128 keeps the unpaired kernel)
+    if (A.b == 32 && !tile_list && ckeys && task_k && !(f32_mode() & (32 | 128)))
+        return launch_p32(tA, tB, A, B, ab, begin, ckeys, task_k, n_ctiles, n_products, Ct);
     if (!(f32_mode() & 32)) {   // leaves of 32 / 64: stacked hi/lo operands, one MMA per K-step
         if (A.b == 32) return launch_q4<32>(tA, tB, A, B, ab, begin, n_ctiles, tile_list, counter, Ct);
         if (A.b == 64) return launch_q4<64>(tA, tB, A, B, ab, begin, n_ctiles, tile_list, counter, Ct);

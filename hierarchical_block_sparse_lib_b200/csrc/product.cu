@@ -775,7 +775,8 @@ void launch_leaf_gemm(const Matrix& A, bool tA, const Matrix& B, bool tB, const 
     if (A.dtype == HBSM_F32 && variant != 1) {   // fp32: split-TF32 on tcgen05 (gemm_f32.cu) for b in {32,64,128,256}
         DevBuf<unsigned> counter(1);
         counter.zero();
-        done = launch_gemm_f32_tc(A, tA, B, tB, tl.ab.p, tl.begin.p, nn, tile_list, counter.p, (float*)ct);
+        done = launch_gemm_f32_tc(A, tA, B, tB, tl.ab.p, tl.begin.p, nn, tile_list, counter.p, (float*)ct, tl.ckeys.p, tl.task_k.p,
+                                  tl.n_products);
         if (done) e.last_gemm_kernel = 3;
     }
     if (!done) {
