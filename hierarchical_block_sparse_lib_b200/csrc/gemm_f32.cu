@@ -716,18 +716,19 @@ bool make_f32_map(CUtensorMap* map, const void* tiles, size_t n_tiles, int LS, i
 // executed-product set and every partial sum are those of the unpaired kernel.  The groups and their merged lists
 // are built on the device from the task list (three small kernels, no host round trip).
 // ---------------------------------------------------------------------------------------------------
-struct P32Cfg {
+template <int GP_>
+struct P32CfgT {
     static constexpr int BS = 32;
     static constexpr int SLAB = 32 * 128;                    // one 32 x 32 fp32 slab, either major
     static constexpr int SP_BYTES = 6 * SLAB;                // A: hi1 lo1 hi2 lo2 | B: hi lo
-    static constexpr int GP = 2;                             // super-products per pipeline stage (= chained into one accumulator set)
-    static constexpr int STAGE_BYTES = GP * SP_BYTES;        // 48 KiB
-    static constexpr int NST = 4;
+    static constexpr int GP = GP_;                           // super-products per pipeline stage (= chained into one accumulator set)
+    static constexpr int STAGE_BYTES = GP * SP_BYTES;        // 24 KiB per super-product
+    static constexpr int NST = 8 / GP;                       // 192 KiB of operand stages
     static constexpr int MM = 128, NN = 64;
     static constexpr int NSETS = 512 / NN;
     static constexpr int TMEM_COLS = 512;
     static constexpr int THREADS = 512;
-    static constexpr int CVT_WARPS = 6, CVT_GROUPS = 3, CVT_WPG = 2;   // groups <= stages (parity aliasing, see Q4Cfg)
+    static constexpr int CVT_WARPS = 6, CVT_GROUPS = NST >= 6 ? 6 : (NST >= 3 ? 3 : 2), CVT_WPG = CVT_WARPS / CVT_GROUPS;   // groups <= stages (parity aliasing, see Q4Cfg)
     static constexpr int EPI_WARPS = 4;
     static constexpr int KSTEPS = 4;
     static constexpr int STG_BYTES = 2 * 32 * 32 * 4;        // lo-row partial tiles of the two members
@@ -741,17 +742,18 @@ struct P32Header {
     uint32_t pad_[3];
     PairMeta ring[16];
 };
+typedef P32CfgT<2> P32Cfg;
 static_assert(sizeof(P32Header) <= P32Cfg::HEADER_BYTES, "header");
 
 constexpr uint32_t P32_NONE = 0xFFFFFFFFu;
 
-template <bool TA, bool TB>
+template <int GPV, bool TA, bool TB>
 __global__ void __launch_bounds__(P32Cfg::THREADS, 1)
 k_gemm_f32_p32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapZ,
                const uint4* __restrict__ gops /* {A1 tile, A2 tile, B tile, -} per super-product; P32_NONE = zero tile */,
                const uint64_t* __restrict__ gbegin, const uint2* __restrict__ gtiles /* {C tile 1, C tile 2 or NONE} */,
                const uint64_t* __restrict__ n_groups_dev, unsigned* __restrict__ next_group, float* __restrict__ Ct) {
-    using Cfg = P32Cfg;
+    using Cfg = P32CfgT<GPV>;
     constexpr int NST = Cfg::NST, BS = Cfg::BS;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1002,10 +1004,10 @@ const float* zero_leaf_f32() {   // one zero leaf (32 x 32 fp32) for the members
     return z;
 }
 
-template <bool TA, bool TB>
-bool launch_p32_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, const uint64_t* ckeys, const uint32_t* task_k,
+template <int GPV, bool TA, bool TB>
+bool launch_p32_gp(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, const uint64_t* ckeys, const uint32_t* task_k,
                      uint32_t n_ctiles, size_t n_products, float* Ct) {
-    using Cfg = P32Cfg;
+    using Cfg = P32CfgT<GPV>;
     CUtensorMap mapA, mapB, mapZ;
     if (!make_f32_map(&mapA, A.tiles.p, A.L, 32, 32, 32, !TA)) return false;
     if (!make_f32_map(&mapB, B.tiles.p, B.n_ext(), 32, 32, 32, TB)) return false;
@@ -1026,7 +1028,7 @@ bool launch_p32_inst(const Matrix& A, const Matrix& B, const uint2* ab, const ui
               gops.p);
     DevBuf<unsigned> counter(1);
     counter.zero();
-    auto kfn = k_gemm_f32_p32<TA, TB>;
+    auto kfn = k_gemm_f32_p32<GPV, TA, TB>;
     static bool configured = false;
     if (!configured) {
         HB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -1035,6 +1037,15 @@ bool launch_p32_inst(const Matrix& A, const Matrix& B, const uint2* ab, const ui
     const unsigned grid = std::min<unsigned>(n_ctiles, (unsigned)engine().sm_count);
     HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, mapZ, gops.p, gbegin.p, gtiles.p, gpos.p + n_ctiles, counter.p, Ct);
     return true;   // (the scratch arrays are released in stream order)
+}
+
+template <bool TA, bool TB>
+bool launch_p32_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, const uint64_t* ckeys, const uint32_t* task_k,
+                     uint32_t n_ctiles, size_t n_products, float* Ct) {
+    static const int gp = [] { const char* e = getenv("HBSM_P32_GP"); return e ? atoi(e) : 2; }();   // tuning switch: super-products per stage
+    if (gp == 1) return launch_p32_gp<1, TA, TB>(A, B, ab, begin, ckeys, task_k, n_ctiles, n_products, Ct);
+    if (gp == 4) return launch_p32_gp<4, TA, TB>(A, B, ab, begin, ckeys, task_k, n_ctiles, n_products, Ct);
+    return launch_p32_gp<2, TA, TB>(A, B, ab, begin, ckeys, task_k, n_ctiles, n_products, Ct);
 }
 
 bool launch_p32(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, const uint64_t* ckeys,

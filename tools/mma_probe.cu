@@ -163,7 +163,9 @@ int main() {
     run<64, 64, 0, false, 4, 0, false, 128, 6>(sms, sink, dclk, "m64n64_k_rot4_fresh_operands", false);
     run<64, 64, 0, false, 4, 4, true, 512, 6>(sms, sink, dclk, "m64n64_k_rot4_fresh_commit4_polling", false);
     run<64, 128, 0, false, 4, 0, false, 128, 6>(sms, sink, dclk, "m64n128_k_rot4_fresh_operands", false);
-    run<128, 128, 0, false, 8, 0, false, 128, 6>(sms, sink, dclk, "m128n128_k_rot8_fresh_operands", false);
+    run<128, 64, 0, false, 4, 0, false, 128, 6>(sms, sink, dclk, "m128n64_k_rot4_fresh_operands", false);
+    run<128, 128, 0, false, 4, 0, false, 128, 4>(sms, sink, dclk, "m128n128_k_rot4_fresh_operands", false);
+    run<128, 64, 0, false, 4, 2, true, 512, 6>(sms, sink, dclk, "m128n64_k_rot4_fresh_commit2_polling", false);
     printf("}\n");
     return 0;
 }
