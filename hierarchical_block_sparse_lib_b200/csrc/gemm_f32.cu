@@ -680,7 +680,7 @@ k_gemm_f32_q4(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 // timing experiments with WRONG results: 4 = skip the hi/lo split, 8 = skip the TMEM drain, 16 = skip the MMAs, 64 = skip the
 // TMA loads (stacked kernel only);
 // 32 = use the three-MMA kernel for leaves of 32 / 64 as well (instead of the stacked-operand kernel); 128 = 32-leaves: the
-// unpaired stacked kernel instead of the paired one
+// single-tile stacked kernel instead of the grouped one
 int f32_mode() {
     static int mode = -1;
     if (mode < 0) { const char* e = getenv("HBSM_F32_MODE"); mode = e ? atoi(e) : 1; }   // default: raw operand as "hi"
@@ -701,63 +701,73 @@ bool make_f32_map(CUtensorMap* map, const void* tiles, size_t n_tiles, int LS, i
 }
 
 
+constexpr uint32_t P32_NONE = 0xFFFFFFFFu;   // "no tile here": the member / operand reads the zero leaf
+
+const float* zero_leaf_f32() {   // one zero leaf (32 x 32 fp32) for the group members that have no product at some k
+    static float* z = nullptr;
+    if (!z) {
+        HB_CUDA(cudaMalloc((void**)&z, 32 * 32 * sizeof(float)));
+        HB_CUDA(cudaMemset(z, 0, 32 * 32 * sizeof(float)));
+    }
+    return z;
+}
+
 // ---------------------------------------------------------------------------------------------------
-// 32-leaves, paired: two C tiles per MMA.
+// 32-leaves, 2 x 2 groups: four C tiles per MMA.
 //
-// Measured (tools/mma_probe.cu, profiles/r02_mma_probe.json): a kind::tf32 MMA with fresh operands costs ~66-76 clk
-// whatever its shape up to M = 128, N = 128, so the M = N = 64 MMA of the stacked kernel above wastes most of the
-// instruction.  The C tiles (ci, cj) and (ci+1, cj), ci even, are NEIGHBOURS in C's Morton-ordered table (keys k and
-// k+1: the lowest key bit is the row bit, H:52-56) and every product of either reads the same op(B) tile B(k, cj).
-// A group = such a pair (or a single tile without its partner); its k-list is the union of the two k-lists, and one
-// "super-product" per k is the M = 128, N = 64 MMA
-//        [A1_hi ; A1_lo ; A2_hi ; A2_lo] (128 x 32)  x  [B_hi | B_lo] (32 x 64)
-// whose TMEM lane quadrants 0..3 hold  C1 (hi rows), C1 (lo rows), C2 (hi rows), C2 (lo rows).  A member without a
-// product at this k gets a ZERO tile (its own tensor map over one zero leaf): the extra term is an exact +0, so the
-// executed-product set and every partial sum are those of the unpaired kernel.  The groups and their merged lists
-// are built on the device from the task list (three small kernels, no host round trip).
+// The Morton-aligned 2 x 2 block of C tiles (ci0 + r, cj0 + c), r, c in {0, 1}, is up to four CONSECUTIVE entries of C's table
+// (keys 4q + 2c + r).  Per contraction index k its products read A(ci0 + r, k) and B(k, cj0 + c): one M = N = 128 MMA per K-step,
+//        [A0_hi ; A0_lo ; A1_hi ; A1_lo] (128 x 32)  x  [B0_hi | B0_lo | B1_hi | B1_lo] (32 x 128),
+// computes all four.  Measured (tools/mma_probe.cu, profiles/r02_mma_probe.json): a kind::tf32 MMA with fresh operands costs
+// ~66 clk whatever its shape up to M = N = 128, so this is the shape at which it runs at the full tensor rate (the M = N = 64
+// MMA of the single-tile kernel uses a quarter of it), and a leaf product moves 20 KiB through shared memory instead of 40
+// (single tiles) -- small leaves are shared-memory-bound (profiles/r02_f32_small_leaves.md).  Vertical pairs only (M = 128,
+// N = 64, 30 KiB per product) were measured on the way: 51 TF/s, against 35 (single tiles) and 74 (this kernel).
+// Exactness: a group-k whose EXECUTED combinations W form a rectangle R x S is one super-product with the operands of the
+// rows not in R / columns not in S replaced by the zero tile (exact +0 for those members); any other W (three of four, or a
+// diagonal pair -- SpAMM prunes per leaf pair) is issued as two super-products, one per row, each a rectangle.  So every member
+// accumulates exactly its own k-list, in k order, plus exact zeros: the executed-product set and the partial sums are those of
+// the single-tile kernel.  TMEM lane quadrant q = 2r + (0 hi rows | 1 lo rows); accumulator columns [64c, 64c + 32) = x * Bc_hi,
+// [64c + 32, 64c + 64) = x * Bc_lo.
 // ---------------------------------------------------------------------------------------------------
-template <int GP_>
-struct P32CfgT {
+struct G32Cfg {
     static constexpr int BS = 32;
-    static constexpr int SLAB = 32 * 128;                    // one 32 x 32 fp32 slab, either major
-    static constexpr int SP_BYTES = 6 * SLAB;                // A: hi1 lo1 hi2 lo2 | B: hi lo
-    static constexpr int GP = GP_;                           // super-products per pipeline stage (= chained into one accumulator set)
-    static constexpr int STAGE_BYTES = GP * SP_BYTES;        // 24 KiB per super-product
-    static constexpr int NST = 8 / GP;                       // 192 KiB of operand stages
-    static constexpr int MM = 128, NN = 64;
+    static constexpr int SLAB = 32 * 128;
+    static constexpr int SP_BYTES = 8 * SLAB;                // A: hi0 lo0 hi1 lo1 | B: hi0 lo0 hi1 lo1  (32 KiB)
+    static constexpr int GP = 2;                             // super-products per stage = chained into one accumulator set (8 MMAs)
+    static constexpr int STAGE_BYTES = GP * SP_BYTES;        // 64 KiB
+    static constexpr int NST = 3;
+    static constexpr int MM = 128, NN = 128;
     static constexpr int NSETS = 512 / NN;
     static constexpr int TMEM_COLS = 512;
     static constexpr int THREADS = 512;
-    static constexpr int CVT_WARPS = 6, CVT_GROUPS = NST >= 6 ? 6 : (NST >= 3 ? 3 : 2), CVT_WPG = CVT_WARPS / CVT_GROUPS;   // groups <= stages (parity aliasing, see Q4Cfg)
-    static constexpr int EPI_WARPS = 4;
+    static constexpr int CVT_WARPS = 6, CVT_GROUPS = 3, CVT_WPG = 2;
+    static constexpr int EPI_WARPS = 8;
     static constexpr int KSTEPS = 4;
-    static constexpr int STG_BYTES = 2 * 32 * 32 * 4;        // lo-row partial tiles of the two members
+    static constexpr int STG_BYTES = 4 * 32 * 32 * 4;        // lo-row partial tiles of the four members
     static constexpr int HEADER_BYTES = 1024;
     static constexpr int SMEM_BYTES = 1024 + HEADER_BYTES + NST * STAGE_BYTES + STG_BYTES;
 };
-struct PairMeta { int t1, t2, flags, pad; };                 // flags: 1 first stage of the group, 2 last, 4 end; n << 8
-struct P32Header {
+struct G32Header {
     uint64_t full_raw[8], full_cvt[8], empty[8], tmem_full[8], tmem_empty[8];
     uint32_t tmem_base;
     uint32_t pad_[3];
-    PairMeta ring[16];
+    int4 ring_tiles[16];                                     // C tile of member m = 2c + r, or -1
+    int ring_flags[16];                                      // 1 first stage of the group, 2 last, 4 end; n << 8
 };
-typedef P32CfgT<2> P32Cfg;
-static_assert(sizeof(P32Header) <= P32Cfg::HEADER_BYTES, "header");
+static_assert(sizeof(G32Header) <= G32Cfg::HEADER_BYTES, "header");
 
-constexpr uint32_t P32_NONE = 0xFFFFFFFFu;
-
-template <int GPV, bool TA, bool TB>
-__global__ void __launch_bounds__(P32Cfg::THREADS, 1)
-k_gemm_f32_p32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapZ,
-               const uint4* __restrict__ gops /* {A1 tile, A2 tile, B tile, -} per super-product; P32_NONE = zero tile */,
-               const uint64_t* __restrict__ gbegin, const uint2* __restrict__ gtiles /* {C tile 1, C tile 2 or NONE} */,
-               const uint64_t* __restrict__ n_groups_dev, unsigned* __restrict__ next_group, float* __restrict__ Ct) {
-    using Cfg = P32CfgT<GPV>;
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(G32Cfg::THREADS, 1)
+k_gemm_f32_g32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapZ,
+               const uint4* __restrict__ gops /* {A row 0, A row 1, B col 0, B col 1} tiles per super-product; P32_NONE = zero tile */,
+               const uint64_t* __restrict__ gbegin, const int4* __restrict__ gtiles, const uint64_t* __restrict__ n_groups_dev,
+               unsigned* __restrict__ next_group, float* __restrict__ Ct) {
+    using Cfg = G32Cfg;
     constexpr int NST = Cfg::NST, BS = Cfg::BS;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    P32Header* hd = reinterpret_cast<P32Header*>(smem);
+    G32Header* hd = reinterpret_cast<G32Header*>(smem);
     unsigned char* stages = smem + Cfg::HEADER_BYTES;
     float* stg = reinterpret_cast<float*>(stages + (size_t)NST * Cfg::STAGE_BYTES);
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -782,7 +792,7 @@ k_gemm_f32_p32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t tmem_base = hd->tmem_base;
 
     if (warp == 0) {
-        // ===== TMA producer: the warp walks the group list together, lanes issue one super-product's three copies each =====
+        // ===== TMA producer =====
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
@@ -797,7 +807,7 @@ k_gemm_f32_p32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (lane == 0) claimed = atomicAdd(next_group, 1u);
             const uint64_t bnd = gbegin[g + (lane & 1u)];
             const uint64_t p0 = __shfl_sync(0xffffffffu, bnd, 0), p1 = __shfl_sync(0xffffffffu, bnd, 1);
-            const uint2 ct = gtiles[g];
+            const int4 ct = gtiles[g];
             for (uint64_t pb = p0; pb < p1; pb += 32) {
                 const uint4 mine = (pb + lane < p1) ? gops[pb + lane] : make_uint4(0u, 0u, 0u, 0u);
                 const int cnt = (int)((p1 - pb) < 32 ? (p1 - pb) : 32);
@@ -807,40 +817,37 @@ k_gemm_f32_p32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const uint32_t fb = smem_u32(&hd->full_raw[s]);
                     if (lane == 0) {
                         mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
-                        PairMeta pm;
-                        pm.t1 = (int)ct.x; pm.t2 = (int)ct.y;
-                        pm.flags = (pb + j0 == p0 ? 1 : 0) | (pb + j0 + n == p1 ? 2 : 0) | (n << 8);
-                        pm.pad = 0;
-                        hd->ring[it & 15u] = pm;
-                        mbar_arrive_expect_tx(fb, (uint32_t)n * 3u * Cfg::SLAB);
+                        hd->ring_tiles[it & 15u] = ct;
+                        hd->ring_flags[it & 15u] = (pb + j0 == p0 ? 1 : 0) | (pb + j0 + n == p1 ? 2 : 0) | (n << 8);
+                        mbar_arrive_expect_tx(fb, (uint32_t)n * 4u * Cfg::SLAB);
                     }
                     __syncwarp();
                     const int l = (int)lane - j0;
-                    if (l >= 0 && l < n) {
+                    if (l >= 0 && l < n) {   // raw tiles land in the "hi" slabs 0, 2 (A rows) and 4, 6 (B columns)
                         const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES + (size_t)l * Cfg::SP_BYTES);
-                        // raw tiles land in the "hi" slabs 0, 2 (A) and 4 (B); for BS = 32 both majors are one 32 x 32 box
                         if (mine.x != P32_NONE) tma_box_g2s(sa, &mapA, 0, (int)mine.x * BS, fb);
                         else tma_box_g2s(sa, &mapZ, 0, 0, fb);
                         if (mine.y != P32_NONE) tma_box_g2s(sa + 2 * Cfg::SLAB, &mapA, 0, (int)mine.y * BS, fb);
                         else tma_box_g2s(sa + 2 * Cfg::SLAB, &mapZ, 0, 0, fb);
-                        tma_box_g2s(sa + 4 * Cfg::SLAB, &mapB, 0, (int)mine.z * BS, fb);
+                        if (mine.z != P32_NONE) tma_box_g2s(sa + 4 * Cfg::SLAB, &mapB, 0, (int)mine.z * BS, fb);
+                        else tma_box_g2s(sa + 4 * Cfg::SLAB, &mapZ, 0, 0, fb);
+                        if (mine.w != P32_NONE) tma_box_g2s(sa + 6 * Cfg::SLAB, &mapB, 0, (int)mine.w * BS, fb);
+                        else tma_box_g2s(sa + 6 * Cfg::SLAB, &mapZ, 0, 0, fb);
                     }
                     __syncwarp();
                 }
             }
         }
-        if (lane == 0) {   // one terminal stage per split group
+        if (lane == 0) {
             for (int e = 0; e < Cfg::CVT_GROUPS; ++e, ++it) {
                 const uint32_t s = it % NST, ph = (it / NST) & 1u;
                 mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
-                PairMeta pm;
-                pm.t1 = -1; pm.t2 = -1; pm.flags = 4; pm.pad = 0;
-                hd->ring[it & 15u] = pm;
+                hd->ring_flags[it & 15u] = 4;
                 mbar_arrive(smem_u32(&hd->full_raw[s]));
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: one M = 128, N = 64 MMA per K-step of a super-product; this lane never stores to shared memory =====
+        // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TA ? 0u : 1u) << 15) | ((TB ? 1u : 0u) << 16) |
                                        ((uint32_t)(Cfg::NN >> 3) << 17) | ((uint32_t)(Cfg::MM >> 4) << 24);
@@ -850,7 +857,7 @@ k_gemm_f32_p32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (uint32_t it = 0;; ++it) {
                 const uint32_t s = it % NST, ph = (it / NST) & 1u;
                 mbar_wait(smem_u32(&hd->full_cvt[s]), ph);
-                const int flags = hd->ring[it & 15u].flags;
+                const int flags = hd->ring_flags[it & 15u];
                 const uint32_t as = it % Cfg::NSETS;
                 mbar_wait(smem_u32(&hd->tmem_empty[as]), ((it / Cfg::NSETS) & 1u) ^ 1u);
                 if (flags & 4) {
@@ -876,17 +883,17 @@ k_gemm_f32_p32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
         }
     } else if (warp >= 2 && warp < 2 + Cfg::CVT_WARPS) {
-        // ===== lo = x - trunc_tf32(x): slabs 1, 3, 5 of every super-product from the raw slabs 0, 2, 4 =====
+        // ===== lo = x - trunc_tf32(x): slabs 1, 3, 5, 7 of every super-product from the raw slabs 0, 2, 4, 6 =====
         const unsigned tid = ((warp - 2) % Cfg::CVT_WPG) * 32 + lane;
         for (uint32_t it = (warp - 2) / Cfg::CVT_WPG;; it += Cfg::CVT_GROUPS) {
             const uint32_t s = it % NST, ph = (it / NST) & 1u;
             mbar_wait(smem_u32(&hd->full_raw[s]), ph);
-            const int flags = hd->ring[it & 15u].flags;
+            const int flags = hd->ring_flags[it & 15u];
             if (!(flags & 4)) {
                 for (int pj = 0; pj < (flags >> 8); ++pj) {
                     unsigned char* st = stages + (size_t)s * Cfg::STAGE_BYTES + (size_t)pj * Cfg::SP_BYTES;
 #pragma unroll
-                    for (int r = 0; r < 3; ++r) {
+                    for (int r = 0; r < 4; ++r) {
                         const float4* hi = reinterpret_cast<const float4*>(st + r * 2 * Cfg::SLAB);
                         float4* lo = reinterpret_cast<float4*>(st + r * 2 * Cfg::SLAB + Cfg::SLAB);
 #pragma unroll 4
@@ -908,38 +915,40 @@ k_gemm_f32_p32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (flags & 4) break;
         }
     } else if (warp >= 8 && (warp - 8) < Cfg::EPI_WARPS) {
-        // ===== epilogue: warp q owns TMEM lane quadrant q: member q >> 1, hi rows (q even) or lo rows (q odd); row = lane =====
-        const unsigned q = warp - 8;
+        // ===== epilogue: warp (q, c): TMEM lane quadrant q (member row r = q >> 1, hi rows if q even else lo rows), member column c =====
+        const unsigned q = (warp - 8) & 3, c = (warp - 8) >> 2;
         const bool lo_rows = (q & 1u) != 0;
-        float* my_stg = stg + (size_t)((q >> 1) * 32 * 32);
+        const unsigned member = 2 * c + (q >> 1);
+        float* my_stg = stg + (size_t)(member * 32 * 32);
         float acc[32];
         for (uint32_t pc = 0;; ++pc) {
             const uint32_t as = pc % Cfg::NSETS;
             mbar_wait(smem_u32(&hd->tmem_full[as]), (pc / Cfg::NSETS) & 1u);
-            const PairMeta m = hd->ring[pc & 15u];
-            if (m.flags & 4) break;
+            const int flags = hd->ring_flags[pc & 15u];
+            if (flags & 4) break;
+            const int4 tiles = hd->ring_tiles[pc & 15u];
             tc_fence_after();
             uint32_t r1[32], r2[32];
-            tmem_ld32(tmem_base + ((q * 32u) << 16) + as * Cfg::NN + BS, r2);   // x * B_lo
-            tmem_ld32(tmem_base + ((q * 32u) << 16) + as * Cfg::NN, r1);        // x * B_hi
+            tmem_ld32(tmem_base + ((q * 32u) << 16) + as * Cfg::NN + c * 64 + BS, r2);   // x * Bc_lo
+            tmem_ld32(tmem_base + ((q * 32u) << 16) + as * Cfg::NN + c * 64, r1);        // x * Bc_hi
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&hd->tmem_empty[as]));
-            if (m.flags & 1) {
+            if (flags & 1) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc[j] = __fadd_rn(__uint_as_float(r2[j]), __uint_as_float(r1[j]));
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc[j] = __fadd_rn(__fadd_rn(acc[j], __uint_as_float(r2[j])), __uint_as_float(r1[j]));
             }
-            if (m.flags & 2) {   // the group's k-list is done: lo-row partial sums -> hi-row warps -> global
+            if (flags & 2) {   // the group's k-list is done: lo-row partial sums -> hi-row warps -> global
                 if (lo_rows) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) my_stg[j * 32 + lane] = acc[j];
                 }
                 asm volatile("bar.sync 1, %0;" ::"r"(Cfg::EPI_WARPS * 32) : "memory");
-                const int ctile = (q >> 1) ? m.t2 : m.t1;
+                const int ctile = member == 0 ? tiles.x : (member == 1 ? tiles.y : (member == 2 ? tiles.z : tiles.w));
                 if (!lo_rows && ctile >= 0) {
                     float* C = Ct + (size_t)ctile * BS * BS + lane;
 #pragma unroll
@@ -955,80 +964,95 @@ k_gemm_f32_p32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-// ---- groups and merged k-lists, built from the task list on the device ----
-// head[t] = 1 unless tile t is the lower member (odd key) of a pair whose upper member exists right before it
-__global__ void k_p32_heads(const uint64_t* __restrict__ ckeys, uint32_t n, uint32_t* __restrict__ head) {
+// ---- 2 x 2 groups and their super-product lists, built from the task list on the device ----
+__global__ void k_g32_heads(const uint64_t* __restrict__ ckeys, uint32_t n, uint32_t* __restrict__ head) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    const uint64_t key = ckeys[t];
-    head[t] = ((key & 1ull) && t > 0 && ckeys[t - 1] == key - 1ull) ? 0u : 1u;
+    head[t] = (t == 0 || (ckeys[t - 1] >> 2) != (ckeys[t] >> 2)) ? 1u : 0u;
 }
-// two sorted k-lists -> their union, one thread per group (a few dozen entries): count pass and fill pass
+// four sorted k-lists -> super-products in k order (one thread per group): count pass and fill pass
 template <bool FILL>
-__global__ void k_p32_merge(const uint64_t* __restrict__ ckeys, uint32_t n, const uint32_t* __restrict__ head, const uint64_t* __restrict__ gpos,
+__global__ void k_g32_merge(const uint64_t* __restrict__ ckeys, uint32_t n, const uint32_t* __restrict__ head, const uint64_t* __restrict__ gpos,
                             const uint64_t* __restrict__ begin, const uint2* __restrict__ ab, const uint32_t* __restrict__ task_k,
-                            uint32_t* __restrict__ cnt, const uint64_t* __restrict__ gbegin, uint2* __restrict__ gtiles, uint4* __restrict__ gops) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n || !head[t]) return;
-    const uint64_t key = ckeys[t];
-    const bool paired = !(key & 1ull) && t + 1 < n && ckeys[t + 1] == key + 1ull;
-    const uint64_t g = gpos[t];
-    uint64_t i = begin[t], ie = begin[t + 1];
-    uint64_t j = paired ? begin[t + 1] : 0, je = paired ? begin[t + 2] : 0;
+                            uint32_t* __restrict__ cnt, const uint64_t* __restrict__ gbegin, int4* __restrict__ gtiles, uint4* __restrict__ gops) {
+    const uint32_t t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t0 >= n || !head[t0]) return;
+    const uint64_t quad = ckeys[t0] >> 2;
+    int tile[4] = {-1, -1, -1, -1};
+    uint64_t p[4] = {0, 0, 0, 0}, pe[4] = {0, 0, 0, 0};
+    for (uint32_t t = t0; t < n && t < t0 + 4 && (ckeys[t] >> 2) == quad; ++t) {
+        const int m = (int)(ckeys[t] & 3ull);   // member 2c + r
+        tile[m] = (int)t;
+        p[m] = begin[t];
+        pe[m] = begin[t + 1];
+    }
+    const uint64_t g = gpos[t0];
     uint64_t out = FILL ? gbegin[g] : 0;
     uint32_t c = 0;
-    while (i < ie || j < je) {
-        const uint32_t ki = i < ie ? task_k[i] : 0xFFFFFFFFu, kj = j < je ? task_k[j] : 0xFFFFFFFFu;
-        if (FILL) {
-            uint4 o;
-            o.x = ki <= kj ? ab[i].x : P32_NONE;
-            o.y = kj <= ki ? ab[j].x : P32_NONE;
-            o.z = ki <= kj ? ab[i].y : ab[j].y;       // the same op(B) tile for both members
-            o.w = 0u;
-            gops[out++] = o;
+    for (;;) {
+        uint32_t kmin = 0xFFFFFFFFu;
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+            if (p[m] < pe[m]) kmin = min(kmin, task_k[p[m]]);
+        if (kmin == 0xFFFFFFFFu) break;
+        bool w[4];
+        uint32_t a[2] = {P32_NONE, P32_NONE}, b[2] = {P32_NONE, P32_NONE};
+        int nw = 0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            w[m] = p[m] < pe[m] && task_k[p[m]] == kmin;
+            if (w[m]) {
+                ++nw;
+                if (FILL) {
+                    const uint2 o = ab[p[m]];
+                    a[m & 1] = o.x;       // row r = m & 1
+                    b[m >> 1] = o.y;      // column c = m >> 1
+                }
+                ++p[m];
+            }
         }
-        ++c;
-        if (ki <= kj) ++i;
-        if (kj <= ki) ++j;
+        const int rows = ((w[0] || w[2]) ? 1 : 0) + ((w[1] || w[3]) ? 1 : 0);
+        const int cols = ((w[0] || w[1]) ? 1 : 0) + ((w[2] || w[3]) ? 1 : 0);
+        if (nw == rows * cols) {   // a rectangle: one super-product
+            if (FILL) gops[out++] = make_uint4(a[0], a[1], b[0], b[1]);
+            ++c;
+        } else {                   // three of four, or a diagonal: one super-product per row
+            if (FILL) {
+                gops[out++] = make_uint4(a[0], P32_NONE, w[0] ? b[0] : P32_NONE, w[2] ? b[1] : P32_NONE);
+                gops[out++] = make_uint4(P32_NONE, a[1], w[1] ? b[0] : P32_NONE, w[3] ? b[1] : P32_NONE);
+            }
+            c += 2;
+        }
     }
     if (!FILL) cnt[g] = c;
-    else gtiles[g] = make_uint2(t, paired ? t + 1 : P32_NONE);
+    else gtiles[g] = make_int4(tile[0], tile[1], tile[2], tile[3]);
 }
 
-const float* zero_leaf_f32() {   // one zero leaf (32 x 32 fp32) for the members of a pair that have no product at some k
-    static float* z = nullptr;
-    if (!z) {
-        HB_CUDA(cudaMalloc((void**)&z, 32 * 32 * sizeof(float)));
-        HB_CUDA(cudaMemset(z, 0, 32 * 32 * sizeof(float)));
-    }
-    return z;
-}
-
-template <int GPV, bool TA, bool TB>
-bool launch_p32_gp(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, const uint64_t* ckeys, const uint32_t* task_k,
+template <bool TA, bool TB>
+bool launch_g32_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, const uint64_t* ckeys, const uint32_t* task_k,
                      uint32_t n_ctiles, size_t n_products, float* Ct) {
-    using Cfg = P32CfgT<GPV>;
+    using Cfg = G32Cfg;
     CUtensorMap mapA, mapB, mapZ;
     if (!make_f32_map(&mapA, A.tiles.p, A.L, 32, 32, 32, !TA)) return false;
     if (!make_f32_map(&mapB, B.tiles.p, B.n_ext(), 32, 32, 32, TB)) return false;
     if (!make_f32_map(&mapZ, zero_leaf_f32(), 1, 32, 32, 32, !TA)) return false;
-    // groups
+    // (one zero map serves both operands: the swizzle mode only permutes where the zeros land)
     DevBuf<uint32_t> head(n_ctiles), cnt(n_ctiles);
     DevBuf<uint64_t> gpos((size_t)n_ctiles + 1), gbegin((size_t)n_ctiles + 1);
-    DevBuf<uint2> gtiles(n_ctiles);
+    DevBuf<int4> gtiles(n_ctiles);
     DevBuf<uint4> gops(std::max<size_t>(n_products, 1));
     cnt.zero();
     const unsigned gb = (n_ctiles + 255) / 256;
-    HB_LAUNCH(k_p32_heads, gb, 256, 0, ckeys, n_ctiles, head.p);
+    HB_LAUNCH(k_g32_heads, gb, 256, 0, ckeys, n_ctiles, head.p);
     exclusive_scan_u32(head.p, gpos.p, n_ctiles);
-    HB_LAUNCH((k_p32_merge<false>), gb, 256, 0, ckeys, n_ctiles, head.p, gpos.p, begin, ab, task_k, cnt.p, (const uint64_t*)nullptr,
-              (uint2*)nullptr, (uint4*)nullptr);
-    exclusive_scan_u32(cnt.p, gbegin.p, n_ctiles);          // (entries past the last group are zero)
-    HB_LAUNCH((k_p32_merge<true>), gb, 256, 0, ckeys, n_ctiles, head.p, gpos.p, begin, ab, task_k, (uint32_t*)nullptr, gbegin.p, gtiles.p,
+    HB_LAUNCH((k_g32_merge<false>), gb, 256, 0, ckeys, n_ctiles, head.p, gpos.p, begin, ab, task_k, cnt.p, (const uint64_t*)nullptr,
+              (int4*)nullptr, (uint4*)nullptr);
+    exclusive_scan_u32(cnt.p, gbegin.p, n_ctiles);
+    HB_LAUNCH((k_g32_merge<true>), gb, 256, 0, ckeys, n_ctiles, head.p, gpos.p, begin, ab, task_k, (uint32_t*)nullptr, gbegin.p, gtiles.p,
               gops.p);
     DevBuf<unsigned> counter(1);
     counter.zero();
-    auto kfn = k_gemm_f32_p32<GPV, TA, TB>;
+    auto kfn = k_gemm_f32_g32<TA, TB>;
     static bool configured = false;
     if (!configured) {
         HB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -1036,24 +1060,15 @@ bool launch_p32_gp(const Matrix& A, const Matrix& B, const uint2* ab, const uint
     }
     const unsigned grid = std::min<unsigned>(n_ctiles, (unsigned)engine().sm_count);
     HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, mapZ, gops.p, gbegin.p, gtiles.p, gpos.p + n_ctiles, counter.p, Ct);
-    return true;   // (the scratch arrays are released in stream order)
+    return true;
 }
 
-template <bool TA, bool TB>
-bool launch_p32_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, const uint64_t* ckeys, const uint32_t* task_k,
-                     uint32_t n_ctiles, size_t n_products, float* Ct) {
-    static const int gp = [] { const char* e = getenv("HBSM_P32_GP"); return e ? atoi(e) : 2; }();   // tuning switch: super-products per stage
-    if (gp == 1) return launch_p32_gp<1, TA, TB>(A, B, ab, begin, ckeys, task_k, n_ctiles, n_products, Ct);
-    if (gp == 4) return launch_p32_gp<4, TA, TB>(A, B, ab, begin, ckeys, task_k, n_ctiles, n_products, Ct);
-    return launch_p32_gp<2, TA, TB>(A, B, ab, begin, ckeys, task_k, n_ctiles, n_products, Ct);
-}
-
-bool launch_p32(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, const uint64_t* ckeys,
+bool launch_g32(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, const uint64_t* ckeys,
                 const uint32_t* task_k, uint32_t n, size_t n_products, float* Ct) {
-    if (!tA && !tB) return launch_p32_inst<false, false>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
-    if (!tA && tB) return launch_p32_inst<false, true>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
-    if (tA && !tB) return launch_p32_inst<true, false>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
-    return launch_p32_inst<true, true>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
+    if (!tA && !tB) return launch_g32_inst<false, false>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
+    if (!tA && tB) return launch_g32_inst<false, true>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
+    if (tA && !tB) return launch_g32_inst<true, false>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
+    return launch_g32_inst<true, true>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
 }
 
 template <int LS, int BS, int MM, bool TA, bool TB>
@@ -1128,9 +1143,9 @@ bool launch_q4(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* 
 bool launch_gemm_f32_tc(const Matrix& A, bool tA, const Matrix& B, bool tB, const uint2* ab, const uint64_t* begin,
                         uint32_t n_ctiles, const uint32_t* tile_list, unsigned* counter, float* Ct, const uint64_t* ckeys,
                         const uint32_t* task_k, size_t n_products) {
-    // 32-leaves over the whole task list: vertical C-tile pairs, M = 128 MMAs (HBSM_F32_MODE bit 128 keeps the unpaired kernel)
+    // 32-leaves over the whole task list: 2 x 2 groups of C tiles, M = N = 128 MMAs (HBSM_F32_MODE bit 128 keeps the single-tile kernel)
     if (A.b == 32 && !tile_list && ckeys && task_k && !(f32_mode() & (32 | 128)))
-        return launch_p32(tA, tB, A, B, ab, begin, ckeys, task_k, n_ctiles, n_products, Ct);
+        return launch_g32(tA, tB, A, B, ab, begin, ckeys, task_k, n_ctiles, n_products, Ct);
     if (!(f32_mode() & 32)) {   // leaves of 32 / 64: stacked hi/lo operands, one MMA per K-step
         if (A.b == 32) return launch_q4<32>(tA, tB, A, B, ab, begin, n_ctiles, tile_list, counter, Ct);
         if (A.b == 64) return launch_q4<64>(tA, tB, A, B, ab, begin, n_ctiles, tile_list, counter, Ct);
