@@ -1071,6 +1071,303 @@ bool launch_g32(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2*
     return launch_g32_inst<true, true>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// 64-leaves, 2 x 2 groups.  Same groups and super-product lists as the 32-leaf kernel above (k_g32_heads / k_g32_merge work on
+// C's table whatever the leaf size), different operand stacking: M = 128 is TWO row tiles, and the hi/lo split is spread over
+// two MMAs per K-step instead of being stacked along M,
+//     D[128 x 256]  = [A0_hi ; A1_hi] x [B0_hi | B1_hi | B0_lo | B1_lo]        (N = 256: hi*hi and hi*lo of all four members)
+//     D[:, 0:128]  += [A0_lo ; A1_lo] x [B0_hi | B1_hi]                        (N = 128: lo*hi into the hi*hi columns)
+// i.e. 194 clk and 20 KiB of operand fetch per K-step for FOUR products (single-tile kernel: 66 clk and 8 KiB for one): 88 KiB
+// through shared memory per leaf product instead of 160.  One pipeline stage = one K-half (32 k) of a super-product = 64 KiB
+// (hi and lo stacks of A and B, 16 KiB each); an accumulator set (256 TMEM columns, two sets) holds one super-product = two
+// stages = 16 MMAs.  There are no "lo rows": every accumulator lane is a C row, so the epilogue is 8 warps of 32 rows x 64
+// columns adding  D[:, hi cols] + D[:, lo cols]  into registers -- no staging, no CTA-level barrier.
+// ---------------------------------------------------------------------------------------------------
+struct G64Cfg {
+    static constexpr int BS = 64, KC = 32;
+    static constexpr int STACK = 128 * KC * 4;               // one stack: two tiles' K-half, 16 KiB
+    static constexpr int STAGE_BYTES = 4 * STACK;            // A_hi | A_lo | B_hi | B_lo
+    static constexpr int NST = 3;
+    static constexpr int NSETS = 2;                          // 256 columns each
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int THREADS = 512;
+    static constexpr int CVT_WARPS = 6, CVT_GROUPS = 3, CVT_WPG = 2;
+    static constexpr int EPI_WARPS = 8;
+    static constexpr int KSTEPS = KC / 8;
+    static constexpr int HEADER_BYTES = 1024;
+    static constexpr int SMEM_BYTES = 1024 + HEADER_BYTES + NST * STAGE_BYTES;
+};
+
+const float* zero_leaf_f32_64() {
+    static float* z = nullptr;
+    if (!z) {
+        HB_CUDA(cudaMalloc((void**)&z, 64 * 64 * sizeof(float)));
+        HB_CUDA(cudaMemset(z, 0, 64 * 64 * sizeof(float)));
+    }
+    return z;
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(G64Cfg::THREADS, 1)
+k_gemm_f32_g64(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapZa,
+               const __grid_constant__ CUtensorMap mapZb, const uint4* __restrict__ gops, const uint64_t* __restrict__ gbegin,
+               const int4* __restrict__ gtiles, const uint64_t* __restrict__ n_groups_dev, unsigned* __restrict__ next_group,
+               float* __restrict__ Ct) {
+    using Cfg = G64Cfg;
+    constexpr int NST = Cfg::NST, BS = Cfg::BS, KC = Cfg::KC;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    G32Header* hd = reinterpret_cast<G32Header*>(smem);
+    unsigned char* stages = smem + Cfg::HEADER_BYTES;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned n_groups = (unsigned)*n_groups_dev;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(smem_u32(&hd->full_raw[s]), 1);
+            mbar_init(smem_u32(&hd->full_cvt[s]), Cfg::CVT_WPG);
+            mbar_init(smem_u32(&hd->empty[s]), 1);
+        }
+        for (int a = 0; a < Cfg::NSETS; ++a) {
+            mbar_init(smem_u32(&hd->tmem_full[a]), 1);
+            mbar_init(smem_u32(&hd->tmem_empty[a]), Cfg::EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&hd->tmem_base), Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = hd->tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer: per super-product two stages (K halves); lanes 0..3 copy one tile's K-half each =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapZa) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapZb) : "memory");
+        }
+        uint32_t it = 0;
+        unsigned claimed = 0;
+        if (lane == 0) claimed = atomicAdd(next_group, 1u);
+        for (;;) {
+            const unsigned g = __shfl_sync(0xffffffffu, claimed, 0);
+            if (g >= n_groups) break;
+            if (lane == 0) claimed = atomicAdd(next_group, 1u);
+            const uint64_t bnd = gbegin[g + (lane & 1u)];
+            const uint64_t p0 = __shfl_sync(0xffffffffu, bnd, 0), p1 = __shfl_sync(0xffffffffu, bnd, 1);
+            const int4 ct = gtiles[g];
+            for (uint64_t pb = p0; pb < p1; pb += 32) {
+                const uint4 mine = (pb + lane < p1) ? gops[pb + lane] : make_uint4(0u, 0u, 0u, 0u);
+                const int cnt = (int)((p1 - pb) < 32 ? (p1 - pb) : 32);
+                for (int j = 0; j < cnt; ++j) {
+                    // this super-product's four tiles: lane l (0..3) takes tile l = {A row 0, A row 1, B col 0, B col 1}
+                    const uint32_t tx = __shfl_sync(0xffffffffu, mine.x, j), ty = __shfl_sync(0xffffffffu, mine.y, j);
+                    const uint32_t tz = __shfl_sync(0xffffffffu, mine.z, j), tw = __shfl_sync(0xffffffffu, mine.w, j);
+                    const uint32_t my_tile = lane == 0 ? tx : (lane == 1 ? ty : (lane == 2 ? tz : tw));
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half, ++it) {
+                        const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                        const uint32_t fb = smem_u32(&hd->full_raw[s]);
+                        if (lane == 0) {
+                            mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
+                            hd->ring_tiles[it & 15u] = ct;
+                            hd->ring_flags[it & 15u] = ((pb + j == p0 && half == 0) ? 1 : 0) | ((pb + j + 1 == p1 && half == 1) ? 2 : 0);
+                            mbar_arrive_expect_tx(fb, 2u * Cfg::STACK);
+                        }
+                        __syncwarp();
+                        if (lane < 4) {
+                            const bool is_a = lane < 2;
+                            const bool kmajor = is_a ? TA : !TB;
+                            const CUtensorMap* map = my_tile != P32_NONE ? (is_a ? &mapA : &mapB) : (is_a ? &mapZa : &mapZb);
+                            const int tcol = my_tile != P32_NONE ? (int)my_tile * BS : 0;
+                            const int k0 = half * KC;
+                            // hi stack of the operand; inside it tile (lane & 1) is rows / chunks [64 (lane & 1), 64 (lane & 1) + 64)
+                            const uint32_t dst = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES) + (is_a ? 0u : 2u * Cfg::STACK);
+                            if (kmajor) {   // [mn][32 k] rows of 128 B: one box {32 k, 64 mn}
+                                tma_box_g2s(dst + (lane & 1u) * (64 * 128), map, k0, tcol, fb);
+                            } else {        // 32-mn chunks of [32 k][32 mn]: two boxes {32 mn, 32 k}
+                                tma_box_g2s(dst + (2 * (lane & 1u) + 0) * (KC * 128), map, 0, tcol + k0, fb);
+                                tma_box_g2s(dst + (2 * (lane & 1u) + 1) * (KC * 128), map, 32, tcol + k0, fb);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        if (lane == 0) {
+            for (int e = 0; e < Cfg::CVT_GROUPS; ++e, ++it) {
+                const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                mbar_wait(smem_u32(&hd->empty[s]), ph ^ 1u);
+                hd->ring_flags[it & 15u] = 4;
+                mbar_arrive(smem_u32(&hd->full_raw[s]));
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: per K-step one N = 256 MMA (hi rows x all of B) and one N = 128 MMA (lo rows x B_hi) =====
+        if (lane == 0) {
+            constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((TA ? 0u : 1u) << 15) | ((TB ? 1u : 0u) << 16) | ((uint32_t)(128 >> 4) << 24);
+            constexpr uint32_t IDESC1 = IDESC_BASE | ((uint32_t)(256 >> 3) << 17), IDESC2 = IDESC_BASE | ((uint32_t)(128 >> 3) << 17);
+            constexpr uint32_t CHUNK = KC * 128;
+            constexpr uint32_t A_LBO = TA ? 16 : CHUNK, B_LBO = TB ? CHUNK : 16;
+            constexpr uint32_t A_SBO = TA ? 1024 : 512, B_SBO = TB ? 512 : 1024;
+            constexpr uint32_t A_LT = TA ? 2 : 1, B_LT = TB ? 1 : 2;
+            for (uint32_t it = 0;; ++it) {
+                const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                mbar_wait(smem_u32(&hd->full_cvt[s]), ph);
+                const int flags = hd->ring_flags[it & 15u];
+                const uint32_t chain = it >> 1, as = chain % Cfg::NSETS;
+                const bool second = (it & 1u) != 0;
+                if (!second || (flags & 4)) mbar_wait(smem_u32(&hd->tmem_empty[as]), ((chain / Cfg::NSETS) & 1u) ^ 1u);
+                if (flags & 4) {   // (always at an even stage: super-products are two stages)
+                    mbar_arrive(smem_u32(&hd->tmem_full[as]));
+                    break;
+                }
+                tc_fence_after();
+                const uint32_t d = tmem_base + as * 256;
+                const uint32_t s0 = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
+                const uint64_t dah = umma_desc(s0, A_LBO, A_SBO, A_LT), dal = umma_desc(s0 + Cfg::STACK, A_LBO, A_SBO, A_LT);
+                const uint64_t dbh = umma_desc(s0 + 2 * Cfg::STACK, B_LBO, B_SBO, B_LT);
+#pragma unroll
+                for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+                    const uint64_t ao = (uint64_t)((TA ? ks * 32 : ks * 1024) >> 4), bo = (uint64_t)((TB ? ks * 1024 : ks * 32) >> 4);
+                    mma_tf32(d, dah + ao, dbh + bo, IDESC1, (ks || second) ? 1u : 0u);   // hi x [B_hi | B_lo]
+                    mma_tf32(d, dal + ao, dbh + bo, IDESC2, 1u);                          // lo x B_hi, into the hi*hi columns
+                }
+                tc_commit(smem_u32(&hd->empty[s]));
+                if (second) tc_commit(smem_u32(&hd->tmem_full[as]));
+            }
+        }
+    } else if (warp >= 2 && warp < 2 + Cfg::CVT_WARPS) {
+        // ===== lo stacks from the raw (= hi) stacks =====
+        const unsigned tid = ((warp - 2) % Cfg::CVT_WPG) * 32 + lane;
+        for (uint32_t it = (warp - 2) / Cfg::CVT_WPG;; it += Cfg::CVT_GROUPS) {
+            const uint32_t s = it % NST, ph = (it / NST) & 1u;
+            mbar_wait(smem_u32(&hd->full_raw[s]), ph);
+            const int flags = hd->ring_flags[it & 15u];
+            if (!(flags & 4)) {
+                unsigned char* st = stages + (size_t)s * Cfg::STAGE_BYTES;
+#pragma unroll
+                for (int op = 0; op < 2; ++op) {
+                    const float4* hi = reinterpret_cast<const float4*>(st + op * 2 * Cfg::STACK);
+                    float4* lo = reinterpret_cast<float4*>(st + op * 2 * Cfg::STACK + Cfg::STACK);
+#pragma unroll 4
+                    for (int i = (int)tid; i < Cfg::STACK / 16; i += Cfg::CVT_WPG * 32) {
+                        const float4 x = hi[i];
+                        float4 l;
+                        l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                        l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                        l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                        l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                        lo[i] = l;
+                    }
+                }
+                fence_proxy_async();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&hd->full_cvt[s]));
+            if (flags & 4) break;
+        }
+    } else if (warp >= 8 && (warp - 8) < Cfg::EPI_WARPS) {
+        // ===== epilogue: warp (q, c): TMEM lanes [32q, 32q + 32) = rows 32 (q & 1) + lane of member row r = q >> 1; member column c =====
+        const unsigned q = (warp - 8) & 3, c = (warp - 8) >> 2;
+        const unsigned member = 2 * c + (q >> 1);
+        const int crow = (int)((q & 1u) * 32 + lane);
+        float acc[64];
+        uint32_t it_e = 0;
+        for (uint32_t pc = 0;; ++pc) {
+            const uint32_t as = pc % Cfg::NSETS;
+            mbar_wait(smem_u32(&hd->tmem_full[as]), (pc / Cfg::NSETS) & 1u);
+            const int f0 = hd->ring_flags[it_e & 15u];
+            if (f0 & 4) break;
+            const int flags = (f0 | hd->ring_flags[(it_e + 1) & 15u]) & 3;
+            const int4 tiles = hd->ring_tiles[it_e & 15u];
+            it_e += 2;
+            tc_fence_after();
+            const uint32_t tbase = tmem_base + ((q * 32u) << 16) + as * 256;
+#pragma unroll
+            for (int hcol = 0; hcol < 2; ++hcol) {   // (one 32-column load in flight at a time: 64 accumulators + 32 loaded values per lane)
+                uint32_t r[32];
+                tmem_ld32(tbase + 128 + c * 64 + hcol * 32, r);    // x_hi * Bc_lo
+                tmem_ld_wait();
+                if (flags & 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[hcol * 32 + j] = __uint_as_float(r[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[hcol * 32 + j] = __fadd_rn(acc[hcol * 32 + j], __uint_as_float(r[j]));
+                }
+                tmem_ld32(tbase + c * 64 + hcol * 32, r);          // x_hi * Bc_hi + x_lo * Bc_hi
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[hcol * 32 + j] = __fadd_rn(acc[hcol * 32 + j], __uint_as_float(r[j]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&hd->tmem_empty[as]));
+            if (flags & 2) {
+                const int ctile = member == 0 ? tiles.x : (member == 1 ? tiles.y : (member == 2 ? tiles.z : tiles.w));
+                if (ctile >= 0) {
+                    float* C = Ct + (size_t)ctile * BS * BS + crow;
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) C[(size_t)j * BS] = acc[j];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <bool TA, bool TB>
+bool launch_g64_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, const uint64_t* ckeys, const uint32_t* task_k,
+                     uint32_t n_ctiles, size_t n_products, float* Ct) {
+    using Cfg = G64Cfg;
+    CUtensorMap mapA, mapB, mapZa, mapZb;
+    // K-major operand (k along leaf rows): box {32 k, 64 mn};  MN-major: box {32 mn, 32 k}
+    if (!make_f32_map(&mapA, A.tiles.p, A.L, 64, 32, TA ? 64 : 32, !TA)) return false;
+    if (!make_f32_map(&mapB, B.tiles.p, B.n_ext(), 64, 32, TB ? 32 : 64, TB)) return false;
+    if (!make_f32_map(&mapZa, zero_leaf_f32_64(), 1, 64, 32, TA ? 64 : 32, !TA)) return false;
+    if (!make_f32_map(&mapZb, zero_leaf_f32_64(), 1, 64, 32, TB ? 32 : 64, TB)) return false;
+    DevBuf<uint32_t> head(n_ctiles), cnt(n_ctiles);
+    DevBuf<uint64_t> gpos((size_t)n_ctiles + 1), gbegin((size_t)n_ctiles + 1);
+    DevBuf<int4> gtiles(n_ctiles);
+    DevBuf<uint4> gops(std::max<size_t>(n_products, 1));
+    cnt.zero();
+    const unsigned gb = (n_ctiles + 255) / 256;
+    HB_LAUNCH(k_g32_heads, gb, 256, 0, ckeys, n_ctiles, head.p);
+    exclusive_scan_u32(head.p, gpos.p, n_ctiles);
+    HB_LAUNCH((k_g32_merge<false>), gb, 256, 0, ckeys, n_ctiles, head.p, gpos.p, begin, ab, task_k, cnt.p, (const uint64_t*)nullptr,
+              (int4*)nullptr, (uint4*)nullptr);
+    exclusive_scan_u32(cnt.p, gbegin.p, n_ctiles);
+    HB_LAUNCH((k_g32_merge<true>), gb, 256, 0, ckeys, n_ctiles, head.p, gpos.p, begin, ab, task_k, (uint32_t*)nullptr, gbegin.p, gtiles.p,
+              gops.p);
+    DevBuf<unsigned> counter(1);
+    counter.zero();
+    auto kfn = k_gemm_f32_g64<TA, TB>;
+    static bool configured = false;
+    if (!configured) {
+        HB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const unsigned grid = std::min<unsigned>(n_ctiles, (unsigned)engine().sm_count);
+    HB_LAUNCH(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, mapA, mapB, mapZa, mapZb, gops.p, gbegin.p, gtiles.p, gpos.p + n_ctiles, counter.p, Ct);
+    return true;
+}
+
+bool launch_g64(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, const uint64_t* ckeys,
+                const uint32_t* task_k, uint32_t n, size_t n_products, float* Ct) {
+    if (!tA && !tB) return launch_g64_inst<false, false>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
+    if (!tA && tB) return launch_g64_inst<false, true>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
+    if (tA && !tB) return launch_g64_inst<true, false>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
+    return launch_g64_inst<true, true>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
+}
+
 template <int LS, int BS, int MM, bool TA, bool TB>
 bool launch_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, uint32_t n_ctiles,
                  const uint32_t* tile_list, unsigned* counter, float* Ct) {
@@ -1143,9 +1440,11 @@ bool launch_q4(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* 
 bool launch_gemm_f32_tc(const Matrix& A, bool tA, const Matrix& B, bool tB, const uint2* ab, const uint64_t* begin,
                         uint32_t n_ctiles, const uint32_t* tile_list, unsigned* counter, float* Ct, const uint64_t* ckeys,
                         const uint32_t* task_k, size_t n_products) {
-    // 32-leaves over the whole task list: 2 x 2 groups of C tiles, M = N = 128 MMAs (HBSM_F32_MODE bit 128 keeps the single-tile kernel)
+    // 32- and 64-leaves over the whole task list: 2 x 2 groups of C tiles (HBSM_F32_MODE bit 128 keeps the single-tile kernels)
     if (A.b == 32 && !tile_list && ckeys && task_k && !(f32_mode() & (32 | 128)))
         return launch_g32(tA, tB, A, B, ab, begin, ckeys, task_k, n_ctiles, n_products, Ct);
+    if (A.b == 64 && !tile_list && ckeys && task_k && !(f32_mode() & (32 | 128)))
+        return launch_g64(tA, tB, A, B, ab, begin, ckeys, task_k, n_ctiles, n_products, Ct);
     if (!(f32_mode() & 32)) {   // leaves of 32 / 64: stacked hi/lo operands, one MMA per K-step
         if (A.b == 32) return launch_q4<32>(tA, tB, A, B, ab, begin, n_ctiles, tile_list, counter, Ct);
         if (A.b == 64) return launch_q4<64>(tA, tB, A, B, ab, begin, n_ctiles, tile_list, counter, Ct);
