@@ -188,7 +188,8 @@ int hbsm_export_tile_tasks(hbsm_handle C, int bi, int bj, size_t cap, int64_t* k
 /* leaves in ascending Morton order; norms/tiles may be NULL; cap=0 -> count */
 int hbsm_export_leaves(hbsm_handle h, size_t cap, int64_t* bi, int64_t* bj, void* norms_cached, void* tiles, size_t* n);
 int hbsm_stage_times_last(hbsm_stage_times* out);
-int hbsm_set_gemm_variant(int variant);    /* 0 = auto (TMA-tiled DMMA), 1 = generic FMA kernel (debug/parity), 2 = bulk-copy DMMA */
+int hbsm_set_gemm_variant(int variant);    /* 0 = auto (TMA-tiled DMMA / grouped tcgen05), 1 = generic FMA kernel (debug/parity), 2 = bulk-copy DMMA,
+                                            * 3 = fp32: single-C-tile tcgen05 kernels instead of the 2x2-group ones (parity) */
 
 /* ---- device-side interface (multi-GPU plumbing, device-resident benchmarks) ---- */
 /* borrowed pointers into the matrix's device block table: valid until the matrix is modified */

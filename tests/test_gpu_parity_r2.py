@@ -231,3 +231,44 @@ def test_wire_format_rejects_a_malformed_tree():
     bad[hdr:hdr + 8] = np.uint64(2 ** 62).tobytes()
     with pytest.raises(hb.HbsmError):
         HBSM(np.float64).assign_from_buffer(bytes(bad))
+
+
+@pytest.mark.parametrize("b", [32, 64])
+@pytest.mark.parametrize("tA,tB", [(0, 0), (1, 1)])
+def test_grouped_fp32_kernels_on_irregular_structure(b, tA, tB):
+    """The 2x2-group tcgen05 kernels (k_gemm_f32_g32 / g64) on a random block structure, where a group's executed
+    combinations at one k are often NOT a rectangle (three of four, diagonal pairs, single members, missing members): the
+    super-product split must leave every C tile with exactly its own k-list.  Exact multiply (structural rule, H:1873) and
+    SpAMM (per-leaf-pair prune, H:6649-6651) against the oracle, and against the single-C-tile tensor kernels (variant 3)."""
+    dtype = np.float32
+    n = 12 * b
+    ra, ca, va = G.random_block_sparse_coo(n, b, 0.45, 11, dtype)
+    rb, cb, vb = G.random_block_sparse_coo(n, b, 0.45, 12, dtype)
+    scale = np.exp(-0.002 * np.abs(ra - ca)).astype(dtype); va = va * scale     # norms that differ from tile to tile: SpAMM prunes unevenly
+    scale = np.exp(-0.002 * np.abs(rb - cb)).astype(dtype); vb = vb * scale
+    g_a, o_a = both_from_coo(b, n, n, ra, ca, va, dtype)
+    g_b, o_b = both_from_coo(b, n, n, rb, cb, vb, dtype)
+    _, _, an, _ = o_a.leaves(tiles=False); _, _, bn, _ = o_b.leaves(tiles=False)
+    tau = float(np.sqrt(np.median(an) * np.median(bn)))                          # about half of the structural products survive
+    for spamm in (False, True):
+        res = {}
+        for variant in (0, 3):
+            hb.set_gemm_variant(variant)
+            try:
+                Cg = HBSM(dtype)
+                nm, nr = (HBSM.spamm(g_a, tA, g_b, tB, Cg, tau, True) if spamm else HBSM.multiply(g_a, tA, g_b, tB, Cg))
+                assert hb.stage_times()["gemm_kernel"] == 3
+                res[variant] = (nm, nr, Cg.export_tasks(), Cg.to_dense())
+            finally:
+                hb.set_gemm_variant(0)
+        Cr, rnm, rnb, rt = po.OrcMatrix.product(o_a, tA, o_b, tB, spamm=spamm, tau=tau, want_tasks=True)
+        if spamm:
+            assert 0 < rnm < n_struct, "the prune must drop some but not all structural products"
+        else:
+            n_struct = rnm
+        for variant in (0, 3):
+            nm, nr, tasks, dense = res[variant]
+            assert (nm, nr) == (rnm, rnb)
+            assert np.array_equal(sort_tasks(tasks), sort_tasks(rt))
+            assert rel_frob(dense, Cr.to_dense()) <= 1e-5
+        assert rel_frob(res[0][3], res[3][3]) <= 3e-6
