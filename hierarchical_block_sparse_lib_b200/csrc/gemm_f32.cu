@@ -965,22 +965,27 @@ k_gemm_f32_g32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 // ---- 2 x 2 groups and their super-product lists, built from the task list on the device ----
-__global__ void k_g32_heads(const uint64_t* __restrict__ ckeys, uint32_t n, uint32_t* __restrict__ head) {
+// (tile_list, if given, is an ascending subset of C's table -- e.g. the C tiles of a sharded product that read no halo tile:
+// position i stands for tile tile_list[i], and a group only takes the members that are in the list)
+__device__ __forceinline__ uint32_t g32_tile(const uint32_t* __restrict__ tile_list, uint32_t i) { return tile_list ? tile_list[i] : i; }
+__global__ void k_g32_heads(const uint64_t* __restrict__ ckeys, const uint32_t* __restrict__ tile_list, uint32_t n, uint32_t* __restrict__ head) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    head[t] = (t == 0 || (ckeys[t - 1] >> 2) != (ckeys[t] >> 2)) ? 1u : 0u;
+    head[t] = (t == 0 || (ckeys[g32_tile(tile_list, t - 1)] >> 2) != (ckeys[g32_tile(tile_list, t)] >> 2)) ? 1u : 0u;
 }
 // four sorted k-lists -> super-products in k order (one thread per group): count pass and fill pass
 template <bool FILL>
-__global__ void k_g32_merge(const uint64_t* __restrict__ ckeys, uint32_t n, const uint32_t* __restrict__ head, const uint64_t* __restrict__ gpos,
+__global__ void k_g32_merge(const uint64_t* __restrict__ ckeys, const uint32_t* __restrict__ tile_list, uint32_t n, const uint32_t* __restrict__ head, const uint64_t* __restrict__ gpos,
                             const uint64_t* __restrict__ begin, const uint2* __restrict__ ab, const uint32_t* __restrict__ task_k,
                             uint32_t* __restrict__ cnt, const uint64_t* __restrict__ gbegin, int4* __restrict__ gtiles, uint4* __restrict__ gops) {
     const uint32_t t0 = blockIdx.x * blockDim.x + threadIdx.x;
     if (t0 >= n || !head[t0]) return;
-    const uint64_t quad = ckeys[t0] >> 2;
+    const uint64_t quad = ckeys[g32_tile(tile_list, t0)] >> 2;
     int tile[4] = {-1, -1, -1, -1};
     uint64_t p[4] = {0, 0, 0, 0}, pe[4] = {0, 0, 0, 0};
-    for (uint32_t t = t0; t < n && t < t0 + 4 && (ckeys[t] >> 2) == quad; ++t) {
+    for (uint32_t i = t0; i < n && i < t0 + 4; ++i) {
+        const uint32_t t = g32_tile(tile_list, i);
+        if ((ckeys[t] >> 2) != quad) break;
         const int m = (int)(ckeys[t] & 3ull);   // member 2c + r
         tile[m] = (int)t;
         p[m] = begin[t];
@@ -1030,7 +1035,7 @@ __global__ void k_g32_merge(const uint64_t* __restrict__ ckeys, uint32_t n, cons
 
 template <bool TA, bool TB>
 bool launch_g32_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, const uint64_t* ckeys, const uint32_t* task_k,
-                     uint32_t n_ctiles, size_t n_products, float* Ct) {
+                     const uint32_t* tile_list, uint32_t n_ctiles, size_t n_products, float* Ct) {
     using Cfg = G32Cfg;
     CUtensorMap mapA, mapB, mapZ;
     if (!make_f32_map(&mapA, A.tiles.p, A.L, 32, 32, 32, !TA)) return false;
@@ -1043,12 +1048,12 @@ bool launch_g32_inst(const Matrix& A, const Matrix& B, const uint2* ab, const ui
     DevBuf<uint4> gops(std::max<size_t>(n_products, 1));
     cnt.zero();
     const unsigned gb = (n_ctiles + 255) / 256;
-    HB_LAUNCH(k_g32_heads, gb, 256, 0, ckeys, n_ctiles, head.p);
+    HB_LAUNCH(k_g32_heads, gb, 256, 0, ckeys, tile_list, n_ctiles, head.p);
     exclusive_scan_u32(head.p, gpos.p, n_ctiles);
-    HB_LAUNCH((k_g32_merge<false>), gb, 256, 0, ckeys, n_ctiles, head.p, gpos.p, begin, ab, task_k, cnt.p, (const uint64_t*)nullptr,
+    HB_LAUNCH((k_g32_merge<false>), gb, 256, 0, ckeys, tile_list, n_ctiles, head.p, gpos.p, begin, ab, task_k, cnt.p, (const uint64_t*)nullptr,
               (int4*)nullptr, (uint4*)nullptr);
     exclusive_scan_u32(cnt.p, gbegin.p, n_ctiles);
-    HB_LAUNCH((k_g32_merge<true>), gb, 256, 0, ckeys, n_ctiles, head.p, gpos.p, begin, ab, task_k, (uint32_t*)nullptr, gbegin.p, gtiles.p,
+    HB_LAUNCH((k_g32_merge<true>), gb, 256, 0, ckeys, tile_list, n_ctiles, head.p, gpos.p, begin, ab, task_k, (uint32_t*)nullptr, gbegin.p, gtiles.p,
               gops.p);
     DevBuf<unsigned> counter(1);
     counter.zero();
@@ -1064,11 +1069,11 @@ bool launch_g32_inst(const Matrix& A, const Matrix& B, const uint2* ab, const ui
 }
 
 bool launch_g32(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, const uint64_t* ckeys,
-                const uint32_t* task_k, uint32_t n, size_t n_products, float* Ct) {
-    if (!tA && !tB) return launch_g32_inst<false, false>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
-    if (!tA && tB) return launch_g32_inst<false, true>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
-    if (tA && !tB) return launch_g32_inst<true, false>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
-    return launch_g32_inst<true, true>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
+                const uint32_t* task_k, const uint32_t* tile_list, uint32_t n, size_t n_products, float* Ct) {
+    if (!tA && !tB) return launch_g32_inst<false, false>(A, B, ab, begin, ckeys, task_k, tile_list, n, n_products, Ct);
+    if (!tA && tB) return launch_g32_inst<false, true>(A, B, ab, begin, ckeys, task_k, tile_list, n, n_products, Ct);
+    if (tA && !tB) return launch_g32_inst<true, false>(A, B, ab, begin, ckeys, task_k, tile_list, n, n_products, Ct);
+    return launch_g32_inst<true, true>(A, B, ab, begin, ckeys, task_k, tile_list, n, n_products, Ct);
 }
 
 
@@ -1326,7 +1331,7 @@ k_gemm_f32_g64(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
 template <bool TA, bool TB>
 bool launch_g64_inst(const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, const uint64_t* ckeys, const uint32_t* task_k,
-                     uint32_t n_ctiles, size_t n_products, float* Ct) {
+                     const uint32_t* tile_list, uint32_t n_ctiles, size_t n_products, float* Ct) {
     using Cfg = G64Cfg;
     CUtensorMap mapA, mapB, mapZa, mapZb;
     // K-major operand (k along leaf rows): box {32 k, 64 mn};  MN-major: box {32 mn, 32 k}
@@ -1340,12 +1345,12 @@ bool launch_g64_inst(const Matrix& A, const Matrix& B, const uint2* ab, const ui
     DevBuf<uint4> gops(std::max<size_t>(n_products, 1));
     cnt.zero();
     const unsigned gb = (n_ctiles + 255) / 256;
-    HB_LAUNCH(k_g32_heads, gb, 256, 0, ckeys, n_ctiles, head.p);
+    HB_LAUNCH(k_g32_heads, gb, 256, 0, ckeys, tile_list, n_ctiles, head.p);
     exclusive_scan_u32(head.p, gpos.p, n_ctiles);
-    HB_LAUNCH((k_g32_merge<false>), gb, 256, 0, ckeys, n_ctiles, head.p, gpos.p, begin, ab, task_k, cnt.p, (const uint64_t*)nullptr,
+    HB_LAUNCH((k_g32_merge<false>), gb, 256, 0, ckeys, tile_list, n_ctiles, head.p, gpos.p, begin, ab, task_k, cnt.p, (const uint64_t*)nullptr,
               (int4*)nullptr, (uint4*)nullptr);
     exclusive_scan_u32(cnt.p, gbegin.p, n_ctiles);
-    HB_LAUNCH((k_g32_merge<true>), gb, 256, 0, ckeys, n_ctiles, head.p, gpos.p, begin, ab, task_k, (uint32_t*)nullptr, gbegin.p, gtiles.p,
+    HB_LAUNCH((k_g32_merge<true>), gb, 256, 0, ckeys, tile_list, n_ctiles, head.p, gpos.p, begin, ab, task_k, (uint32_t*)nullptr, gbegin.p, gtiles.p,
               gops.p);
     DevBuf<unsigned> counter(1);
     counter.zero();
@@ -1361,11 +1366,11 @@ bool launch_g64_inst(const Matrix& A, const Matrix& B, const uint2* ab, const ui
 }
 
 bool launch_g64(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* ab, const uint64_t* begin, const uint64_t* ckeys,
-                const uint32_t* task_k, uint32_t n, size_t n_products, float* Ct) {
-    if (!tA && !tB) return launch_g64_inst<false, false>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
-    if (!tA && tB) return launch_g64_inst<false, true>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
-    if (tA && !tB) return launch_g64_inst<true, false>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
-    return launch_g64_inst<true, true>(A, B, ab, begin, ckeys, task_k, n, n_products, Ct);
+                const uint32_t* task_k, const uint32_t* tile_list, uint32_t n, size_t n_products, float* Ct) {
+    if (!tA && !tB) return launch_g64_inst<false, false>(A, B, ab, begin, ckeys, task_k, tile_list, n, n_products, Ct);
+    if (!tA && tB) return launch_g64_inst<false, true>(A, B, ab, begin, ckeys, task_k, tile_list, n, n_products, Ct);
+    if (tA && !tB) return launch_g64_inst<true, false>(A, B, ab, begin, ckeys, task_k, tile_list, n, n_products, Ct);
+    return launch_g64_inst<true, true>(A, B, ab, begin, ckeys, task_k, tile_list, n, n_products, Ct);
 }
 
 template <int LS, int BS, int MM, bool TA, bool TB>
@@ -1440,12 +1445,13 @@ bool launch_q4(bool tA, bool tB, const Matrix& A, const Matrix& B, const uint2* 
 bool launch_gemm_f32_tc(const Matrix& A, bool tA, const Matrix& B, bool tB, const uint2* ab, const uint64_t* begin,
                         uint32_t n_ctiles, const uint32_t* tile_list, unsigned* counter, float* Ct, const uint64_t* ckeys,
                         const uint32_t* task_k, size_t n_products) {
-    // 32- and 64-leaves over the whole task list: 2 x 2 groups of C tiles (HBSM_F32_MODE bit 128 keeps the single-tile kernels)
+    // 32- and 64-leaves: 2 x 2 groups of C tiles, over the whole task list or a tile list (HBSM_F32_MODE bit 128 / variant 3 keep
+    // the single-tile kernels)
     const bool single_tile = (f32_mode() & (32 | 128)) != 0 || shared().gemm_variant.load() == 3;   // variant 3: parity hook of the tests
-    if (A.b == 32 && !tile_list && ckeys && task_k && !single_tile)
-        return launch_g32(tA, tB, A, B, ab, begin, ckeys, task_k, n_ctiles, n_products, Ct);
-    if (A.b == 64 && !tile_list && ckeys && task_k && !single_tile)
-        return launch_g64(tA, tB, A, B, ab, begin, ckeys, task_k, n_ctiles, n_products, Ct);
+    if (A.b == 32 && ckeys && task_k && !single_tile)
+        return launch_g32(tA, tB, A, B, ab, begin, ckeys, task_k, tile_list, n_ctiles, n_products, Ct);
+    if (A.b == 64 && ckeys && task_k && !single_tile)
+        return launch_g64(tA, tB, A, B, ab, begin, ckeys, task_k, tile_list, n_ctiles, n_products, Ct);
     if (!(f32_mode() & 32)) {   // leaves of 32 / 64: stacked hi/lo operands, one MMA per K-step
         if (A.b == 32) return launch_q4<32>(tA, tB, A, B, ab, begin, n_ctiles, tile_list, counter, Ct);
         if (A.b == 64) return launch_q4<64>(tA, tB, A, B, ab, begin, n_ctiles, tile_list, counter, Ct);

@@ -20,7 +20,8 @@ H = hb.HierarchicalBlockSparseMatrix
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr); dist.init_process_group("nccl", device_id=torch.device("cuda", lr)); hb.init(lr); S.comm_init()
 assert S.comm_info()[:2] == (rank, world)
-n, b, lam = 4096, 64, 0.02
+DT = np.float32 if os.environ.get("HBSM_TEST_DTYPE") == "float32" else np.float64
+n, b, lam = (2048, 32, 0.04) if DT == np.float32 else (4096, 64, 0.02)     # fp32: the grouped tcgen05 kernels on own/halo tile lists
 W = G.decay_width(lam); g = n // b
 lo, hi = S.slab_bounds(g, world, rank)
 if os.environ.get("HBSM_TEST_BALANCED") == "1":     # uneven slabs (what balanced_bounds produces for a clipped band)
@@ -28,18 +29,18 @@ if os.environ.get("HBSM_TEST_BALANCED") == "1":     # uneven slabs (what balance
     lo, hi = bounds[rank], bounds[rank + 1]
 for (tA, tB, spamm, tau) in [(0, 0, True, 1e-6), (0, 0, False, 0.0), (0, 1, True, 1e-4), (1, 0, True, 1e-4)]:
     # full matrices (every rank, for the check) and the slabs (what a rank really holds)
-    Af = H(np.float64, b); Af.generate_decay(n, lam, W, 1); Af.update_internal_info()
-    Bf = H(np.float64, b); Bf.generate_decay(n, lam, W, 2); Bf.update_internal_info()
+    Af = H(DT, b); Af.generate_decay(n, lam, W, 1); Af.update_internal_info()
+    Bf = H(DT, b); Bf.generate_decay(n, lam, W, 2); Bf.update_internal_info()
     def slab(Mf, by_col):
         bi, bj, nr, t = Mf.export_leaves()
         line = bj if by_col else bi
         m = (line >= lo) & (line < hi)
-        X = H(np.float64, b); X.resize(n, n); X.assign_tiles(bi[m], bj[m], t[m]); X.update_internal_info(); return X
+        X = H(DT, b); X.resize(n, n); X.assign_tiles(bi[m], bj[m], t[m]); X.update_internal_info(); return X
     Al = slab(Af, bool(tA)); Bl = slab(Bf, bool(tB))
     S.publish(Bl)
     Cl, nm, nb = S.sharded_product(Al, tA, Bl, tB, spamm, tau)
     wts = S.row_weights(Al, tA, Bl, tB, spamm, tau)
-    Cf = H(np.float64)
+    Cf = H(DT)
     nmf, nbf = (H.spamm(Af, tA, Bf, tB, Cf, tau, True) if spamm else H.multiply(Af, tA, Bf, tB, Cf))
     tot = torch.tensor([nm, nb], dtype=torch.int64, device="cuda"); dist.all_reduce(tot)
     assert (int(tot[0]), int(tot[1])) == (nmf, nbf), (tot.tolist(), nmf, nbf)
@@ -51,14 +52,18 @@ for (tA, tB, spamm, tau) in [(0, 0, True, 1e-6), (0, 0, False, 0.0), (0, 1, True
     assert np.array_equal(key(tl), key(mine)), "per-rank executed set differs from the single-GPU set restricted to the slab"
     bi, bj, _, t = Cl.export_leaves(norms=False); fbi, fbj, _, ft = Cf.export_leaves(norms=False)
     m = (fbi >= lo) & (fbi < hi)
-    assert np.array_equal(bi, fbi[m]) and np.array_equal(bj, fbj[m]) and np.array_equal(t, ft[m])   # same kernel, same k order: bitwise
+    assert np.array_equal(bi, fbi[m]) and np.array_equal(bj, fbj[m])
+    if DT == np.float64:
+        assert np.array_equal(t, ft[m])   # same kernel, same k order: bitwise
+    else:   # fp32: a 2x2 group that straddles the own / halo split is chained differently in TMEM -- same sums to rounding
+        assert np.linalg.norm(t.astype(np.float64) - ft[m]) <= 2e-6 * np.linalg.norm(ft[m])
 if rank == 0: print("sharded ok world=%%d" %% world)
 S.comm_finalize(); dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("slabs", ["equal", "balanced"])
-def test_sharded_matches_single_gpu(tmp_path, slabs):
+@pytest.mark.parametrize("slabs,dtype", [("equal", "float64"), ("balanced", "float64"), ("equal", "float32")])
+def test_sharded_matches_single_gpu(tmp_path, slabs, dtype):
     import torch
     ngpu = torch.cuda.device_count()
     world = 1
@@ -70,7 +75,7 @@ def test_sharded_matches_single_gpu(tmp_path, slabs):
     script.write_text(SCRIPT % {"root": ROOT})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)]
-    env = dict(os.environ, HBSM_TEST_BALANCED="1" if slabs == "balanced" else "0")
+    env = dict(os.environ, HBSM_TEST_BALANCED="1" if slabs == "balanced" else "0", HBSM_TEST_DTYPE=dtype)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "sharded ok" in r.stdout
