@@ -553,6 +553,8 @@ def _e2e_sharded(hb, H, A, B, w, steps, local_rank):
         sm = v.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         if i > 1:
             times.append(float(mx[0]))
+            per_rank_ms = [None] * dist.get_world_size()
+            dist.all_gather_object(per_rank_ms, round(1e3 * dt, 2))
             phases = {}
             prev = t0
             for name, t in marks:
@@ -563,6 +565,7 @@ def _e2e_sharded(hb, H, A, B, w, steps, local_rank):
         nm_tot = int(sm[1]); h2d_tot = int(sm[2]); d2h = int(sm[3])
     ms = 1e3 * float(np.mean(times))
     return {"value": 2.0 * b ** 3 * nm_tot / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ms,
-            "h2d_bytes_per_step": h2d_tot, "d2h_bytes_per_step": d2h, "rank0_phases": phases,
+            "h2d_bytes_per_step": h2d_tot, "d2h_bytes_per_step": d2h, "ms_per_step_all": [round(1e3 * t, 2) for t in times],
+            "last_step_ms_per_rank": per_rank_ms, "rank0_phases": phases,
             "path": "per rank: hbsm_assign_tiles(A_r,B_r from pinned host) + hbsm_update_norms + hbsm_publish + hbsm_sharded_product "
                     "(NCCL halo exchange inside the library) + hbsm_export_leaves(C_r to pinned host); max over ranks"}
