@@ -2,6 +2,7 @@
 // HBM-bound structure operations (add, transpose, upper triangle, rescale, copy, symmetric expansion).
 // Reference behaviour reproduced here is cited as H:<line> of source/HierarchicalBlockSparseMatrix.h.
 #include "matrix.cuh"
+#include <chrono>
 #include <cmath>
 
 namespace hbsm_b200 {
@@ -987,12 +988,35 @@ void assign_tiles_host(Matrix& A, size_t n_tiles, const int* bi, const int* bj, 
             throw_ref("Error in HierarchicalBlockSparseMatrix<Treal>::assign_from_vectors: index outside matrix boundaries.");
         hk[i] = morton_encode((uint32_t)bi[i], (uint32_t)bj[i]);
     }
+    static const bool trace = getenv("HBSM_TRACE_ASSIGN") != nullptr;   // diagnosis: where an upload spends its time
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    if (trace) {
+        cudaMemPool_t pool;
+        uint64_t reserved = 0, used = 0, thr = 0;
+        cudaDeviceGetMemPool(&pool, engine().device);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        fprintf(stderr, "[pool before assign] reserved %.2f GB used %.2f GB release threshold %s\n", reserved / 1e9, used / 1e9,
+                thr == UINT64_MAX ? "max" : "NOT max");
+    }
+    const auto t0 = now();
     DevBuf<uint64_t> dk(n_tiles);
     dk.upload(hk.data(), n_tiles);
     DevBuf<char> dt(n_tiles * A.tile_bytes());
+    if (trace) sync_stream();
+    const auto t1 = now();
     HB_CUDA(cudaMemcpyAsync(dt.p, tiles, n_tiles * A.tile_bytes(), cudaMemcpyHostToDevice, engine().stream));
+    if (trace) sync_stream();
+    const auto t2 = now();
     assign_tiles_device(A, n_tiles, dk.p, dt.p, nullptr);
     sync_stream();
+    if (trace)
+        fprintf(stderr, "[assign_tiles %zu tiles] alloc %.2f ms | H2D %.2f ms (%.1f GB/s) | sort + permute + table %.2f ms\n", n_tiles, ms(t0, t1),
+                ms(t1, t2), n_tiles * A.tile_bytes() / ms(t1, t2) / 1e6, ms(t2, now()));
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -522,21 +522,31 @@ def _e2e_sharded(hb, H, A, B, w, steps, local_rank):
     nm_tot = 0
     d2h = 0
     phases = None
+    phases_all = []
     WARM = 4                        # untimed passes: the stream-ordered pool, the halo tail and NCCL's buffers reach their steady state
     for i in range(steps + WARM):   # (measured at 4 GPUs: 186, 102, 73 ms for passes 3-5 with only two warm-ups)
-        torch.cuda.synchronize(); dist.barrier()
+        # (barrier() only ENQUEUES its NCCL kernel: without the second synchronize the clock starts while that kernel still waits
+        # for the slowest rank, and the first call that happens to wait for the device is billed the skew -- 60-340 ms at 2 GPUs)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         marks = []
 
         def mark(name):
             marks.append((name, time.perf_counter()))
 
-        # B first: its norms and published table are what the peers wait for
-        B2 = H(np.float64, b); B2.resize(n, n); B2.assign_tiles(bbi, bbj, bt.numpy()); mark("upload_B")
-        B2.update_internal_info(); mark("norms_B")
-        publish(B2); mark("publish_B")                      # inside the e2e region: B2 is a new matrix every step
-        A2 = H(np.float64, b); A2.resize(n, n); A2.assign_tiles(abi, abj, at.numpy()); mark("upload_A")
-        A2.update_internal_info(); mark("norms_A")
+        if os.environ.get("HBSM_E2E_ORDER", "BA") == "AB":
+            A2 = H(np.float64, b); A2.resize(n, n); A2.assign_tiles(abi, abj, at.numpy()); mark("upload_A")
+            A2.update_internal_info(); mark("norms_A")
+            B2 = H(np.float64, b); B2.resize(n, n); B2.assign_tiles(bbi, bbj, bt.numpy()); mark("upload_B")
+            B2.update_internal_info(); mark("norms_B")
+            publish(B2); mark("publish_B")
+        else:
+            # B first: its norms and published table are what the peers wait for
+            B2 = H(np.float64, b); B2.resize(n, n); B2.assign_tiles(bbi, bbj, bt.numpy()); mark("upload_B")
+            B2.update_internal_info(); mark("norms_B")
+            publish(B2); mark("publish_B")                      # inside the e2e region: B2 is a new matrix every step
+            A2 = H(np.float64, b); A2.resize(n, n); A2.assign_tiles(abi, abj, at.numpy()); mark("upload_A")
+            A2.update_internal_info(); mark("norms_A")
         t_up = time.perf_counter() - t0
         Cm, nm, nr = sharded_product(A2, False, B2, False, True, tau); mark("sharded_product")
         t_prod = time.perf_counter() - t0 - t_up
@@ -548,7 +558,7 @@ def _e2e_sharded(hb, H, A, B, w, steps, local_rank):
                                                     None, C.c_void_p(out.data_ptr()), C.byref(m)))
         torch.cuda.synchronize()
         t_local = time.perf_counter() - t0          # this rank's own work (uploads wait for nobody; the product waits for the peers' thresholds / tiles)
-        dist.barrier()
+        dist.barrier(); torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         del A2, B2, Cm
         v = torch.tensor([dt, float(nm), float(h2d), float(nr * b * b * 8 + 16 * nr)], dtype=torch.float64, device="cuda")
@@ -564,11 +574,12 @@ def _e2e_sharded(hb, H, A, B, w, steps, local_rank):
                 phases[name + "_ms"] = round(1e3 * (t - prev), 3); prev = t
             phases["download_C_ms"] = round(1e3 * (t0 + dt - prev), 3)
             phases["engine_stage_ms"] = {k: round(v, 3) for k, v in hb.stage_times().items() if k.endswith("_ms")}
+            phases_all.append({k: v for k, v in phases.items() if k.endswith("_ms") and not isinstance(v, dict)})
             phases["shard_stats"] = shard_stats()
         nm_tot = int(sm[1]); h2d_tot = int(sm[2]); d2h = int(sm[3])
     ms = 1e3 * float(np.mean(times))
     return {"value": 2.0 * b ** 3 * nm_tot / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ms,
             "h2d_bytes_per_step": h2d_tot, "d2h_bytes_per_step": d2h, "ms_per_step_all": [round(1e3 * t, 2) for t in times],
-            "last_step_ms_per_rank": per_rank_ms, "rank0_phases": phases,
+            "last_step_ms_per_rank": per_rank_ms, "rank0_phases": phases, "rank0_phases_all": phases_all,
             "path": "per rank: hbsm_assign_tiles(A_r,B_r from pinned host) + hbsm_update_norms + hbsm_publish + hbsm_sharded_product "
                     "(NCCL halo exchange inside the library) + hbsm_export_leaves(C_r to pinned host); max over ranks"}
