@@ -62,6 +62,7 @@ int hbsm_finalize(void) {
         Engine& e = engine();
         if (!e.ready) return;
         HB_CUDA(cudaStreamSynchronize(e.stream));
+        e.cache.drop_all();   // large blocks kept for exact-size reuse go back to the driver
     });
 }
 

@@ -20,9 +20,12 @@ Engine& engine() {
     return e;
 }
 
+
 Engine::~Engine() {   // thread exit: errors are ignored (at process exit the runtime may already be gone)
     if (!ready) return;
-    if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+    if (stream) cudaStreamSynchronize(stream);
+    cache.drop_all();
+    if (stream) cudaStreamDestroy(stream);
     if (stream2) { cudaStreamSynchronize(stream2); cudaStreamDestroy(stream2); }
     if (mailbox) cudaFreeHost(mailbox);
     ready = false; stream = nullptr; stream2 = nullptr; mailbox = nullptr;   // late frees fall back to the default stream

@@ -355,10 +355,12 @@ def sharded_symm_square_spamm(F_loc, tau):
     return sharded_product(F_loc, False, F_loc, False, tau is not None, 0.0 if tau is None else tau, upper_only=True)
 
 
-def bind_near_gpu(local_rank):
-    """Pin this rank's host threads to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function) BEFORE pinned
-    host buffers are allocated: first touch then places them on the GPU's NUMA node, and 8 ranks stop sharing one socket's
-    memory controllers for their PCIe traffic.  Returns the cpulist used or None."""
+def bind_near_gpu(local_rank, local_world=1):
+    """Pin this rank's host threads to its own share of the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI
+    function, split evenly among the ranks of the box) BEFORE pinned host buffers, NCCL's proxy threads and the engine's
+    streams exist: first touch then places pinned memory on the GPU's NUMA node, and the ranks' launch threads stop
+    migrating over each other's cores (the step of a sharded product is ~50 short launches and four host reads: host jitter
+    on ONE rank delays every rank at the next all-gather).  Returns the cpu list used or None."""
     try:
         p = torch.cuda.get_device_properties(local_rank)
         bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
@@ -369,11 +371,13 @@ def bind_near_gpu(local_rank):
                 a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
             elif part:
                 cpus.add(int(part))
-        allowed = os.sched_getaffinity(0)
-        use = cpus & allowed
+        use = sorted(cpus & os.sched_getaffinity(0))
+        if local_world > 1 and len(use) >= 2 * local_world:
+            per = len(use) // local_world
+            use = use[local_rank * per:(local_rank + 1) * per]
         if use:
-            os.sched_setaffinity(0, use)
-            return txt
+            os.sched_setaffinity(0, set(use))
+            return "%d-%d" % (use[0], use[-1]) if use == list(range(use[0], use[-1] + 1)) else ",".join(map(str, use))
     except Exception:
         pass
     return None
@@ -393,7 +397,9 @@ def bench_main(args, w, bm):
         raise SystemExit("bench.py --gpus N>1 runs the fp64 SpAMM NN cases (headline, --config 2, --config 4)")
     world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"]); local_rank = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local_rank)
-    cpulist = bind_near_gpu(local_rank)
+    # CPUs next to the GPU; HBSM_BIND_CORES=split additionally gives every rank its own share of them (untested at scale:
+    # at 2 GPUs it changed nothing, 17.73 vs 17.70 ms)
+    cpulist = bind_near_gpu(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)) if os.environ.get("HBSM_BIND_CORES") == "split" else 1)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hb.init(local_rank)
     comm_init()
