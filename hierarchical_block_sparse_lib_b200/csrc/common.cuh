@@ -52,20 +52,31 @@ Shared& shared();
 struct BlockCache {
     static constexpr size_t MIN_BYTES = (size_t)64 << 20;
     static constexpr size_t MAX_BLOCKS = 12;
+    static constexpr size_t MAX_TOTAL = (size_t)32 << 30;   // never hold more than this back from the pool (180 GB devices)
     std::vector<std::pair<size_t, void*>> blocks;   // oldest first
+    size_t total = 0;
     void* take(size_t bytes) {
         for (size_t i = blocks.size(); i-- > 0;)
-            if (blocks[i].first == bytes) { void* p = blocks[i].second; blocks.erase(blocks.begin() + (long)i); return p; }
+            if (blocks[i].first == bytes) {
+                void* p = blocks[i].second;
+                blocks.erase(blocks.begin() + (long)i);
+                total -= bytes;
+                return p;
+            }
         return nullptr;
     }
-    void* give(size_t bytes, void* p) {   // returns the block to hand to the pool instead (the evicted one), or null
+    // keeps the block unless it is too large to keep; fills `evicted` with the blocks the caller must hand to the pool
+    void give(size_t bytes, void* p, std::vector<void*>& evicted) {
+        if (bytes > MAX_TOTAL) { evicted.push_back(p); return; }
         blocks.emplace_back(bytes, p);
-        if (blocks.size() <= MAX_BLOCKS) return nullptr;
-        void* old = blocks.front().second;
-        blocks.erase(blocks.begin());
-        return old;
+        total += bytes;
+        while (blocks.size() > MAX_BLOCKS || total > MAX_TOTAL) {
+            total -= blocks.front().first;
+            evicted.push_back(blocks.front().second);
+            blocks.erase(blocks.begin());
+        }
     }
-    void drop_all() { for (auto& b : blocks) cudaFree(b.second); blocks.clear(); }   // (errors ignored: at process exit the runtime may be gone)
+    void drop_all() { for (auto& b : blocks) cudaFree(b.second); blocks.clear(); total = 0; }   // (errors ignored: at process exit the runtime may be gone)
 };
 
 // Per host thread: its own stream, mailbox, pending product and stage times.  Two threads can run products concurrently on
@@ -121,14 +132,26 @@ struct DevBuf {
         ensure_engine();
         const size_t bytes = std::max<size_t>(count * sizeof(T), 256);
         if (bytes >= BlockCache::MIN_BYTES && (p = (T*)engine().cache.take(bytes)) != nullptr) return;
-        HB_CUDA(cudaMallocAsync((void**)&p, bytes, engine().stream));
+        cudaError_t err = cudaMallocAsync((void**)&p, bytes, engine().stream);
+        if (err == cudaErrorMemoryAllocation && !engine().cache.blocks.empty()) {   // the cache must never be the reason for an OOM
+            cudaGetLastError();
+            cudaStreamSynchronize(engine().stream);
+            engine().cache.drop_all();
+            err = cudaMallocAsync((void**)&p, bytes, engine().stream);
+        }
+        if (err != cudaSuccess) { p = nullptr; n = 0; }
+        HB_CUDA(err);
     }
     void release() {
         if (p) {
             const size_t bytes = std::max<size_t>(n * sizeof(T), 256);
-            void* out = p;
-            if (bytes >= BlockCache::MIN_BYTES && engine().ready) out = engine().cache.give(bytes, p);
-            if (out) cudaFreeAsync(out, engine().stream);
+            if (bytes >= BlockCache::MIN_BYTES && engine().ready) {
+                std::vector<void*> evicted;
+                engine().cache.give(bytes, p, evicted);
+                for (void* q : evicted) cudaFreeAsync(q, engine().stream);
+            } else {
+                cudaFreeAsync(p, engine().stream);
+            }
             p = nullptr;
         }
         n = 0;
