@@ -1,21 +1,28 @@
-"""Multi-GPU multiply / SpAMM: one process per GPU, C sharded by top-level quadtree block rows.
+"""Multi-GPU multiply / SpAMM: one process per GPU, C sharded by block rows.
 
-Rank r owns the contiguous slab of block rows  [r*g/G, (r+1)*g/G)  (g = block-grid side, G = world size; for
-G in {2,4,8} these are exactly the top-level quadtree block rows).  It holds the tiles of op(A) whose C-row index
-ci lies in its slab and the tiles of op(B) whose contraction index k lies in its slab.  One product is
+The product path lives in the library: csrc/sharded.cu behind the C ABI (hbsm_comm_init / hbsm_publish /
+hbsm_sharded_product / hbsm_sharded_row_weights / hbsm_shard_rows_balanced; NCCL is loaded by libhbsm_b200.so itself).
+This module is
+  * the thin ctypes caller of those entry points (comm_init, publish, sharded_product, row_weights, ...), which only uses
+    torch.distributed to hand the 128-byte NCCL id to the peers;
+  * the protocol MODEL as device-agnostic torch ops (request_thresholds, publish_table, exchange_b_allgather, and the
+    self-contained three-round exchange_b), which tests/test_sharded_cpu.py runs over `gloo` at world 2 and 4 against the
+    oracle's single-process executed-product set;
+  * bench.py's N > 1 arm (bench_main).
 
-  1. request   every rank computes, per k, the largest leaf norm^2 among its op(A) tiles (ci,k)   -> all_to_all
-  2. select    the owner of row k keeps the op(B) tiles (k,cj) that can survive the SpAMM test against that
-               maximum, fl(max_na * nb) > fl(tau*tau) (monotone rounding => exactly the tiles that at least one
-               executed product of the requester touches; exact multiply: every tile of a requested row)
-  3. exchange  keys, leaf norms and tiles of the selected op(B) tiles                                -> all_to_all
-  4. multiply  the single-GPU engine call (task list + leaf GEMMs) on (A_r, received B tiles) -> C_r
+Rank r owns a contiguous slab of block rows (equal slabs = the top-level quadtree block rows for world in {2,4,8}, or
+boundaries balanced on the per-row product counts).  It holds the tiles of op(A) whose C-row index ci lies in its slab and the
+tiles of op(B) whose contraction index k lies in its slab.  One product is
+
+  1. request   every rank computes, per k, the largest leaf norm^2 among its op(A) tiles (ci,k); the thresholds are all-gathered
+  2. select    requester and owner evaluate the same predicate on the published (key, norm^2) table of op(B):
+               fl(max_na * nb) > fl(tau*tau) (monotone rounding => exactly the tiles that at least one executed product of the
+               requester touches; exact multiply: every tile of a requested row) -- no masks, no counts travel
+  3. exchange  the selected op(B) tiles, straight into the halo tail behind the requester's own tiles
+  4. multiply  task list + leaf GEMMs on (A_r, own + halo B tiles) -> C_r; the GEMMs that need no halo tile overlap step 3
 
 There is NO reduction: each rank owns whole block rows of C.  The executed-product set is the disjoint union of
 the per-rank sets and is bit-identical to the single-GPU one because the predicate is per leaf pair.
-
-The planning (steps 1-2) is written with device-agnostic torch ops, so the same code runs on CPU tensors over
-`gloo` (tests/test_sharded_cpu.py, world_size 2) and on CUDA tensors over NCCL/NVLink.  Only step 4 needs the GPU.
 """
 import ctypes as C
 import os
